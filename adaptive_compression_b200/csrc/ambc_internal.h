@@ -1,0 +1,21 @@
+// ambc_internal.h -- host-side plumbing shared by the .cu files of libambc.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <cuda_runtime.h>
+#include "../../include/ambc.h"
+
+using std::min;
+using std::max;
+
+int ambc_fail(int code, const char *fmt, ...);
+void ambc_count_launch();
+
+#define CUDA_TRY(expr)                                                                                    \
+    do {                                                                                                  \
+        cudaError_t e__ = (expr);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            return ambc_fail(AMBC_E_CUDA, "%s:%d: %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+    } while (0)

@@ -1,0 +1,687 @@
+// chunk_codec.cuh -- per-chunk device code: should_use gates and the four native encoders.
+// One CTA (AMBC_BLOCK threads) works on one chunk staged in shared memory.  Every function
+// here is block-collective: all threads of the CTA must call it with the same arguments.
+//
+// Reference behaviour restated (file:line relative to the reference repo):
+//   RLE        compression_methods.py:78-114, gate :154-180
+//   Dictionary compression_methods.py:195-234 + 283-313 (earliest-longest greedy LZ77), gate :315-343
+//   Huffman    compression_methods.py:354-405 + 472-549 ((weight, leader) tie-break), gate :551-574
+//   Delta      compression_methods.py:585-608, gate :640-667
+#pragma once
+#include "common.cuh"
+
+struct ChunkCtx {
+    uint8_t *sd;       // chunk bytes, 16-byte aligned, followed by AMBC_PAD zero bytes
+    int n;             // chunk length (<= AMBC_NMAX)
+    uint8_t *pay;      // payload buffer, 16-byte aligned
+    int pcap;          // payload capacity; longer payloads are counted but not stored
+    uint16_t *sorted;  // n+2 entries (LZ bucket-sorted positions); reused as Huffman bit words
+    uint16_t *bstart;  // AMBC_NBUCKET+1 bucket starts
+    uint8_t *X;        // 16 KiB + 64 scratch (LZ counters / trigram set / block exits / Huffman nodes)
+    uint8_t *mlen;     // n match lengths (0 = literal)
+    uint16_t *mpos;    // n match positions
+    uint32_t *hist;    // 256 byte counts
+    uint32_t *bmask;   // run-boundary bitmap, ceil(n/32) words
+    uint32_t *reach;   // token-start bitmap, ceil(n/32) words
+    uint8_t *estart;   // per 32-block chain entry offset
+    int *red;          // 16 ints of reduction scratch (8-byte aligned)
+};
+
+// shared-memory bytes of a ChunkCtx for chunk size N and payload capacity pcap
+__host__ __device__ inline size_t r16(size_t x) { return (x + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t chunkctx_smem_bytes(int N, int pcap)
+{
+    size_t sorted_b = 2 * (size_t)(N + 2);
+    if (sorted_b < (size_t)pcap + 16) sorted_b = (size_t)pcap + 16;
+    size_t nb = (size_t)(N + 31) / 32;
+    return r16((size_t)N) + AMBC_PAD          // sd
+           + r16((size_t)pcap) + 16           // pay
+           + r16(sorted_b)                    // sorted
+           + r16(2 * (AMBC_NBUCKET + 1))      // bstart
+           + 16384 + 64                       // X
+           + r16((size_t)N)                   // mlen
+           + r16(2 * (size_t)N)               // mpos
+           + 1024                             // hist
+           + r16(nb * 4) * 2                  // bmask, reach
+           + r16(nb)                          // estart
+           + 64;                              // red
+}
+
+__device__ inline void chunkctx_carve(ChunkCtx &c, uint8_t *base, int N, int pcap)
+{
+    size_t sorted_b = 2 * (size_t)(N + 2);
+    if (sorted_b < (size_t)pcap + 16) sorted_b = (size_t)pcap + 16;
+    size_t nb = (size_t)(N + 31) / 32;
+    uint8_t *p = base;
+    c.sd = p; p += r16((size_t)N) + AMBC_PAD;
+    c.pay = p; p += r16((size_t)pcap) + 16;
+    c.sorted = (uint16_t *)p; p += r16(sorted_b);
+    c.bstart = (uint16_t *)p; p += r16(2 * (AMBC_NBUCKET + 1));
+    c.X = p; p += 16384 + 64;
+    c.mlen = p; p += r16((size_t)N);
+    c.mpos = (uint16_t *)p; p += r16(2 * (size_t)N);
+    c.hist = (uint32_t *)p; p += 1024;
+    c.bmask = (uint32_t *)p; p += r16(nb * 4);
+    c.reach = (uint32_t *)p; p += r16(nb * 4);
+    c.estart = p; p += r16(nb);
+    c.red = (int *)p;
+    c.pcap = pcap;
+    c.n = 0;
+}
+
+// Stage chunk [src, src+n) in c.sd and zero the pad.  Ends with __syncthreads().
+__device__ inline void chunk_load(ChunkCtx &c, const uint8_t *__restrict__ src, int n)
+{
+    c.n = n;
+    copy_g2s(c.sd, src, n);
+    int padend = (int)r16((size_t)n) + AMBC_PAD;
+    for (int i = n + threadIdx.x; i < padend; i += AMBC_BLOCK) c.sd[i] = 0;
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------
+// features: histogram, run-boundary bitmap, sampled gates, distinct trigrams, entropy
+// ---------------------------------------------------------------------------------------
+struct ChunkFeatures {
+    int rep;        // sampled adjacent-equal count      (compression_methods.py:172-175)
+    int small;      // sampled |delta| < 32 count        (:658-662)
+    int distinct3;  // distinct trigrams among the first min(n-3, 1000) positions (:333-336)
+    int K;          // distinct byte values
+    int rle_pairs;  // (byte,count) pairs RLE would emit
+    double H;       // entropy, parallel sum (order-insensitive to ~1e-13)
+};
+
+// extract byte j (compile-time after unrolling) of a 32-byte slice held in two uint4
+__device__ __forceinline__ uint32_t slice_byte(const uint4 &a, const uint4 &b, int j)
+{
+    uint32_t w;
+    switch (j >> 2) {
+    case 0: w = a.x; break; case 1: w = a.y; break; case 2: w = a.z; break; case 3: w = a.w; break;
+    case 4: w = b.x; break; case 5: w = b.y; break; case 6: w = b.z; break; default: w = b.w; break;
+    }
+    return (w >> ((j & 3) * 8)) & 0xFF;
+}
+
+__device__ inline void chunk_features(ChunkCtx &c, ChunkFeatures &f)
+{
+    const int n = c.n, tid = threadIdx.x;
+    const int nsl = (n + 31) >> 5;
+    uint32_t *tri = (uint32_t *)c.X; // 2048-slot open-addressing set
+    for (int i = tid; i < 256; i += AMBC_BLOCK) c.hist[i] = 0;
+    for (int i = tid; i < 2048 / 4; i += AMBC_BLOCK) ((uint4 *)tri)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+
+    // histogram (run-aggregated shared atomics) + run-boundary bitmap
+    for (int s = tid; s < nsl; s += AMBC_BLOCK) {
+        const uint4 a = *(const uint4 *)(c.sd + 32 * s);
+        const uint4 b = *(const uint4 *)(c.sd + 32 * s + 16);
+        const int m = min(32, n - 32 * s);
+        uint32_t prev = s ? c.sd[32 * s - 1] : 0x100u; // 0x100: never equal -> boundary at position 0
+        uint32_t mask = 0, cur = 0, cnt = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            if (j < m) {
+                uint32_t v = slice_byte(a, b, j);
+                if (v != prev) mask |= 1u << j;
+                if (j == 0) { cur = v; cnt = 1; }
+                else if (v == cur) cnt++;
+                else { atomicAdd(&c.hist[cur], cnt); cur = v; cnt = 1; }
+                prev = v;
+            }
+        }
+        atomicAdd(&c.hist[cur], cnt);
+        c.bmask[s] = mask;
+    }
+
+    // sampled gates: RLE (:165-180) and Delta (:651-667) share the sample positions
+    int rep = 0, small = 0;
+    if (n >= 4) {
+        const int ss = min(1000, n);
+        const int step = max(1, n / ss);
+        for (int i = tid * step; i < n - 1; i += AMBC_BLOCK * step) {
+            int x = c.sd[i], y = c.sd[i + 1];
+            rep += (x == y);
+            small += (abs(x - y) < 32);
+        }
+    }
+    // distinct trigrams (:326-343)
+    int ins = 0;
+    if (n >= 100) {
+        const int cnt3 = min(n - 3, min(1000, n));
+        for (int i = tid; i < cnt3; i += AMBC_BLOCK) {
+            uint32_t t = lds_u32u(c.sd + i) & 0xFFFFFFu;
+            uint32_t key = t + 1, h = (t * 2654435761u) >> 21;
+            for (;;) {
+                uint32_t old = atomicCAS(&tri[h], 0u, key);
+                if (old == 0u) { ins++; break; }
+                if (old == key) break;
+                h = (h + 1) & 2047;
+            }
+        }
+    }
+    f.rep = block_sum(rep, c.red);
+    f.small = block_sum(small, c.red);
+    f.distinct3 = block_sum(ins, c.red); // also orders hist / bmask writes before the reads below
+
+    // RLE pair count: a run of R bytes -> ceil(R/255) pairs (:95-109)
+    int pairs = 0;
+    for (int s = tid; s < nsl; s += AMBC_BLOCK) {
+        uint32_t w = c.bmask[s];
+        while (w) {
+            int bit = __ffs(w) - 1;
+            w &= w - 1;
+            int p = 32 * s + bit, q;
+            if (w) q = 32 * s + __ffs(w) - 1;
+            else {
+                q = n;
+                for (int s2 = s + 1; s2 < nsl; s2++) {
+                    uint32_t w2 = c.bmask[s2];
+                    if (w2) { q = 32 * s2 + __ffs(w2) - 1; break; }
+                }
+            }
+            pairs += (q - p + 254) / 255;
+        }
+    }
+    f.rle_pairs = block_sum(pairs, c.red);
+
+    // entropy (:566-574), tree sum; the caller resolves near-threshold cases in order
+    double hsum = 0.0;
+    int k = 0;
+    for (int b = tid; b < 256; b += AMBC_BLOCK) {
+        uint32_t cnt = c.hist[b];
+        if (cnt) {
+            k++;
+            double p = __ddiv_rn((double)cnt, (double)n);
+            hsum -= p * log2(p);
+        }
+    }
+    f.K = block_sum(k, c.red);
+    f.H = block_sum_f64(hsum, (volatile double *)c.red);
+}
+
+// first-occurrence order of the byte values (Counter insertion order, :368-370 / :566).
+// order[r] = r-th distinct byte value; firstpos scratch = 256 uint32.  Collective.
+__device__ inline void chunk_first_order(ChunkCtx &c, uint32_t *firstpos, uint8_t *order)
+{
+    const int n = c.n, tid = threadIdx.x;
+    for (int i = tid; i < 256; i += AMBC_BLOCK) firstpos[i] = 0xFFFFFFFFu;
+    __syncthreads();
+    const int nsl = (n + 31) >> 5;
+    for (int s = tid; s < nsl; s += AMBC_BLOCK) {
+        uint32_t w = c.bmask[s]; // run starts: only they can be first occurrences
+        while (w) {
+            int bit = __ffs(w) - 1;
+            w &= w - 1;
+            int p = 32 * s + bit;
+            atomicMin(&firstpos[c.sd[p]], (uint32_t)p);
+        }
+    }
+    __syncthreads();
+    for (int b = tid; b < 256; b += AMBC_BLOCK) {
+        uint32_t fp = firstpos[b];
+        if (fp != 0xFFFFFFFFu) {
+            int r = 0;
+            for (int j = 0; j < 256; j++) r += (firstpos[j] < fp);
+            order[r] = (uint8_t)b;
+        }
+    }
+    __syncthreads();
+}
+
+// exact Python-order entropy: e -= p*log2(p) over the Counter's insertion order, no FMA
+// contraction.  Result valid in every thread.  Collective.
+__device__ inline double chunk_entropy_ordered(ChunkCtx &c, int K, const uint8_t *order)
+{
+    volatile double *out = (volatile double *)c.red;
+    if (threadIdx.x == 0) {
+        double e = 0.0;
+        for (int r = 0; r < K; r++) {
+            double p = __ddiv_rn((double)c.hist[order[r]], (double)c.n);
+            e = __dsub_rn(e, __dmul_rn(p, log2(p)));
+        }
+        out[0] = e;
+    }
+    __syncthreads();
+    double e = out[0];
+    __syncthreads();
+    return e;
+}
+
+// ---------------------------------------------------------------------------------------
+// RLE encode (compression_methods.py:78-114): payload -> c.pay.  Returns the length.
+// Requires c.bmask from chunk_features.  Collective.
+// ---------------------------------------------------------------------------------------
+__device__ inline int chunk_rle_encode(ChunkCtx &c)
+{
+    const int n = c.n, tid = threadIdx.x;
+    const int nsl = (n + 31) >> 5;
+    const int spt = (nsl + AMBC_BLOCK - 1) / AMBC_BLOCK; // slices per thread, contiguous
+    int pairs = 0;
+    for (int s = tid * spt; s < min(nsl, (tid + 1) * spt); s++) {
+        uint32_t w = c.bmask[s];
+        while (w) {
+            int bit = __ffs(w) - 1;
+            w &= w - 1;
+            int p = 32 * s + bit, q;
+            if (w) q = 32 * s + __ffs(w) - 1;
+            else {
+                q = n;
+                for (int s2 = s + 1; s2 < nsl; s2++) {
+                    uint32_t w2 = c.bmask[s2];
+                    if (w2) { q = 32 * s2 + __ffs(w2) - 1; break; }
+                }
+            }
+            pairs += (q - p + 254) / 255;
+        }
+    }
+    int total;
+    int off = 2 * block_excl_scan(pairs, c.red, &total);
+    for (int s = tid * spt; s < min(nsl, (tid + 1) * spt); s++) {
+        uint32_t w = c.bmask[s];
+        while (w) {
+            int bit = __ffs(w) - 1;
+            w &= w - 1;
+            int p = 32 * s + bit, q;
+            if (w) q = 32 * s + __ffs(w) - 1;
+            else {
+                q = n;
+                for (int s2 = s + 1; s2 < nsl; s2++) {
+                    uint32_t w2 = c.bmask[s2];
+                    if (w2) { q = 32 * s2 + __ffs(w2) - 1; break; }
+                }
+            }
+            int R = q - p;
+            uint8_t v = c.sd[p];
+            while (R > 0) {
+                int cnt = R > 255 ? 255 : R;
+                if (off + 2 <= c.pcap) { c.pay[off] = v; c.pay[off + 1] = (uint8_t)cnt; }
+                off += 2;
+                R -= cnt;
+            }
+        }
+    }
+    __syncthreads();
+    return 2 * total;
+}
+
+// ---------------------------------------------------------------------------------------
+// Delta encode (compression_methods.py:585-608): payload -> c.pay (needs pcap >= n).
+// ---------------------------------------------------------------------------------------
+__device__ inline int chunk_delta_encode(ChunkCtx &c)
+{
+    const int n = c.n;
+    for (int i = threadIdx.x; i < n; i += AMBC_BLOCK) {
+        uint8_t v = i ? (uint8_t)(c.sd[i] - c.sd[i - 1]) : c.sd[0];
+        if (i < c.pcap) c.pay[i] = v;
+    }
+    __syncthreads();
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------
+// Dictionary / greedy LZ77 (compression_methods.py:195-234, 283-313)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lz_hash(uint32_t trigram)
+{
+    return (trigram * 2654435761u) >> (32 - AMBC_HB);
+}
+
+// Lower bound of the Dictionary payload for n bytes: the first token is a literal, every
+// other token covers at most 32 bytes (lookahead_size) for at least 2 bytes of output.
+__host__ __device__ inline int lz_lower_bound(int n)
+{
+    if (n <= 0) return 0;
+    int r = (n - 1) % 32;
+    return 2 + 4 * ((n - 1) / 32) + (2 * r < 4 ? 2 * r : 4);
+}
+
+// Payload -> c.pay (as far as pcap allows).  Returns the exact payload length.  Collective.
+__device__ inline int chunk_lz_encode(ChunkCtx &c)
+{
+    const int n = c.n, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int P = n - 2; // positions that start a trigram: 0 .. n-3
+    uint16_t *cnt = (uint16_t *)c.X; // [AMBC_WARPS][AMBC_NBUCKET]
+
+    if (P > 0) {
+        // ---- stable bucket sort of positions by trigram hash ----------------------------
+        for (int i = tid; i < AMBC_WARPS * AMBC_NBUCKET * 2 / 16; i += AMBC_BLOCK)
+            ((uint4 *)cnt)[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        const int Q = ((P + AMBC_BLOCK - 1) / AMBC_BLOCK) * 32; // positions per warp
+        const int wbeg = wid * Q, wend = min(P, wbeg + Q);
+        uint16_t *mycnt = cnt + wid * AMBC_NBUCKET;
+        for (int base = wbeg; base < wend; base += 32) { // pass 1: per-warp bucket counts
+            int p = base + lane;
+            bool valid = p < wend;
+            uint32_t h = valid ? lz_hash(lds_u32u(c.sd + p) & 0xFFFFFFu) : (uint32_t)(AMBC_NBUCKET + lane);
+            uint32_t peers = __match_any_sync(FULL_MASK, h);
+            uint32_t prior = valid ? mycnt[h] : 0;
+            __syncwarp();
+            if (valid && lane == 31 - __clz(peers)) mycnt[h] = (uint16_t)(prior + __popc(peers));
+            __syncwarp();
+        }
+        __syncthreads();
+        {   // exclusive scan in (bucket-major, warp-minor) order; thread owns 16 buckets
+            uint32_t v[AMBC_WARPS][8];
+#pragma unroll
+            for (int w = 0; w < AMBC_WARPS; w++) {
+                const uint4 *src = (const uint4 *)(cnt + w * AMBC_NBUCKET + 16 * tid);
+                uint4 a = src[0], b = src[1];
+                v[w][0] = a.x; v[w][1] = a.y; v[w][2] = a.z; v[w][3] = a.w;
+                v[w][4] = b.x; v[w][5] = b.y; v[w][6] = b.z; v[w][7] = b.w;
+            }
+            uint32_t run = 0;
+#pragma unroll
+            for (int hh = 0; hh < 16; hh++) {
+#pragma unroll
+                for (int w = 0; w < AMBC_WARPS; w++) {
+                    uint32_t word = v[w][hh >> 1];
+                    uint32_t x = (hh & 1) ? (word >> 16) : (word & 0xFFFF);
+                    v[w][hh >> 1] = (hh & 1) ? ((word & 0xFFFF) | (run << 16)) : ((word & 0xFFFF0000u) | run);
+                    run += x;
+                }
+            }
+            int tot;
+            uint32_t off = (uint32_t)block_excl_scan((int)run, c.red, &tot);
+            uint32_t off2 = off | (off << 16);
+#pragma unroll
+            for (int w = 0; w < AMBC_WARPS; w++) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[w][k] += off2;
+                uint4 *dst = (uint4 *)(cnt + w * AMBC_NBUCKET + 16 * tid);
+                dst[0] = make_uint4(v[w][0], v[w][1], v[w][2], v[w][3]);
+                dst[1] = make_uint4(v[w][4], v[w][5], v[w][6], v[w][7]);
+            }
+            uint4 *bs = (uint4 *)(c.bstart + 16 * tid);
+            bs[0] = make_uint4(v[0][0], v[0][1], v[0][2], v[0][3]);
+            bs[1] = make_uint4(v[0][4], v[0][5], v[0][6], v[0][7]);
+            if (tid == 0) c.bstart[AMBC_NBUCKET] = (uint16_t)P;
+        }
+        __syncthreads();
+        for (int base = wbeg; base < wend; base += 32) { // pass 2: ordered scatter
+            int p = base + lane;
+            bool valid = p < wend;
+            uint32_t h = valid ? lz_hash(lds_u32u(c.sd + p) & 0xFFFFFFu) : (uint32_t)(AMBC_NBUCKET + lane);
+            uint32_t peers = __match_any_sync(FULL_MASK, h);
+            uint32_t prior = valid ? mycnt[h] : 0;
+            __syncwarp();
+            if (valid) {
+                c.sorted[prior + __popc(peers & ((1u << lane) - 1))] = (uint16_t)p;
+                if (lane == 31 - __clz(peers)) mycnt[h] = (uint16_t)(prior + __popc(peers));
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+
+        // ---- earliest-longest match for every position (thread per sorted slot) ----------
+        for (int s = tid; s < P; s += AMBC_BLOCK) {
+            const int p = c.sorted[s];
+            const uint32_t w0 = lds_u32u(c.sd + p);
+            const int b0 = c.bstart[lz_hash(w0 & 0xFFFFFFu)];
+            const int cap = min(32, n - p);
+            int best = 0, bpos = 0;
+            if (b0 < s) {
+                uint32_t pw[8];
+                pw[0] = w0;
+#pragma unroll
+                for (int k = 1; k < 8; k++) pw[k] = lds_u32u(c.sd + p + 4 * k);
+                const int lo = p - 4096; // window_size (:294)
+                for (int j = b0; j < s; j++) {
+                    const int i = c.sorted[j];
+                    if (i < lo) continue;
+                    uint32_t x = lds_u32u(c.sd + i) ^ pw[0];
+                    if (x & 0xFFFFFFu) continue; // hash collision: different trigram
+                    int len;
+                    if (x) len = 3;
+                    else {
+                        len = 4;
+#pragma unroll
+                        for (int k = 1; k < 8; k++) {
+                            x = lds_u32u(c.sd + i + 4 * k) ^ pw[k];
+                            if (x) { len = 4 * k + ((__ffs(x) - 1) >> 3); break; }
+                            len = 4 * k + 4;
+                        }
+                    }
+                    len = min(len, cap);
+                    if (len > best) { // strictly longer: earliest wins ties (:309-311)
+                        best = len; bpos = i;
+                        if (len == cap) break;
+                    }
+                }
+            }
+            c.mlen[p] = (uint8_t)best;
+            c.mpos[p] = (uint16_t)bpos;
+        }
+    }
+    for (int p = max(P, 0) + tid; p < n; p += AMBC_BLOCK) c.mlen[p] = 0;
+    for (int p = n + tid; p < (int)r16((size_t)n); p += AMBC_BLOCK) c.mlen[p] = 0;
+    __syncthreads();
+
+    // ---- token chain: pos -> pos + (len>2 ? len : 1) (:211-232), resolved per 32-block ---
+    const int nb = (n + 31) >> 5;
+    uint8_t *fexit = c.X; // fexit[q * nb + b]: where a chain entering block b at offset q leaves it
+    for (int b = tid; b < nb; b += AMBC_BLOCK) {
+        const uint4 a4 = *(const uint4 *)(c.mlen + 32 * b);
+        const uint4 b4 = *(const uint4 *)(c.mlen + 32 * b + 16);
+#pragma unroll
+        for (int q = 31; q >= 0; q--) {
+            uint32_t L = slice_byte(a4, b4, q);
+            int t = q + (L >= 3 ? (int)L : 1);
+            uint8_t fx;
+            if (32 * b + q >= n) fx = 255; // past the end of the chunk
+            else if (t >= 32) fx = (uint8_t)(t - 32);
+            else fx = fexit[t * nb + b];
+            fexit[q * nb + b] = fx;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int e = 0;
+        for (int b = 0; b < nb; b++) {
+            c.estart[b] = (uint8_t)e;
+            if (e != 255) e = fexit[e * nb + b];
+        }
+    }
+    __syncthreads();
+    const int bpt = (nb + AMBC_BLOCK - 1) / AMBC_BLOCK; // blocks per thread, contiguous
+    int tbytes = 0;
+    for (int b = tid * bpt; b < min(nb, (tid + 1) * bpt); b++) {
+        int q = c.estart[b];
+        uint32_t mask = 0;
+        while (q < 32 && 32 * b + q < n) {
+            mask |= 1u << q;
+            int L = c.mlen[32 * b + q];
+            if (L >= 3) { tbytes += 4; q += L; } else { tbytes += 2; q += 1; }
+        }
+        c.reach[b] = mask;
+    }
+    int total;
+    int off = block_excl_scan(tbytes, c.red, &total);
+    for (int b = tid * bpt; b < min(nb, (tid + 1) * bpt); b++) {
+        uint32_t w = c.reach[b];
+        while (w) {
+            int p = 32 * b + __ffs(w) - 1;
+            w &= w - 1;
+            int L = c.mlen[p];
+            if (L >= 3) {
+                if (off + 4 <= c.pcap) {
+                    int d = p - (int)c.mpos[p];
+                    c.pay[off] = 1; c.pay[off + 1] = (uint8_t)(d & 0xFF);
+                    c.pay[off + 2] = (uint8_t)(d >> 8); c.pay[off + 3] = (uint8_t)L;
+                }
+                off += 4;
+            } else {
+                if (off + 2 <= c.pcap) { c.pay[off] = 0; c.pay[off + 1] = c.sd[p]; }
+                off += 2;
+            }
+        }
+    }
+    __syncthreads();
+    return total;
+}
+
+// ---------------------------------------------------------------------------------------
+// Huffman (compression_methods.py:354-405, 472-549)
+// ---------------------------------------------------------------------------------------
+// scratch layout inside c.X
+struct HuffScratch {
+    uint32_t *key;      // [256] (count << 8 | sym) or 0xFFFFFFFF
+    uint32_t *nodeW;    // [512]
+    uint16_t *lead;     // [512]
+    uint16_t *parent;   // [512]
+    uint8_t *nbit;      // [512]
+    uint8_t *lenOf;     // [256] by symbol
+    uint8_t *order;     // [256] first-occurrence order
+    uint32_t *codeOf;   // [256] by symbol
+    uint32_t *firstpos; // [256]
+    uint8_t *leafsym;   // [256] symbol of sorted leaf j
+};
+__device__ inline HuffScratch huff_scratch(uint8_t *X)
+{
+    HuffScratch h;
+    h.key = (uint32_t *)X;
+    h.nodeW = (uint32_t *)(X + 1024);
+    h.lead = (uint16_t *)(X + 3072);
+    h.parent = (uint16_t *)(X + 4096);
+    h.nbit = X + 5120;
+    h.lenOf = X + 5632;
+    h.order = X + 5888;
+    h.codeOf = (uint32_t *)(X + 6144);
+    h.firstpos = (uint32_t *)(X + 7168);
+    h.leafsym = X + 8192;
+    return h;
+}
+
+// Build the reference's tree for the counts in c.hist (K distinct values, 2 <= K <= 256):
+// repeatedly merge the two smallest nodes under (weight, leader); lo gets bit 0, hi bit 1;
+// leader(merged) = leader(lo) (:482-494).  Leaves are pre-sorted by (weight, symbol) and the
+// merged nodes come out already ordered by the same key, so two queues suffice.
+// Fills lenOf / codeOf and returns the total number of code bits.  Collective.
+__device__ inline int chunk_huff_build(ChunkCtx &c, HuffScratch &h, int K)
+{
+    const int tid = threadIdx.x;
+    for (int b = tid; b < 256; b += AMBC_BLOCK) {
+        uint32_t cnt = c.hist[b];
+        h.key[b] = cnt ? ((cnt << 8) | (uint32_t)b) : 0xFFFFFFFFu;
+        h.lenOf[b] = 0;
+        h.codeOf[b] = 0;
+    }
+    __syncthreads();
+    for (int b = tid; b < 256; b += AMBC_BLOCK) { // rank sort: keys are distinct
+        uint32_t k = h.key[b];
+        if (k != 0xFFFFFFFFu) {
+            int r = 0;
+            for (int j = 0; j < 256; j++) r += (h.key[j] < k);
+            h.nodeW[r] = k >> 8;
+            h.lead[r] = (uint16_t)b;
+            h.leafsym[r] = (uint8_t)b;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int li = 0, mi = K, t = K;
+        for (int it = 0; it < K - 1; it++) {
+            int pick[2];
+#pragma unroll
+            for (int z = 0; z < 2; z++) {
+                bool hasL = li < K, hasM = mi < t;
+                bool takeL;
+                if (hasL && hasM) {
+                    uint32_t wl = h.nodeW[li], wm = h.nodeW[mi];
+                    takeL = (wl < wm) || (wl == wm && h.lead[li] < h.lead[mi]);
+                } else takeL = hasL;
+                pick[z] = takeL ? li++ : mi++;
+            }
+            h.nodeW[t] = h.nodeW[pick[0]] + h.nodeW[pick[1]];
+            h.lead[t] = h.lead[pick[0]];
+            h.parent[pick[0]] = (uint16_t)t; h.nbit[pick[0]] = 0;
+            h.parent[pick[1]] = (uint16_t)t; h.nbit[pick[1]] = 1;
+            t++;
+        }
+    }
+    __syncthreads();
+    const int root = 2 * K - 2;
+    int bits = 0;
+    for (int j = tid; j < K; j += AMBC_BLOCK) {
+        int node = j, len = 0;
+        uint32_t code = 0;
+        while (node != root) {
+            code |= (uint32_t)h.nbit[node] << len;
+            len++;
+            node = h.parent[node];
+        }
+        int sym = h.leafsym[j];
+        h.lenOf[sym] = (uint8_t)len;
+        h.codeOf[sym] = code;
+        bits += len * (int)c.hist[sym];
+    }
+    return block_sum(bits, c.red);
+}
+
+// Payload (table in first-occurrence order + bit count + MSB-first bit stream, :379-403)
+// -> c.pay.  Requires chunk_huff_build and c.bmask.  Returns the payload length.  Collective.
+__device__ inline int chunk_huff_emit(ChunkCtx &c, HuffScratch &h, int K, int total_bits)
+{
+    const int n = c.n, tid = threadIdx.x;
+    chunk_first_order(c, h.firstpos, h.order);
+    const int hdr = 1 + 5 * K + 4;
+    const int nbytes = (total_bits + 7) >> 3;
+    if (tid == 0 && c.pcap >= 1) c.pay[0] = (uint8_t)K;
+    for (int r = tid; r < K; r += AMBC_BLOCK) {
+        int o = 1 + 5 * r;
+        if (o + 5 <= c.pcap) {
+            int sym = h.order[r];
+            c.pay[o] = (uint8_t)sym;
+            store_u32le(c.pay + o + 1, c.hist[sym]);
+        }
+    }
+    if (tid == 0 && hdr <= c.pcap) store_u32le(c.pay + hdr - 4, (uint32_t)total_bits);
+    // bit stream built as big-endian 32-bit words in the (now dead) sorted[] region
+    uint32_t *bw = (uint32_t *)c.sorted;
+    const int nwords = (total_bits + 31) >> 5;
+    const int wcap = min(nwords, (c.pcap >> 2) + 1);
+    for (int i = tid; i < wcap; i += AMBC_BLOCK) bw[i] = 0;
+    const int nsl = (n + 31) >> 5;
+    const int spt = (nsl + AMBC_BLOCK - 1) / AMBC_BLOCK;
+    int mybits = 0;
+    for (int s = tid * spt; s < min(nsl, (tid + 1) * spt); s++) {
+        const int m = min(32, n - 32 * s);
+        for (int j = 0; j < m; j++) mybits += h.lenOf[c.sd[32 * s + j]];
+    }
+    int tot;
+    int g = block_excl_scan(mybits, c.red, &tot); // includes the barrier after zeroing bw
+    {
+        int w = g >> 5, used = g & 31;
+        uint32_t cur = 0;
+        for (int s = tid * spt; s < min(nsl, (tid + 1) * spt); s++) {
+            const int m = min(32, n - 32 * s);
+            for (int j = 0; j < m; j++) {
+                int sym = c.sd[32 * s + j];
+                uint32_t code = h.codeOf[sym];
+                int l = h.lenOf[sym];
+                int space = 32 - used;
+                if (l <= space) {
+                    cur |= code << (space - l);
+                    used += l;
+                    if (used == 32) {
+                        if (w < wcap) atomicOr(&bw[w], cur);
+                        w++; cur = 0; used = 0;
+                    }
+                } else {
+                    cur |= code >> (l - space);
+                    if (w < wcap) atomicOr(&bw[w], cur);
+                    w++;
+                    used = l - space;
+                    cur = code << (32 - used);
+                }
+            }
+        }
+        if (used && w < wcap) atomicOr(&bw[w], cur);
+    }
+    __syncthreads();
+    for (int k = tid; k < nbytes; k += AMBC_BLOCK) {
+        if (hdr + k < c.pcap) c.pay[hdr + k] = (uint8_t)(bw[k >> 2] >> (24 - 8 * (k & 3)));
+    }
+    __syncthreads();
+    return hdr + nbytes;
+}

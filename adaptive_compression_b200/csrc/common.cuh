@@ -1,0 +1,131 @@
+// common.cuh -- shared device helpers for libambc (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define AMBC_BLOCK 128              // threads per CTA in the chunk kernels
+#define AMBC_WARPS (AMBC_BLOCK / 32)
+#define AMBC_HB 11                  // LZ trigram hash bits
+#define AMBC_NBUCKET (1 << AMBC_HB)
+#define AMBC_NMAX 8192              // largest chunk a native method accepts (adaptive_compressor.py:114-127)
+#define AMBC_PAD 64                 // zeroed bytes after the chunk in shared memory
+
+#define FULL_MASK 0xffffffffu
+
+// unaligned 32-bit little-endian load from shared memory (two aligned words + funnel shift)
+__device__ __forceinline__ uint32_t lds_u32u(const uint8_t *s)
+{
+    uintptr_t a = (uintptr_t)s;
+    const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
+    return __funnelshift_r(w[0], w[1], (uint32_t)(a & 3) * 8);
+}
+
+__device__ __forceinline__ int warp_incl_scan(int v)
+{
+    int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(FULL_MASK, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+__device__ __forceinline__ int warp_sum(int v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL_MASK, v, d);
+    return v;
+}
+
+// block-wide exclusive scan (AMBC_BLOCK threads).  red: >= AMBC_WARPS ints of shared memory.
+// Contains two __syncthreads(); every thread of the block must call it.
+__device__ __forceinline__ int block_excl_scan(int v, volatile int *red, int *total)
+{
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = warp_incl_scan(v);
+    __syncthreads();
+    if (lane == 31) red[w] = inc;
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < AMBC_WARPS; i++) {
+        int x = red[i];
+        if (i < w) base += x;
+        tot += x;
+    }
+    *total = tot;
+    return base + inc - v;
+}
+
+// block-wide sum; two __syncthreads()
+__device__ __forceinline__ int block_sum(int v, volatile int *red)
+{
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    int tot = 0;
+#pragma unroll
+    for (int i = 0; i < AMBC_WARPS; i++) tot += red[i];
+    return tot;
+}
+
+__device__ __forceinline__ double block_sum_f64(double v, volatile double *red)
+{
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL_MASK, v, d);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    double tot = 0.0;
+#pragma unroll
+    for (int i = 0; i < AMBC_WARPS; i++) tot += red[i];
+    return tot;
+}
+
+// Copy `len` bytes global -> shared.  dst is 16-byte aligned shared memory.  Uses 16-byte
+// vector loads when src is 16-byte aligned, byte loads otherwise (odd chunk sizes).
+__device__ __forceinline__ void copy_g2s(uint8_t *dst, const uint8_t *__restrict__ src, int len)
+{
+    if ((((uintptr_t)src) & 15) == 0) {
+        int nv = len >> 4;
+        const uint4 *s4 = (const uint4 *)src;
+        uint4 *d4 = (uint4 *)dst;
+        for (int i = threadIdx.x; i < nv; i += AMBC_BLOCK) d4[i] = __ldg(s4 + i);
+        for (int i = (nv << 4) + threadIdx.x; i < len; i += AMBC_BLOCK) dst[i] = __ldg(src + i);
+    } else {
+        for (int i = threadIdx.x; i < len; i += AMBC_BLOCK) dst[i] = __ldg(src + i);
+    }
+}
+
+// Copy `len` bytes shared (any alignment) -> global (any alignment): byte stores up to the
+// first 16-byte boundary of dst, aligned 16-byte stores fed by funnel-shifted shared loads,
+// byte stores for the tail.
+__device__ __forceinline__ void copy_s2g(uint8_t *__restrict__ dst, const uint8_t *src, int len)
+{
+    int head = (int)((16 - ((uintptr_t)dst & 15)) & 15);
+    if (head > len) head = len;
+    for (int i = threadIdx.x; i < head; i += AMBC_BLOCK) dst[i] = src[i];
+    int body = (len - head) >> 4;
+    uint4 *d4 = (uint4 *)(dst + head);
+    const uint8_t *s = src + head;
+    for (int i = threadIdx.x; i < body; i += AMBC_BLOCK) {
+        const uint8_t *p = s + (i << 4);
+        uint4 v;
+        v.x = lds_u32u(p); v.y = lds_u32u(p + 4); v.z = lds_u32u(p + 8); v.w = lds_u32u(p + 12);
+        d4[i] = v;
+    }
+    for (int i = head + (body << 4) + threadIdx.x; i < len; i += AMBC_BLOCK) dst[i] = src[i];
+}
+
+__device__ __forceinline__ void store_u32le(uint8_t *p, uint32_t v)
+{
+    p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24);
+}
+__device__ __forceinline__ uint32_t load_u32le(const uint8_t *p)
+{
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}

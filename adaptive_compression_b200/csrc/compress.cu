@@ -1,0 +1,462 @@
+// compress.cu -- chunk trial / select / pack kernels and the ambc_compress_* entry points.
+//
+// Replaces AdaptiveCompressor._adaptive_compress and its helpers
+// (adaptive_compressor.py:363-394, 537-590, 595-700) in fixed-candidate mode.
+//
+//   k_select   one CTA per grid chunk: stage 4 KiB in shared memory, evaluate the gates,
+//              compute every enabled candidate's exact size, pick the argmin in list order
+//              with the benefit test len+overhead < n, encode the winner into its slot.
+//   k_sizes / k_scan_blocks / k_offsets
+//              exclusive scan of package sizes with the "rest of file raw" rule: everything
+//              from the first chunk without a winner onward is ONE raw package.
+//   k_pack     one CTA per chunk: 18-byte package header + payload to the final offset.
+#include "ambc_internal.h"
+#include "chunk_codec.cuh"
+
+static_assert(AMBC_NBUCKET == 16 * AMBC_BLOCK, "scan in chunk_lz_encode assumes 16 buckets per thread");
+
+// per-chunk decision ------------------------------------------------------------------------
+struct SelectOut { int type; int len; };
+
+// size-range eligibility (adaptive_compressor.py:114-127, tested on the clamped size :565-567)
+__device__ __forceinline__ bool eligible(int id, int n)
+{
+    switch (id) {
+    case 1: return n >= 32 && n <= 4096;
+    case 2: return n >= 128 && n <= 8192;
+    case 3: return n >= 32 && n <= 8192;
+    case 4: return n >= 32 && n <= 4096;
+    }
+    return false;
+}
+
+// Evaluate one chunk already staged in c; leaves the winner's payload in c.pay.
+__device__ SelectOut select_chunk(ChunkCtx &c, uint32_t mask, int ovh)
+{
+    const int n = c.n;
+    ChunkFeatures f;
+    chunk_features(c, f);
+    HuffScratch hs = huff_scratch(c.X);
+
+    // gates (compression_methods.py:154-180, 315-343, 551-574)
+    bool rle_ok = (mask & 2u) && eligible(1, n) && n >= 4 &&
+                  __ddiv_rn((double)f.rep, (double)(min(1000, n) - 1)) > 0.3;
+    bool lz_ok = (mask & 4u) && eligible(2, n) && n >= 100 &&
+                 __ddiv_rn((double)f.distinct3, (double)min(1000, n)) < 0.8;
+    bool hf_ok = (mask & 8u) && eligible(3, n) && n >= 100 && f.K >= 2 && f.K <= 255;
+    if (hf_ok) {
+        double H = f.H;
+        if (fabs(H - 7.0) < 1e-9) { // resolve in the reference's summation order
+            chunk_first_order(c, hs.firstpos, hs.order);
+            H = chunk_entropy_ordered(c, f.K, hs.order);
+        }
+        hf_ok = H < 7.0;
+    }
+    // Delta (id 4) always produces n bytes, so (n + overhead)/n > 1 never wins (:574-577).
+
+    int best_type = 255, best_len = 0x7fffffff;
+    if (rle_ok) {
+        int len = 2 * f.rle_pairs;
+        if (len + ovh < n) { best_type = 1; best_len = len; }
+    }
+    if (lz_ok) {
+        // a Dictionary payload can never be shorter than lz_lower_bound(n): skip the trial
+        // when it cannot win (strict '<' keeps the earlier method on ties, :575)
+        int lb = lz_lower_bound(n);
+        if (lb < best_len && lb + ovh < n) {
+            int len = chunk_lz_encode(c);
+            if (len < best_len && len + ovh < n) { best_type = 2; best_len = len; }
+        }
+    }
+    if (hf_ok) {
+        // lower bound from the entropy: bits >= max(n, n*H)
+        double lbits = fmax((double)n, (double)n * f.H - 0.01);
+        int lb = 1 + 5 * f.K + 4 + (int)ceil(lbits / 8.0);
+        if (lb < best_len && lb + ovh < n) {
+            int bits = chunk_huff_build(c, hs, f.K);
+            int len = 1 + 5 * f.K + 4 + ((bits + 7) >> 3);
+            if (len < best_len && len + ovh < n) {
+                best_type = 3; best_len = len;
+                chunk_huff_emit(c, hs, f.K, bits);
+            }
+        }
+    }
+    if (best_type == 1) chunk_rle_encode(c);
+    SelectOut o;
+    o.type = best_type;
+    o.len = best_type == 255 ? n : best_len;
+    return o;
+}
+
+__global__ void __launch_bounds__(AMBC_BLOCK)
+k_select(const uint8_t *__restrict__ in, uint64_t total, uint32_t N, uint32_t mask, uint32_t ovh,
+         uint8_t *__restrict__ slots, uint64_t slot_stride, uint8_t *__restrict__ type,
+         uint32_t *__restrict__ comp, unsigned long long *first_raw, uint64_t n_chunks)
+{
+    extern __shared__ uint4 smem4[];
+    ChunkCtx c;
+    chunkctx_carve(c, (uint8_t *)smem4, (int)N, (int)N);
+    for (uint64_t i = blockIdx.x; i < n_chunks; i += gridDim.x) {
+        uint64_t off = i * (uint64_t)N;
+        int n = (int)min((uint64_t)N, total - off);
+        chunk_load(c, in + off, n);
+        SelectOut o = select_chunk(c, mask, (int)ovh);
+        __syncthreads();
+        if (o.type != 255) {
+            uint8_t *dst = slots + i * slot_stride; // 16-byte aligned
+            int nv = (o.len + 15) >> 4;
+            for (int k = threadIdx.x; k < nv; k += AMBC_BLOCK) ((uint4 *)dst)[k] = ((const uint4 *)c.pay)[k];
+        }
+        if (threadIdx.x == 0) {
+            type[i] = (uint8_t)o.type;
+            comp[i] = (uint32_t)o.len;
+            if (o.type == 255) atomicMin(first_raw, (unsigned long long)i);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- package-size scan ---------------------------------------------------------------------
+// In strict mode chunks >= first_raw contribute nothing (they live inside the single raw
+// package); in per-chunk-raw mode every chunk is its own package.
+#define SCAN_TILE 2048
+struct ScanState {
+    unsigned long long first_raw;  // min chunk index without a winner, ~0 if none
+    unsigned long long body_len;
+    unsigned long long n_packages;
+    unsigned long long payload_bytes;
+    unsigned long long usage[5];
+};
+
+__device__ __forceinline__ uint64_t pkg_size(uint64_t i, const uint8_t *type, const uint32_t *comp, uint32_t N,
+                                             uint64_t total, uint32_t ovh, uint64_t first_raw, bool pcr)
+{
+    if (!pcr && i >= first_raw) return 0;
+    uint64_t len = comp[i]; // raw chunks carry comp = n
+    (void)N; (void)total; (void)type;
+    return ovh + len;
+}
+
+__global__ void __launch_bounds__(256)
+k_sizes(const uint8_t *__restrict__ type, const uint32_t *__restrict__ comp, uint64_t n_chunks, uint32_t N,
+        uint64_t total, uint32_t ovh, uint32_t flags, const ScanState *st, unsigned long long *tile_sum)
+{
+    __shared__ unsigned long long red[8];
+    const bool pcr = flags & 1u;
+    const uint64_t fr = st->first_raw;
+    uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE;
+    unsigned long long s = 0;
+    for (int k = threadIdx.x; k < SCAN_TILE; k += 256) {
+        uint64_t i = base + k;
+        if (i < n_chunks) s += pkg_size(i, type, comp, N, total, ovh, fr, pcr);
+    }
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(FULL_MASK, s, d);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int i = 0; i < 8; i++) t += red[i];
+        tile_sum[blockIdx.x] = t;
+    }
+}
+
+// single CTA: exclusive scan of the tile sums in place, body length, END package, stats
+__global__ void __launch_bounds__(1024)
+k_scan_tiles(unsigned long long *tile_sum, uint64_t n_tiles, const uint8_t *__restrict__ type,
+             const uint32_t *__restrict__ comp, uint64_t n_chunks, uint32_t N, uint64_t total, uint32_t ovh,
+             uint32_t flags, ScanState *st, uint8_t *out, uint64_t out_cap, uint32_t marker_word, uint32_t mb)
+{
+    __shared__ unsigned long long wsum[32];
+    __shared__ unsigned long long carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (uint64_t base = 0; base < n_tiles; base += 1024) {
+        uint64_t i = base + tid;
+        unsigned long long v = i < n_tiles ? tile_sum[i] : 0, inc = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long t = __shfl_up_sync(FULL_MASK, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) wsum[w] = inc;
+        __syncthreads();
+        unsigned long long wbase = 0;
+        for (int k = 0; k < w; k++) wbase += wsum[k];
+        unsigned long long carry = carry_s;
+        if (i < n_tiles) tile_sum[i] = carry + wbase + inc - v;
+        __syncthreads();
+        if (tid == 1023) carry_s = carry + wbase + inc;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const bool pcr = flags & 1u;
+        unsigned long long body = carry_s;
+        unsigned long long fr = st->first_raw;
+        unsigned long long npk = n_chunks;
+        if (!pcr && fr != ~0ull) {
+            // one raw package for the rest of the file (adaptive_compressor.py:586-590)
+            body += ovh + (total - fr * (unsigned long long)N);
+            npk = fr + 1;
+        }
+        st->n_packages = npk;
+        body += mb + 12; // END package (:595-607)
+        st->body_len = body;
+        if (body <= out_cap) {
+            uint8_t *e = out + body - (mb + 12);
+            for (uint32_t k = 0; k < mb; k++) e[k] = (uint8_t)(marker_word >> (8 * k));
+            for (uint32_t k = 0; k < 12; k++) e[mb + k] = 0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_offsets(const uint8_t *__restrict__ type, const uint32_t *__restrict__ comp, uint64_t n_chunks, uint32_t N,
+          uint64_t total, uint32_t ovh, uint32_t flags, ScanState *st, const unsigned long long *tile_base,
+          unsigned long long *offs)
+{
+    // one tile per CTA, 8 chunks per thread
+    __shared__ unsigned long long wsum[8];
+    __shared__ unsigned long long ustat[6];
+    const bool pcr = flags & 1u;
+    const uint64_t fr = st->first_raw;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid < 6) ustat[tid] = 0;
+    uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)tid * 8;
+    unsigned long long v[8], s = 0;
+    unsigned long long usage[5] = {0, 0, 0, 0, 0}, pbytes = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        uint64_t i = base + k;
+        v[k] = i < n_chunks ? pkg_size(i, type, comp, N, total, ovh, fr, pcr) : 0;
+        s += v[k];
+        if (i < n_chunks && (pcr || i < fr)) {
+            int t = type[i];
+            if (t >= 1 && t <= 4) { usage[t]++; pbytes += comp[i]; }
+            else usage[0]++;
+        }
+    }
+    unsigned long long inc = s;
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long t = __shfl_up_sync(FULL_MASK, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    unsigned long long wbase = 0;
+    for (int k = 0; k < w; k++) wbase += wsum[k];
+    unsigned long long run = tile_base[blockIdx.x] + wbase + inc - s;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        uint64_t i = base + k;
+        if (i < n_chunks) offs[i] = run;
+        run += v[k];
+    }
+    // statistics (adaptive_compressor.py:471-480)
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        unsigned long long u = usage[k];
+        for (int d = 16; d > 0; d >>= 1) u += __shfl_xor_sync(FULL_MASK, u, d);
+        if (lane == 0 && u) atomicAdd(&ustat[k], u);
+    }
+    for (int d = 16; d > 0; d >>= 1) pbytes += __shfl_xor_sync(FULL_MASK, pbytes, d);
+    if (lane == 0 && pbytes) atomicAdd(&ustat[5], pbytes);
+    __syncthreads();
+    if (tid < 5 && ustat[tid]) atomicAdd(&st->usage[tid], ustat[tid]);
+    if (tid == 5 && ustat[5]) atomicAdd(&st->payload_bytes, ustat[5]);
+}
+
+// ---- pack ----------------------------------------------------------------------------------
+// package header (adaptive_compressor.py:609-621): marker, type, k=0, used u32, orig u32, comp u32
+__device__ __forceinline__ void write_pkg_header(uint8_t *h, uint32_t marker_word, uint32_t mb, int type,
+                                                 uint32_t orig, uint32_t comp)
+{
+    for (uint32_t k = 0; k < mb; k++) h[k] = (uint8_t)(marker_word >> (8 * k));
+    h[mb] = (uint8_t)type;
+    h[mb + 1] = 0;
+    store_u32le(h + mb + 2, orig);
+    store_u32le(h + mb + 6, orig);
+    store_u32le(h + mb + 10, comp);
+}
+
+__global__ void __launch_bounds__(AMBC_BLOCK)
+k_pack(const uint8_t *__restrict__ in, uint64_t total, uint32_t N, const uint8_t *__restrict__ slots,
+       uint64_t slot_stride, const uint8_t *__restrict__ type, const uint32_t *__restrict__ comp,
+       const unsigned long long *__restrict__ offs, const ScanState *st, uint32_t flags, uint32_t marker_word,
+       uint32_t mb, uint8_t *__restrict__ out, uint64_t out_cap, uint64_t n_chunks)
+{
+    extern __shared__ uint4 smem4[];
+    uint8_t *buf = (uint8_t *)smem4; // [32 header area][payload]
+    const bool pcr = flags & 1u;
+    const uint64_t fr = st->first_raw;
+    const uint32_t ovh = mb + 14;
+    if (st->body_len > out_cap) return;
+    for (uint64_t i = blockIdx.x; i < n_chunks; i += gridDim.x) {
+        uint64_t coff = i * (uint64_t)N;
+        int n = (int)min((uint64_t)N, total - coff);
+        if (!pcr && i >= fr) {
+            // inside the single raw package: header once, then plain bytes
+            uint64_t pbase = offs[fr]; // == offset of the raw package (sizes beyond fr are 0)
+            uint64_t rawlen = total - fr * (uint64_t)N;
+            copy_g2s(buf + 32, in + coff, n);
+            uint8_t *src = buf + 32;
+            int len = n;
+            if (i == fr) {
+                if (threadIdx.x == 0) write_pkg_header(buf + 32 - ovh, marker_word, mb, 255, (uint32_t)rawlen, (uint32_t)rawlen);
+                src = buf + 32 - ovh;
+                len = n + ovh;
+            }
+            __syncthreads();
+            uint64_t dst = (i == fr) ? pbase : pbase + ovh + (coff - fr * (uint64_t)N);
+            copy_s2g(out + dst, src, len);
+        } else {
+            int t = type[i];
+            int len = (int)comp[i];
+            if (t == 255) copy_g2s(buf + 32, in + coff, n);
+            else copy_g2s(buf + 32, slots + i * slot_stride, len);
+            if (threadIdx.x == 0) write_pkg_header(buf + 32 - ovh, marker_word, mb, t, (uint32_t)n, (uint32_t)len);
+            __syncthreads();
+            copy_s2g(out + offs[i], buf + 32 - ovh, len + ovh);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------
+struct WorkLayout {
+    uint64_t slots, type, comp, offs, tiles, state, total;
+    uint64_t slot_stride, n_chunks, n_tiles;
+};
+static WorkLayout work_layout(uint64_t n, uint32_t chunk)
+{
+    WorkLayout L;
+    L.n_chunks = chunk ? (n + chunk - 1) / chunk : 0;
+    L.n_tiles = (L.n_chunks + SCAN_TILE - 1) / SCAN_TILE;
+    L.slot_stride = chunk <= AMBC_NMAX ? ((uint64_t)chunk + 15) & ~15ull : 0;
+    uint64_t o = 0;
+    auto take = [&](uint64_t bytes) { uint64_t r = o; o += (bytes + 255) & ~255ull; return r; };
+    L.slots = take(L.n_chunks * L.slot_stride + 16);
+    L.type = take(L.n_chunks + 16);
+    L.comp = take(L.n_chunks * 4 + 16);
+    L.offs = take(L.n_chunks * 8 + 16);
+    L.tiles = take(L.n_tiles * 8 + 16);
+    L.state = take(sizeof(ScanState));
+    L.total = o;
+    return L;
+}
+
+extern "C" uint64_t ambc_compress_workspace_bytes(uint64_t n, uint32_t chunk)
+{
+    return work_layout(n, chunk).total;
+}
+
+extern "C" uint64_t ambc_compress_bound(uint64_t n, uint32_t chunk, uint32_t marker_bytes)
+{
+    uint64_t chunks = chunk ? (n + chunk - 1) / chunk : 0;
+    return n + (chunks + 1) * (marker_bytes + 14) + marker_bytes + 12 + 64;
+}
+
+extern "C" int ambc_compress_dev(const void *in_dev, uint64_t n, uint32_t chunk, uint32_t method_mask,
+                                 uint32_t flags, const uint8_t *marker, uint32_t marker_bytes, void *out_dev,
+                                 uint64_t out_cap, void *work_dev, uint64_t work_bytes, ambc_compress_result *res,
+                                 void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!res || !marker || marker_bytes < 1 || marker_bytes > 4 || chunk == 0)
+        return ambc_fail(AMBC_E_ARG, "ambc_compress_dev: bad argument");
+    if ((n && (!in_dev || !work_dev)) || !out_dev) return ambc_fail(AMBC_E_ARG, "ambc_compress_dev: null buffer");
+    WorkLayout L = work_layout(n, chunk);
+    if (work_bytes < L.total) return ambc_fail(AMBC_E_CAPACITY, "ambc_compress_dev: workspace too small");
+    if ((uint64_t)chunk > 0xFFFFFFFFull - 32) return ambc_fail(AMBC_E_ARG, "chunk too large");
+    uint32_t ovh = marker_bytes + 14;
+    uint32_t marker_word = 0;
+    for (uint32_t k = 0; k < marker_bytes; k++) marker_word |= (uint32_t)marker[k] << (8 * k);
+    memset(res, 0, sizeof(*res));
+    res->n_chunks = L.n_chunks;
+    res->map_type_off = L.type;
+    res->map_comp_off = L.comp;
+
+    uint8_t *W = (uint8_t *)work_dev;
+    ScanState *st = (ScanState *)(W + L.state);
+    ScanState h_st;
+    memset(&h_st, 0, sizeof h_st);
+    h_st.first_raw = ~0ull;
+
+    if (n == 0) { // only the END package
+        uint8_t endp[16];
+        memcpy(endp, marker, marker_bytes);
+        memset(endp + marker_bytes, 0, 12);
+        if (out_cap < marker_bytes + 12) return ambc_fail(AMBC_E_CAPACITY, "out too small");
+        CUDA_TRY(cudaMemcpyAsync(out_dev, endp, marker_bytes + 12, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        res->body_len = marker_bytes + 12;
+        res->first_raw = -1;
+        return AMBC_OK;
+    }
+    // chunks of more than 4 GiB cannot be framed (u32 length fields, :617-619)
+    bool native = chunk <= AMBC_NMAX && (method_mask & AMBC_NATIVE_MASK);
+    if (!native) h_st.first_raw = 0; // no native method is eligible: everything is raw
+    CUDA_TRY(cudaMemcpyAsync(st, &h_st, sizeof h_st, cudaMemcpyHostToDevice, stream));
+
+    uint8_t *type = W + L.type;
+    uint32_t *comp = (uint32_t *)(W + L.comp);
+    unsigned long long *offs = (unsigned long long *)(W + L.offs);
+    unsigned long long *tiles = (unsigned long long *)(W + L.tiles);
+    unsigned grid_chunks = (unsigned)min<uint64_t>(L.n_chunks, 0x7fffffffull);
+
+    if (native) {
+        size_t smem = chunkctx_smem_bytes((int)chunk, (int)chunk);
+        CUDA_TRY(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_select<<<grid_chunks, AMBC_BLOCK, smem, stream>>>((const uint8_t *)in_dev, n, chunk, method_mask, ovh,
+                                                            W + L.slots, L.slot_stride, type, comp,
+                                                            &st->first_raw, L.n_chunks);
+        ambc_count_launch();
+        CUDA_TRY(cudaGetLastError());
+        k_sizes<<<(unsigned)L.n_tiles, 256, 0, stream>>>(type, comp, L.n_chunks, chunk, n, ovh, flags, st, tiles);
+        ambc_count_launch();
+        k_scan_tiles<<<1, 1024, 0, stream>>>(tiles, L.n_tiles, type, comp, L.n_chunks, chunk, n, ovh, flags, st,
+                                             (uint8_t *)out_dev, out_cap, marker_word, marker_bytes);
+        ambc_count_launch();
+        k_offsets<<<(unsigned)L.n_tiles, 256, 0, stream>>>(type, comp, L.n_chunks, chunk, n, ovh, flags, st, tiles,
+                                                           offs);
+        ambc_count_launch();
+        CUDA_TRY(cudaGetLastError());
+        size_t psmem = 32 + (((size_t)chunk + 15) & ~(size_t)15) + 32;
+        CUDA_TRY(cudaFuncSetAttribute(k_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+        k_pack<<<grid_chunks, AMBC_BLOCK, psmem, stream>>>((const uint8_t *)in_dev, n, chunk, W + L.slots,
+                                                           L.slot_stride, type, comp, offs, st, flags, marker_word,
+                                                           marker_bytes, (uint8_t *)out_dev, out_cap, L.n_chunks);
+        ambc_count_launch();
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(&h_st, st, sizeof h_st, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    } else {
+        // one raw package: header + memcpy + END, no kernel needed beyond the copy engine
+        uint64_t body = (uint64_t)ovh + n + marker_bytes + 12;
+        if (n > 0xFFFFFFFFull) return ambc_fail(AMBC_E_ARG, "raw package over 4 GiB cannot be framed (u32 fields)");
+        if (body > out_cap) return ambc_fail(AMBC_E_CAPACITY, "out too small");
+        uint8_t hdr[18], endp[16];
+        memcpy(hdr, marker, marker_bytes);
+        hdr[marker_bytes] = 255; hdr[marker_bytes + 1] = 0;
+        uint32_t n32 = (uint32_t)n;
+        for (int r = 0; r < 3; r++) memcpy(hdr + marker_bytes + 2 + 4 * r, &n32, 4);
+        memcpy(endp, marker, marker_bytes);
+        memset(endp + marker_bytes, 0, 12);
+        uint8_t *o = (uint8_t *)out_dev;
+        CUDA_TRY(cudaMemcpyAsync(o, hdr, ovh, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(o + ovh, in_dev, n, cudaMemcpyDeviceToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(o + ovh + n, endp, marker_bytes + 12, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemsetAsync(type, 255, L.n_chunks, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        h_st.body_len = body;
+        h_st.n_packages = 1;
+        h_st.usage[0] = 1;
+    }
+    if (h_st.body_len > out_cap) return ambc_fail(AMBC_E_CAPACITY, "ambc_compress_dev: out_cap too small");
+    res->body_len = h_st.body_len;
+    res->first_raw = h_st.first_raw == ~0ull ? -1 : (int64_t)h_st.first_raw;
+    res->n_packages = h_st.n_packages;
+    res->payload_bytes = h_st.payload_bytes;
+    for (int k = 0; k < 5; k++) res->usage[k] = h_st.usage[k];
+    if (native && !(flags & AMBC_F_PER_CHUNK_RAW) && res->first_raw >= 0) res->usage[0] = 1;
+    return AMBC_OK;
+}

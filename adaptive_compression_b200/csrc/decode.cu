@@ -1,0 +1,256 @@
+// decode.cu -- package index walk (host) and the per-package decode kernel.
+// Replaces AdaptiveCompressor._adaptive_decompress (adaptive_compressor.py:396-454).
+#include "ambc_internal.h"
+#include "decode_codec.cuh"
+
+#define RAW_PIECE 65536u
+
+// nominal number of bytes the reference appends for a package, knowable without decoding
+static inline uint64_t nominal_out(uint32_t type, bool known, uint32_t comp, uint32_t orig)
+{
+    if (!known) return comp;                       // copied through (:432-435)
+    switch (type) {
+    case 255: return orig;                         // pad / truncate (compression_methods.py:703-713)
+    case 4: return comp == 0 ? 0 : (comp < orig ? comp : orig); // :621-638
+    default: return comp == 0 ? 0 : orig;          // `if not data: return b''`
+    }
+}
+
+extern "C" int ambc_index_host(const uint8_t *body, uint64_t body_len, const uint8_t *marker, uint32_t mb,
+                               uint64_t orig_size, uint32_t known_mask, ambc_pkg *table, uint64_t table_cap,
+                               uint64_t *n_entries, uint64_t *out_bytes)
+{
+    if (!marker || mb < 1 || mb > 4 || (body_len && !body)) return ambc_fail(AMBC_E_ARG, "ambc_index_host: bad argument");
+    uint64_t pos = 0, o = 0, ne = 0;
+    const uint64_t hdr = mb + 14;
+    while (pos < body_len) {
+        if (pos + hdr > body_len) break;                            // :400-403
+        if (memcmp(body + pos, marker, mb) != 0)                    // :405-407
+            return ambc_fail(AMBC_E_MARKER, "Marker mismatch in chunk header.");
+        uint32_t type = body[pos + mb];
+        uint32_t orig, comp;
+        memcpy(&orig, body + pos + mb + 6, 4);
+        memcpy(&comp, body + pos + mb + 10, 4);
+        pos += hdr;
+        if (type == 0) break;                                       // :422-424
+        if (pos + comp > body_len) break;                           // :425-427
+        bool known = type == 255 || (type < 32 && ((known_mask >> type) & 1u));
+        uint64_t nominal = nominal_out(type, known, comp, orig);
+        uint64_t room = orig_size > o ? orig_size - o : 0;
+        uint64_t emit = nominal < room ? nominal : room;
+        if (emit) {
+            if (!known || type == 255) {
+                // plain bytes (+ zero pad): pieces of at most 64 KiB
+                uint64_t done = 0;
+                while (done < emit) {
+                    uint64_t piece = emit - done < RAW_PIECE ? emit - done : RAW_PIECE;
+                    uint64_t have = comp > done ? comp - done : 0; // payload bytes left for this piece
+                    if (table) {
+                        if (ne >= table_cap) return ambc_fail(AMBC_E_CAPACITY, "ambc_index_host: table too small");
+                        ambc_pkg &e = table[ne];
+                        e.src_off = pos + done; e.dst_off = o + done;
+                        e.comp_len = (uint32_t)(have < piece ? have : piece);
+                        e.orig_len = (uint32_t)piece; e.type = 255; e.out_len = (uint32_t)piece;
+                    }
+                    ne++;
+                    done += piece;
+                }
+            } else {
+                if (table) {
+                    if (ne >= table_cap) return ambc_fail(AMBC_E_CAPACITY, "ambc_index_host: table too small");
+                    ambc_pkg &e = table[ne];
+                    e.src_off = pos; e.dst_off = o; e.comp_len = comp; e.orig_len = orig; e.type = type;
+                    e.out_len = (uint32_t)emit;
+                }
+                ne++;
+            }
+        }
+        o += nominal;
+        pos += comp;
+        if (o >= orig_size) break;                                  // :444-445
+    }
+    if (n_entries) *n_entries = ne;
+    if (out_bytes) *out_bytes = o < orig_size ? o : orig_size;
+    return AMBC_OK;
+}
+
+// ---- kernel ----------------------------------------------------------------------------------
+// Decode one package (block-collective).  src/dst in global memory.  Writes min(produced, cap)
+// bytes to dst and returns produced (or -1 where the reference's codec raises).
+__device__ int decode_package(DecCtx &d, uint32_t type, const uint8_t *__restrict__ src, uint32_t comp,
+                              uint32_t orig, uint8_t *__restrict__ dst, uint32_t cap)
+{
+    const bool fast = comp <= (uint32_t)d.in_cap && orig <= DEC_OUT_CAP;
+    if (type == 255) { // bytes + zero pad, any size up to RAW_PIECE
+        uint32_t done = 0;
+        while (done < cap) {
+            uint32_t piece = min(cap - done, (uint32_t)DEC_OUT_CAP);
+            uint32_t have = comp > done ? min(comp - done, piece) : 0;
+            copy_g2s(d.out, src + done, (int)have);
+            for (uint32_t i = have + threadIdx.x; i < piece; i += AMBC_BLOCK) d.out[i] = 0;
+            __syncthreads();
+            copy_s2g(dst + done, d.out, (int)piece);
+            __syncthreads();
+            done += piece;
+        }
+        return (int)orig;
+    }
+    if (fast) {
+        copy_g2s(d.in, src, (int)comp);
+        for (int i = (int)comp + threadIdx.x; i < (int)dec_r16(comp) + 16; i += AMBC_BLOCK) d.in[i] = 0;
+        __syncthreads();
+        int produced;
+        switch (type) {
+        case 1: produced = dec_rle(d, (int)comp, (int)orig); break;
+        case 2: produced = dec_lz(d, (int)comp, (int)orig); break;
+        case 3: produced = dec_huff(d, (int)comp, (int)orig); break;
+        default: produced = dec_delta(d, (int)comp, (int)orig); break;
+        }
+        if (produced > 0) copy_s2g(dst, d.out, (int)min((uint32_t)produced, cap));
+        __syncthreads();
+        return produced;
+    }
+    // oversized package (never written by the reference's own encoder at <= 8192-byte chunks)
+    volatile int *res = d.red;
+    if (type == 3) {
+        HuffDec h = huffdec_scratch(d.X);
+        int boff; uint32_t nbits;
+        int rc = comp ? huffdec_build(d, h, src, (int)min(comp, 0x7fffffffu), &boff, &nbits) : 0;
+        if (comp == 0) return 0;
+        if (rc < 0) return -1;
+        if (threadIdx.x == 0) {
+            uint32_t o = 0, limit = orig > 1 ? orig : 1;
+            int node = h.root;
+            for (uint32_t q = 0; q < nbits && o < limit; q++) {
+                uint32_t bit = (src[boff + (q >> 3)] >> (7 - (q & 7))) & 1;
+                node = bit ? h.child1[node] : h.child0[node];
+                if (node < h.K) { if (o < cap) dst[o] = (uint8_t)h.lead[node]; o++; node = h.root; }
+            }
+            res[8] = (int)o;
+        }
+    } else if (threadIdx.x == 0) {
+        long r;
+        if (type == 1) r = slow_rle(src, comp, orig, dst, cap);
+        else if (type == 2) r = lz_walk(src, comp, orig, dst, cap);
+        else r = slow_delta(src, comp, orig, dst, cap);
+        res[8] = (int)r;
+    }
+    __syncthreads();
+    int r = res[8];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(AMBC_BLOCK)
+k_decode(const uint8_t *__restrict__ body, const ambc_pkg *__restrict__ table, uint64_t n_entries,
+         uint8_t *__restrict__ out, int in_cap, uint32_t *status)
+{
+    extern __shared__ uint4 smem4[];
+    DecCtx d;
+    decctx_carve(d, (uint8_t *)smem4, in_cap);
+    for (uint64_t i = blockIdx.x; i < n_entries; i += gridDim.x) {
+        const ambc_pkg e = table[i];
+        uint8_t *dst = out + e.dst_off;
+        int produced = decode_package(d, e.type, body + e.src_off, e.comp_len, e.orig_len, dst, e.out_len);
+        // nominal length the index assumed for this package (see nominal_out)
+        uint32_t nominal = e.type == 255 ? e.orig_len
+                         : e.type == 4 ? (e.comp_len == 0 ? 0 : min(e.comp_len, e.orig_len))
+                                       : (e.comp_len == 0 ? 0 : e.orig_len);
+        if (produced < 0) { // codec raised: orig_len zero bytes (:440-442)
+            for (uint32_t k = threadIdx.x; k < e.out_len; k += AMBC_BLOCK) dst[k] = 0;
+            if (threadIdx.x == 0 && status) atomicAdd(&status[0], 1u);
+        } else if ((uint32_t)produced != nominal) {
+            // malformed stream: the reference would shift everything after it; we keep the
+            // grid and zero the gap, and report it
+            for (uint32_t k = (uint32_t)produced + threadIdx.x; k < e.out_len; k += AMBC_BLOCK) dst[k] = 0;
+            if (threadIdx.x == 0 && status) atomicAdd(&status[1], 1u);
+        }
+        __syncthreads();
+    }
+}
+
+// zero [end of the last entry, orig_size) -- adaptive_compressor.py:447-449
+__global__ void k_zero_tail(const ambc_pkg *__restrict__ table, uint64_t n_entries, uint8_t *__restrict__ out,
+                            uint64_t orig_size)
+{
+    uint64_t covered = 0;
+    if (n_entries) { const ambc_pkg e = table[n_entries - 1]; covered = e.dst_off + e.out_len; }
+    for (uint64_t i = covered + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < orig_size;
+         i += (uint64_t)gridDim.x * blockDim.x)
+        out[i] = 0;
+}
+
+extern "C" int ambc_decompress_dev(const void *body_dev, uint64_t body_len, const ambc_pkg *table_dev,
+                                   uint64_t n_entries, void *out_dev, uint64_t orig_size, uint32_t *status_dev,
+                                   void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    (void)body_len;
+    if (orig_size && !out_dev) return ambc_fail(AMBC_E_ARG, "ambc_decompress_dev: null output");
+    if (n_entries == 0) {
+        if (orig_size) CUDA_TRY(cudaMemsetAsync(out_dev, 0, orig_size, stream));
+        return AMBC_OK;
+    }
+    if (!body_dev || !table_dev) return ambc_fail(AMBC_E_ARG, "ambc_decompress_dev: null buffer");
+    k_zero_tail<<<148, 256, 0, stream>>>(table_dev, n_entries, (uint8_t *)out_dev, orig_size);
+    ambc_count_launch();
+    const int in_cap = DEC_OUT_CAP; // payloads the reference's encoder emits are < orig_len <= 8192
+    size_t smem = decctx_smem_bytes(in_cap);
+    CUDA_TRY(cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unsigned grid = (unsigned)min<uint64_t>(n_entries, 0x7fffffffull);
+    k_decode<<<grid, AMBC_BLOCK, smem, stream>>>((const uint8_t *)body_dev, table_dev, n_entries, (uint8_t *)out_dev,
+                                                 in_cap, status_dev);
+    ambc_count_launch();
+    CUDA_TRY(cudaGetLastError());
+    return AMBC_OK;
+}
+
+// ---- codec plug-in batch kernels (CompressionMethod API parity) -------------------------------
+__global__ void __launch_bounds__(AMBC_BLOCK)
+k_codec_decode(int method, const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
+               const uint32_t *__restrict__ orig_len, uint32_t n_items, uint8_t *__restrict__ out,
+               uint64_t out_stride, int32_t *__restrict__ out_len, int in_cap)
+{
+    extern __shared__ uint4 smem4[];
+    DecCtx d;
+    decctx_carve(d, (uint8_t *)smem4, in_cap);
+    for (uint32_t i = blockIdx.x; i < n_items; i += gridDim.x) {
+        uint64_t a = in_off[i], b = in_off[i + 1];
+        uint32_t comp = (uint32_t)(b - a), orig = orig_len[i];
+        uint32_t cap = out_stride > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)out_stride;
+        int produced;
+        if (method == 255) {
+            // NoCompression.decompress: pad / truncate to orig (compression_methods.py:691-713)
+            uint32_t done = 0, want = min(orig, cap);
+            while (done < want) {
+                uint32_t piece = min(want - done, (uint32_t)RAW_PIECE);
+                decode_package(d, 255, in + a + done, comp > done ? comp - done : 0, piece, out + (uint64_t)i * out_stride + done, piece);
+                done += piece;
+            }
+            produced = (int)orig;
+        } else {
+            produced = decode_package(d, (uint32_t)method, in + a, comp, orig, out + (uint64_t)i * out_stride, cap);
+        }
+        if (threadIdx.x == 0) out_len[i] = produced;
+        __syncthreads();
+    }
+}
+
+extern "C" int ambc_codec_decode_batch(int method, const void *in_dev, const uint64_t *in_off_dev,
+                                       const uint32_t *orig_len_dev, uint32_t n_items, void *out_dev,
+                                       uint64_t out_stride, int32_t *out_len_dev, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!(method == 1 || method == 2 || method == 3 || method == 4 || method == 255))
+        return ambc_fail(AMBC_E_ARG, "ambc_codec_decode_batch: unknown method %d", method);
+    if (n_items == 0) return AMBC_OK;
+    if (!in_off_dev || !orig_len_dev || !out_dev || !out_len_dev) return ambc_fail(AMBC_E_ARG, "null buffer");
+    const int in_cap = 2 * AMBC_NMAX + 2048; // any payload the encoders can emit for <= 8192 bytes
+    size_t smem = decctx_smem_bytes(in_cap);
+    CUDA_TRY(cudaFuncSetAttribute(k_codec_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_codec_decode<<<n_items, AMBC_BLOCK, smem, stream>>>(method, (const uint8_t *)in_dev, in_off_dev, orig_len_dev,
+                                                          n_items, (uint8_t *)out_dev, out_stride, out_len_dev, in_cap);
+    ambc_count_launch();
+    CUDA_TRY(cudaGetLastError());
+    return AMBC_OK;
+}

@@ -1,0 +1,370 @@
+// decode_codec.cuh -- per-package decoders.  One CTA (AMBC_BLOCK threads) per package,
+// block-collective functions.  Fast path: payload and output staged in shared memory.
+// Slow path (foreign files with oversized packages): one thread, directly on global memory.
+//
+// Reference behaviour restated (file:line relative to the reference repo):
+//   RLE        compression_methods.py:116-152   (pairs, odd tail ignored, truncate / zero pad)
+//   Dictionary compression_methods.py:236-281   (token walk incl. its quirks, no padding)
+//   Huffman    compression_methods.py:407-470   (tree rebuilt from the table, bit walk)
+//   Delta      compression_methods.py:610-638   (running sum, min(len, orig) bytes)
+//   raw        compression_methods.py:691-713   (truncate / zero pad)
+#pragma once
+#include "common.cuh"
+
+#define DEC_OUT_CAP 8192      // largest orig_len decoded in shared memory
+#define DEC_OUT_SLACK 512     // LZ may overrun orig_len by one match (<= 255 bytes) before truncation
+#define DEC_LUT_BITS 10
+
+struct DecCtx {
+    uint8_t *in;   // staged payload, 16-byte aligned, in_cap + 16 bytes
+    int in_cap;
+    uint8_t *out;  // DEC_OUT_CAP + DEC_OUT_SLACK
+    uint8_t *X;    // scratch: max(2*(in_cap/2+1), 12 KiB)
+    int *red;      // 16 ints
+};
+
+__host__ __device__ inline size_t dec_r16(size_t x) { return (x + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t dec_x_bytes(int in_cap)
+{
+    size_t rle = 2 * ((size_t)in_cap / 2 + 8);
+    return dec_r16(rle < 12288 ? 12288 : rle);
+}
+__host__ __device__ inline size_t decctx_smem_bytes(int in_cap)
+{
+    return dec_r16((size_t)in_cap) + 16 + DEC_OUT_CAP + DEC_OUT_SLACK + dec_x_bytes(in_cap) + 64;
+}
+__device__ inline void decctx_carve(DecCtx &d, uint8_t *base, int in_cap)
+{
+    uint8_t *p = base;
+    d.in = p; p += dec_r16((size_t)in_cap) + 16;
+    d.in_cap = in_cap;
+    d.out = p; p += DEC_OUT_CAP + DEC_OUT_SLACK;
+    d.X = p; p += dec_x_bytes(in_cap);
+    d.red = (int *)p;
+}
+
+// ---- RLE ------------------------------------------------------------------------------------
+// payload in d.in[0..len), writes d.out[0..orig).  Returns bytes produced (0 for an empty
+// payload, :127-128, else orig).  Collective.
+__device__ inline int dec_rle(DecCtx &d, int len, int orig)
+{
+    if (len <= 0) return 0;
+    const int tid = threadIdx.x;
+    const int P = len >> 1; // complete pairs (:132-133)
+    uint16_t *pos = (uint16_t *)d.X; // start offset of pair k, clamped to orig; pos[P] = end
+    const int ppt = (P + AMBC_BLOCK - 1) / AMBC_BLOCK;
+    int sum = 0;
+    for (int k = tid * ppt; k < min(P, (tid + 1) * ppt); k++) sum += d.in[2 * k + 1];
+    int total;
+    int run = block_excl_scan(sum, d.red, &total);
+    for (int k = tid * ppt; k < min(P, (tid + 1) * ppt); k++) {
+        pos[k] = (uint16_t)min(run, orig);
+        run += d.in[2 * k + 1];
+    }
+    if (tid == 0) pos[P] = (uint16_t)min(total, orig);
+    __syncthreads();
+    const int filled = min(total, orig);
+    for (int g = tid; 4 * g < orig; g += AMBC_BLOCK) {
+        int j0 = 4 * g;
+        uint32_t word = 0;
+        if (j0 < filled) {
+            int lo = 0, hi = P; // largest k in [0,P) with pos[k] <= j0
+            while (hi - lo > 1) {
+                int mid = (lo + hi) >> 1;
+                if (pos[mid] <= j0) lo = mid; else hi = mid;
+            }
+            int k = lo;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                int j = j0 + b;
+                if (j < filled) {
+                    while (pos[k + 1] <= j) k++;
+                    word |= (uint32_t)d.in[2 * k] << (8 * b);
+                }
+            }
+        }
+        *(uint32_t *)(d.out + j0) = word; // zero pad beyond `filled` (:145-150)
+    }
+    __syncthreads();
+    return orig;
+}
+
+// ---- Delta ----------------------------------------------------------------------------------
+__device__ inline int dec_delta(DecCtx &d, int len, int orig)
+{
+    if (len <= 0) return 0;
+    const int tid = threadIdx.x;
+    const int m = min(len, orig);
+    const int bpt = ((m + AMBC_BLOCK - 1) / AMBC_BLOCK + 3) & ~3; // bytes per thread
+    const int beg = min(m, tid * bpt), end = min(m, beg + bpt);
+    int sum = 0;
+    for (int i = beg; i < end; i++) sum += d.in[i];
+    int total;
+    int run = block_excl_scan(sum, d.red, &total);
+    for (int i = beg; i < end; i++) {
+        run += d.in[i];
+        d.out[i] = (uint8_t)run;
+    }
+    __syncthreads();
+    return m;
+}
+
+// ---- Dictionary -----------------------------------------------------------------------------
+// Serial token walk with the reference's exact quirks (see oracle/ambc_oracle.c:orc_lz_decompress).
+// Works on any address space (shared for the fast path, global for the slow path).
+__device__ inline int lz_walk(const uint8_t *in, long len, long orig, uint8_t *out, long out_cap)
+{
+    if (len <= 0) return 0;
+    long pos = 0, o = 0;
+    while (pos < len && o < orig) {
+        uint8_t flag = in[pos++];
+        if (flag == 0) {
+            if (pos < len) { uint8_t v = in[pos++]; if (o < out_cap) out[o] = v; o++; }
+        } else if (pos + 2 < len) {
+            long dist = in[pos] | (in[pos + 1] << 8);
+            pos += 2;
+            long length = in[pos++];
+            long start = o - dist;
+            for (long i = 0; i < length; i++) {
+                long idx;
+                if (start + i < o) {
+                    idx = start + i;
+                    if (idx < 0) idx += o; // Python negative index
+                    if (idx < 0) return -1;
+                } else {
+                    if (o == 0) return -1;
+                    idx = o - 1;
+                }
+                if (o < out_cap) out[o] = (idx < out_cap) ? out[idx] : 0;
+                o++;
+            }
+        }
+    }
+    return (int)(o < orig ? o : orig);
+}
+
+__device__ inline int dec_lz(DecCtx &d, int len, int orig)
+{
+    volatile int *res = d.red;
+    if (threadIdx.x == 0) res[8] = lz_walk(d.in, len, orig, d.out, DEC_OUT_CAP + DEC_OUT_SLACK);
+    __syncthreads();
+    int r = res[8];
+    __syncthreads();
+    return r;
+}
+
+// ---- Huffman --------------------------------------------------------------------------------
+struct HuffDec {
+    unsigned long long *nodeW; // [512] node weights (leaves sorted by (weight, symbol), then merges)
+    unsigned long long *key;   // [256] weight << 8 | symbol; dead after the rank sort
+    uint16_t *lead;            // [512] leader symbol of the node (leaf: its symbol)
+    uint16_t *child0, *child1; // [512]
+    uint16_t *lut;             // [1 << DEC_LUT_BITS]: leaf -> 0x8000 | len << 8 | sym ; else node id
+    uint32_t *firstidx;        // [256] first table entry of the symbol
+    uint32_t *lastidx;         // [256] last table entry (overlays lut, dead before it is built)
+    uint32_t *start;           // [AMBC_BLOCK + 4] subsequence start bits (overlays key)
+    uint32_t *cnt;             // [AMBC_BLOCK] symbols per subsequence (overlays key)
+    int K, root;
+};
+__device__ inline HuffDec huffdec_scratch(uint8_t *X) // needs 12288 bytes
+{
+    HuffDec h;
+    h.nodeW = (unsigned long long *)X;            // 0     .. 4096
+    h.key = (unsigned long long *)(X + 4096);     // 4096  .. 6144
+    h.lead = (uint16_t *)(X + 6144);              // 6144  .. 7168
+    h.child0 = (uint16_t *)(X + 7168);            // 7168  .. 8192
+    h.child1 = (uint16_t *)(X + 8192);            // 8192  .. 9216
+    h.lut = (uint16_t *)(X + 9216);               // 9216  .. 11264
+    h.firstidx = (uint32_t *)(X + 11264);         // 11264 .. 12288
+    h.lastidx = (uint32_t *)(X + 9216);
+    h.start = (uint32_t *)(X + 4096);
+    h.cnt = (uint32_t *)(X + 4096 + 4 * (AMBC_BLOCK + 4));
+    h.K = 0; h.root = 0;
+    return h;
+}
+
+// Decode one code starting at bit `pos` of the MSB-first stream `bits` (readable 8 bytes past
+// the last stream byte).  Returns the symbol and its length via *len (0 = no complete code
+// before nbits).
+__device__ __forceinline__ int huff_next(const HuffDec &h, const uint8_t *bits, uint32_t pos, uint32_t nbits, int *len)
+{
+    const uint8_t *p = bits + (pos >> 3);
+    uint32_t w = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+    uint32_t top = (w << (pos & 7)) >> (32 - DEC_LUT_BITS);
+    uint32_t e = h.lut[top];
+    if (e & 0x8000u) {
+        int l = (e >> 8) & 0x7F;
+        if (pos + l > nbits) { *len = 0; return 0; }
+        *len = l;
+        return e & 0xFF;
+    }
+    int node = (int)e;
+    uint32_t q = pos + DEC_LUT_BITS;
+    for (;;) {
+        if (q >= nbits) { *len = 0; return 0; }
+        uint32_t bit = (bits[q >> 3] >> (7 - (q & 7))) & 1;
+        node = bit ? h.child1[node] : h.child0[node];
+        q++;
+        if (node < h.K) { *len = (int)(q - pos); return h.lead[node]; }
+    }
+}
+
+// Parse the table, rebuild the reference's tree (same rule as the encoder) and the lookup
+// table.  in[0..len).  Returns 0, or -1 where the reference raises (IndexError).  On success
+// *bits_off = offset of the bit stream, *nbits = number of stream bits to decode.  Collective.
+__device__ inline int huffdec_build(DecCtx &d, HuffDec &h, const uint8_t *in, int len, int *bits_off, uint32_t *nbits)
+{
+    const int tid = threadIdx.x;
+    const int ne = in[0];
+    // IndexError when a table entry's symbol byte lies past the payload (:430)
+    if (ne > 0 && 1 + 5 * (ne - 1) >= len) return -1;
+    uint32_t *firstidx = h.firstidx, *lastidx = h.lastidx;
+    for (int b = tid; b < 256; b += AMBC_BLOCK) { firstidx[b] = 0xFFFFFFFFu; lastidx[b] = 0; }
+    __syncthreads();
+    for (int e = tid; e < ne; e += AMBC_BLOCK) {
+        int s = in[1 + 5 * e];
+        atomicMin(&firstidx[s], (uint32_t)e);
+        atomicMax(&lastidx[s], (uint32_t)e);
+    }
+    __syncthreads();
+    // key = weight << 8 | sym for present symbols (dict semantics: last value wins, :436)
+    int present = 0;
+    for (int b = tid; b < 256; b += AMBC_BLOCK) {
+        unsigned long long k = ~0ull;
+        if (firstidx[b] != 0xFFFFFFFFu) {
+            int o = 2 + 5 * (int)lastidx[b];
+            uint32_t wgt = 0;
+            for (int t = 0; t < 4; t++) if (o + t < len) wgt |= (uint32_t)in[o + t] << (8 * t);
+            k = ((unsigned long long)wgt << 8) | (unsigned long long)b;
+            present++;
+        }
+        h.key[b] = k;
+    }
+    const int K = block_sum(present, d.red);
+    h.K = K;
+    if (K <= 1) return -1; // heappop on an empty heap / code[-1] of an empty code (:497, :527)
+    for (int b = tid; b < 256; b += AMBC_BLOCK) {
+        unsigned long long k = h.key[b];
+        if (k != ~0ull) {
+            int r = 0;
+            for (int j = 0; j < 256; j++) r += (h.key[j] < k);
+            h.nodeW[r] = k >> 8;
+            h.lead[r] = (uint16_t)b;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int li = 0, mi = K, t = K;
+        for (int it = 0; it < K - 1; it++) {
+            int pick[2];
+#pragma unroll
+            for (int z = 0; z < 2; z++) {
+                bool hasL = li < K, hasM = mi < t;
+                bool takeL;
+                if (hasL && hasM) {
+                    unsigned long long wl = h.nodeW[li], wm = h.nodeW[mi];
+                    takeL = (wl < wm) || (wl == wm && h.lead[li] < h.lead[mi]);
+                } else takeL = hasL;
+                pick[z] = takeL ? li++ : mi++;
+            }
+            h.nodeW[t] = h.nodeW[pick[0]] + h.nodeW[pick[1]];
+            h.lead[t] = h.lead[pick[0]];
+            h.child0[t] = (uint16_t)pick[0];
+            h.child1[t] = (uint16_t)pick[1];
+            t++;
+        }
+    }
+    __syncthreads();
+    h.root = 2 * K - 2;
+    for (int idx = tid; idx < (1 << DEC_LUT_BITS); idx += AMBC_BLOCK) {
+        int node = h.root, l = 0;
+        while (node >= K && l < DEC_LUT_BITS) {
+            int bit = (idx >> (DEC_LUT_BITS - 1 - l)) & 1;
+            node = bit ? h.child1[node] : h.child0[node];
+            l++;
+        }
+        h.lut[idx] = node < K ? (uint16_t)(0x8000u | (l << 8) | h.lead[node]) : (uint16_t)node;
+    }
+    int off = 1 + 5 * ne;
+    uint32_t nb = 0;
+    for (int t = 0; t < 4; t++) if (off + t < len) nb |= (uint32_t)in[off + t] << (8 * t);
+    off += 4;
+    uint32_t avail = off < len ? (uint32_t)(len - off) * 8u : 0u;
+    *bits_off = off;
+    *nbits = nb < avail ? nb : avail;
+    __syncthreads();
+    return 0;
+}
+
+// Fast path: payload in d.in[0..len) (zero padded 16 bytes), output to d.out.  Self-synchronising
+// parallel decode: every thread decodes one bit range; ranges re-align to the previous
+// thread's true end until nothing moves.  Returns symbols produced or -1.  Collective.
+__device__ inline int dec_huff(DecCtx &d, int len, int orig)
+{
+    if (len <= 0) return 0;
+    const int tid = threadIdx.x;
+    HuffDec h = huffdec_scratch(d.X);
+    int boff;
+    uint32_t nbits;
+    if (huffdec_build(d, h, d.in, len, &boff, &nbits) < 0) return -1;
+    const uint8_t *bits = d.in + boff;
+    uint32_t *start = h.start, *cnt = h.cnt;
+    const uint32_t S = max(32u, (nbits + AMBC_BLOCK - 1) / AMBC_BLOCK);
+    if (tid == 0) start[0] = 0;
+    start[tid + 1] = min(nbits, (uint32_t)(tid + 1) * S); // provisional
+    __syncthreads();
+    const uint32_t lim = min(nbits, (uint32_t)(tid + 1) * S);
+    for (int iter = 0; iter <= AMBC_BLOCK; iter++) {
+        uint32_t pos = start[tid], c = 0;
+        while (pos < lim) {
+            int l;
+            huff_next(h, bits, pos, nbits, &l);
+            if (l == 0) { pos = nbits; break; } // incomplete tail code: nothing more decodes
+            pos += l; c++;
+        }
+        if (pos > nbits) pos = nbits;
+        bool changed = start[tid + 1] != pos;
+        __syncthreads();
+        start[tid + 1] = pos;
+        cnt[tid] = c;
+        int any = __syncthreads_or(changed);
+        if (!any) break;
+    }
+    int total;
+    int o = block_excl_scan((int)cnt[tid], d.red, &total);
+    const int limit = max(orig, 1); // stops after the append that reaches orig_len (:464-468)
+    {
+        uint32_t pos = start[tid];
+        while (pos < lim && o < limit) {
+            int l;
+            int sym = huff_next(h, bits, pos, nbits, &l);
+            if (l == 0) break;
+            if (o < DEC_OUT_CAP + DEC_OUT_SLACK) d.out[o] = (uint8_t)sym;
+            pos += l; o++;
+        }
+    }
+    __syncthreads();
+    return min(total, limit);
+}
+
+// ---- slow paths: one thread, global memory, any size -------------------------------------------
+__device__ inline long slow_rle(const uint8_t *in, long len, long orig, uint8_t *out, long cap)
+{
+    if (len <= 0) return 0;
+    long o = 0;
+    for (long i = 0; i + 1 < len && o < orig; i += 2) {
+        uint8_t v = in[i];
+        long c = in[i + 1];
+        for (long k = 0; k < c && o < orig; k++, o++) if (o < cap) out[o] = v;
+    }
+    for (; o < orig; o++) if (o < cap) out[o] = 0;
+    return orig;
+}
+__device__ inline long slow_delta(const uint8_t *in, long len, long orig, uint8_t *out, long cap)
+{
+    if (len <= 0) return 0;
+    long m = len < orig ? len : orig;
+    uint8_t prev = 0;
+    for (long i = 0; i < m; i++) { prev = (uint8_t)(prev + in[i]); if (i < cap) out[i] = prev; }
+    return m;
+}
