@@ -1,0 +1,129 @@
+"""GPU parity, whole body: the CUDA select / scan / pack path and the decode path through the
+C-ABI against the oracle and the golden .ambc files of the unmodified reference."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import inputs
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(b):
+    return hashlib.sha256(b).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from adaptive_compression_b200 import engine
+    engine.require_cuda()
+    return engine
+
+
+def gpu_body(eng, data, chunk, methods=(1, 2, 3, 4), marker=O.FIXED_MARKER, pcr=False):
+    t = eng.to_device(data)
+    o = eng.compress_device(t, chunk, eng.method_mask(methods), 1 if pcr else 0, marker)
+    return o.body.cpu().numpy().tobytes(), eng.package_map(o, len(data), chunk, pcr), o
+
+
+def test_body_matches_golden_reference_files(eng, golden):
+    """body bytes == bytes 47.. of the .ambc the unmodified reference wrote"""
+    cases = {c[0]: c for c in inputs.container_cases()}
+    bad = []
+    for row in golden["container_kat"]:
+        name, data, _ = cases[row["name"]]
+        cfg = row["cfg"]
+        if not data:
+            continue
+        marker = O.FIXED_MARKER
+        if cfg.get("found_marker"):
+            mb, ml = O.find_marker(data, 32)
+            marker = O.marker_aligned(mb, ml)
+        want_file, raw, want_pm = O.compress_file(data, cfg["chunk_size"], tuple(cfg.get("method_ids", (1, 2, 3, 4))),
+                                                  (O.FIXED_MARKER, 32) if not cfg.get("found_marker") else O.find_marker(data, 32),
+                                                  bool(cfg.get("per_chunk_raw")))
+        body, pm, o = gpu_body(eng, data, cfg["chunk_size"], tuple(cfg.get("method_ids", (1, 2, 3, 4))), marker,
+                               bool(cfg.get("per_chunk_raw")))
+        wbody, wpm = O.compress_body(data, cfg["chunk_size"], tuple(cfg.get("method_ids", (1, 2, 3, 4))), marker,
+                                     bool(cfg.get("per_chunk_raw")))
+        if body != wbody or [tuple(p) for p in pm] != [tuple(p) for p in wpm]:
+            bad.append((name, len(body), len(wbody), pm[:6], wpm[:6]))
+            continue
+        if not row["stored_verbatim"]:
+            hs = 43 + len(marker)
+            assert sha(want_file) == row["ambc_sha256"]
+            assert want_file[hs:] == body, name
+            assert [list(p) for p in pm] == row["packages"], name
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("chunk", [512, 1024, 2048, 4096, 8192, 3000])
+def test_body_fuzz_vs_oracle(eng, chunk):
+    r = np.random.RandomState(chunk)
+    bad = []
+    for it in range(6):
+        nch = int(r.randint(3, 40))
+        data = inputs.mixed_file(nch, chunk, 5000 + chunk + it) + inputs.text(int(r.randint(0, chunk)), it)
+        pcr = bool(it % 2)
+        if it == 3:  # a random chunk in the middle: tail-raw rule / per-chunk raw
+            data = data[:chunk * 2] + inputs.rand(chunk, it) + data[chunk * 2:]
+        body, pm, o = gpu_body(eng, data, chunk, pcr=pcr)
+        wbody, wpm = O.compress_body(data, chunk, per_chunk_raw=pcr)
+        if body != wbody:
+            first = next((i for i, (a, b) in enumerate(zip(body, wbody)) if a != b), min(len(body), len(wbody)))
+            bad.append((chunk, it, len(body), len(wbody), first, pm[:8], wpm[:8]))
+            continue
+        out, status = eng.decompress_device(o.body, len(data), body_host=np.frombuffer(body, dtype=np.uint8))
+        if out.cpu().numpy().tobytes() != data or status != [0, 0]:
+            bad.append(("roundtrip", chunk, it, status))
+    assert not bad, bad
+
+
+def test_method_masks(eng):
+    data = inputs.mixed_file(10, 4096, 909)
+    for methods in [(1,), (2,), (3,), (4,), (1, 3), (2, 4), (1, 2, 3, 4), ()]:
+        body, pm, o = gpu_body(eng, data, 4096, methods)
+        wbody, wpm = O.compress_body(data, 4096, methods)
+        assert body == wbody, methods
+        assert [tuple(p) for p in pm] == [tuple(p) for p in wpm], methods
+
+
+def test_decode_reference_files(eng, golden):
+    """the CUDA decoder reads what the reference wrote (via the oracle restatement, pinned by sha256)"""
+    cases = {c[0]: c for c in inputs.container_cases()}
+    for row in golden["container_kat"]:
+        name, data, _ = cases[row["name"]]
+        cfg = row["cfg"]
+        if row["stored_verbatim"] or not data:
+            continue
+        marker = (O.FIXED_MARKER, 32) if not cfg.get("found_marker") else O.find_marker(data, 32)
+        f, raw, _ = O.compress_file(data, cfg["chunk_size"], tuple(cfg.get("method_ids", (1, 2, 3, 4))), marker,
+                                    bool(cfg.get("per_chunk_raw")))
+        assert sha(f) == row["ambc_sha256"]
+        hs = int.from_bytes(f[5:9], "little")
+        body = np.frombuffer(f[hs:], dtype=np.uint8)
+        out, status = eng.decompress_device(eng.to_device(body), len(data), O.marker_aligned(*marker), body_host=body)
+        assert out.cpu().numpy().tobytes() == data, name
+        assert status == [0, 0], name
+
+
+def test_synthetic_corpus_roundtrip_and_oracle(eng):
+    """device-generated corpus (the bench workload): body == oracle on 2 MiB, round trip on 64 MiB"""
+    n = 2 << 20
+    t = eng.synth(n, offset=0)
+    data = t.cpu().numpy().tobytes()
+    o = eng.compress_device(t, 4096)
+    body = o.body.cpu().numpy().tobytes()
+    wbody, wpm = O.compress_body(data, 4096)
+    assert body == wbody
+    assert [tuple(p) for p in eng.package_map(o, n, 4096)] == [tuple(p) for p in wpm]
+    n = 64 << 20
+    t = eng.synth(n, offset=123 * 65536)
+    o = eng.compress_device(t, 4096)
+    out, status = eng.decompress_device(o.body, n)
+    assert status == [0, 0]
+    import torch
+    assert torch.equal(out, t)
+    assert o.first_raw == -1, "bench corpus must have a native winner in every chunk"
