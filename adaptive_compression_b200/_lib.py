@@ -65,6 +65,8 @@ _SIGS = {
     "ambc_find_marker_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint32),
                                        C.POINTER(C.c_uint64), C.c_void_p]),
     "ambc_synth_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),
+    "ambc_enable_timing": (None, [C.c_int]),
+    "ambc_last_timing": (C.c_int, [C.POINTER(C.c_float)]),
     "ambc_host_alloc": (C.c_void_p, [C.c_uint64]),
     "ambc_host_free": (None, [C.c_void_p]),
 }

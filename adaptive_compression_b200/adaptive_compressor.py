@@ -1,0 +1,259 @@
+"""AdaptiveCompressor: the reference's compress / decompress API (adaptive_compressor.py:49-700)
+over the CUDA chunk path.
+
+Byte compatibility follows the reference's CODE: constant 32-bit marker
+FF FF 00 00 (:303-310), 47-byte header (:312-325), 18-byte package headers (:609-621), 16-byte
+END package (:595-607), "rest of the file is one raw package" when a chunk has no winner
+(:586-590), verbatim copy when header+body is larger than the input (:241-247).
+
+What differs, on purpose:
+  * CHUNK_SIZE_CANDIDATES holds ONE size (default 4096, the documented --chunk-size default,
+    README.md:79).  The reference's dynamic multi-size search (:548-584) is not built yet.
+  * only the repo-native methods 1-4 (+255) are loaded; third-party codecs 5-11 are out of scope.
+  * per_chunk_raw=True and use_marker_search=True are labelled extensions (files stay readable by
+    the reference decoder)."""
+import hashlib
+import os
+import struct
+import threading
+import time
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import engine
+from .compression_methods import (DeltaCompression, DictionaryCompression, HuffmanCompression, NoCompression,
+                                  RLECompression)
+from .marker_finder import MarkerFinder
+
+METHOD_NAMES = {1: "RLE", 2: "Dictionary", 3: "Huffman", 4: "Delta", 5: "DEFLATE", 6: "BZIP2", 7: "LZMA",
+                8: "ZStandard", 9: "LZ4", 10: "Brotli", 11: "LZHAM", 255: "No Compression"}
+METHOD_CHUNK_PREFS = {1: (32, 4096), 2: (128, 8192), 3: (32, 8192), 4: (32, 4096), 5: (64, 65536),
+                      6: (1024, 262144), 7: (8192, 524288), 8: (512, 262144), 9: (1024, 65536),
+                      10: (1024, 262144), 11: (1024, 262144), 255: (1, 999999999)}
+
+
+class AdaptiveCompressor:
+    MAGIC_NUMBER = b"AMBC"
+    FORMAT_VERSION = 2
+    CHUNK_SIZE_CANDIDATES = [4096]
+
+    def __init__(self, marker_max_length=32, sample_size=10000, chunk_size=None, methods=None,
+                 disable_methods=None, per_chunk_raw=False, use_marker_search=False):
+        self.marker_finder = MarkerFinder(marker_max_length)
+        self.sample_size = sample_size
+        self.marker_bytes = None
+        self.marker_length = 0
+        self.marker_pattern = ""
+        self.marker_bytes_aligned = b""
+        self.marker_byte_length = 0
+        self.use_multithreading = False
+        self.max_workers = max(1, (os.cpu_count() or 2) - 1)
+        self.progress_callback = None
+        self.per_chunk_raw = bool(per_chunk_raw)
+        self.use_marker_search = bool(use_marker_search)
+        if chunk_size is not None:
+            self.CHUNK_SIZE_CANDIDATES = [int(chunk_size)]
+        self.compression_methods = [RLECompression(), DictionaryCompression(), HuffmanCompression(),
+                                    DeltaCompression(), NoCompression()]
+        if methods is not None:
+            keep = set(int(m) for m in methods) | {255}
+            self.compression_methods = [m for m in self.compression_methods if m.type_id in keep]
+        if disable_methods:
+            drop = set(int(m) for m in disable_methods) - {255}
+            self.compression_methods = [m for m in self.compression_methods if m.type_id not in drop]
+        self.method_lookup = {m.type_id: m for m in self.compression_methods}
+        self.method_names = dict(METHOD_NAMES)
+        self.method_chunk_prefs = dict(METHOD_CHUNK_PREFS)
+        self.chunk_stats = {}
+        self.last_timing = {}
+
+    # ---- no-op knobs kept for API compatibility (adaptive_compressor.py:179-194) ----
+    def set_progress_callback(self, callback):
+        self.progress_callback = callback
+
+    def enable_multithreading(self, max_workers=None):
+        self.use_multithreading = True
+        if max_workers:
+            self.max_workers = max_workers
+        print(f"Multithreading enabled with {self.max_workers} workers")
+
+    def disable_multithreading(self):
+        self.use_multithreading = False
+        print("Multithreading disabled")
+
+    # ---- marker (adaptive_compressor.py:196-219, 303-310) ----
+    def _init_marker(self, marker_bytes, marker_length):
+        self.marker_bytes = bytes(marker_bytes)
+        self.marker_length = marker_length
+        nb = (marker_length + 7) // 8
+        value = int.from_bytes(self.marker_bytes[:nb], "big") >> (8 * nb - marker_length) if marker_length else 0
+        self.marker_pattern = format(value, "0%db" % marker_length) if marker_length else ""
+        self.marker_bytes_aligned = (value << (8 * nb - marker_length)).to_bytes(nb, "big") if nb else b""
+        self.marker_byte_length = nb
+
+    def _find_marker(self, file_data, sample_size):
+        if self.use_marker_search:
+            return self.marker_finder.find_marker(file_data, None)
+        return b"\xff\xff\x00\x00", 32
+
+    # ---- header (adaptive_compressor.py:312-358) ----
+    def _build_header(self, marker_bytes, marker_len, chksum, original_size, compressed_size=0):
+        body = (bytes([marker_len]) + bytes(marker_bytes) + b"\x01" + chksum +
+                struct.pack("<QQ", original_size, compressed_size))
+        hsize = 4 + 1 + 4 + len(body)
+        return self.MAGIC_NUMBER + bytes([self.FORMAT_VERSION]) + struct.pack("<I", hsize) + body
+
+    def _parse_header(self, data):
+        if data[:4] != self.MAGIC_NUMBER:
+            raise ValueError("Magic mismatch")
+        version = data[4]
+        if version > self.FORMAT_VERSION:
+            raise ValueError(f"Unsupported version: {version}")
+        (hdr_size,) = struct.unpack("<I", data[5:9])
+        marker_len = data[9]
+        msize = (marker_len + 7) // 8
+        ctype = data[10 + msize]
+        csum_size = 16 if ctype == 1 else 0
+        p = 11 + msize + csum_size
+        orig_size, comp_size = struct.unpack("<QQ", data[p:p + 16])
+        return {"format_version": version, "header_size": hdr_size, "marker_length": marker_len,
+                "marker_bytes": bytes(data[10:10 + msize]), "checksum_type": ctype,
+                "checksum": bytes(data[11 + msize:p]), "original_size": orig_size, "compressed_size": comp_size}
+
+    # ---- configuration checks ----
+    def _fixed_chunk(self):
+        c = list(self.CHUNK_SIZE_CANDIDATES)
+        if len(c) != 1:
+            raise NotImplementedError("the B200 path runs one chunk size (CHUNK_SIZE_CANDIDATES=[N]); the reference's "
+                                      "dynamic multi-size search is not built yet")
+        if c[0] <= 0:
+            raise ValueError("chunk size must be positive")
+        return int(c[0])
+
+    def _method_mask(self):
+        ids = [m.type_id for m in self.compression_methods if m.type_id != 255]
+        foreign = [i for i in ids if i not in (1, 2, 3, 4)]
+        if foreign:
+            raise NotImplementedError("only the repo-native methods 1-4 run on the B200 path; got %s" % foreign)
+        return engine.method_mask(ids)
+
+    # ---- compress (adaptive_compressor.py:221-255) ----
+    def compress(self, input_file, output_file):
+        start_t = time.time()
+        engine.require_cuda()
+        chunk = self._fixed_chunk()
+        mask = self._method_mask()
+        file_data = np.fromfile(input_file, dtype=np.uint8)
+        n = int(file_data.size)
+        t_read = time.time()
+        md5 = {}
+        th = threading.Thread(target=lambda: md5.setdefault("d", hashlib.md5(file_data).digest()))
+        th.start()  # MD5 is a serial chain; hashlib releases the GIL, so it overlaps the GPU work
+
+        marker_bytes, marker_len = self._find_marker(file_data, self.sample_size)
+        self._init_marker(marker_bytes, marker_len)
+        t_in = torch.from_numpy(file_data).to("cuda") if n else torch.empty(0, dtype=torch.uint8, device="cuda")
+        flags = L.F_PER_CHUNK_RAW if self.per_chunk_raw else 0
+        out = engine.compress_device(t_in, chunk, mask, flags, self.marker_bytes_aligned)
+        if out.first_raw >= 0 and not self.per_chunk_raw and n - out.first_raw * chunk > 0xFFFFFFFF:
+            raise struct.error("'I' format requires 0 <= number <= 4294967295")  # as struct.pack at :617-619
+        self._fill_chunk_stats(out, n, chunk)
+        t_gpu = time.time()
+        th.join()
+        header = self._build_header(marker_bytes[:self.marker_byte_length], marker_len, md5["d"], n, out.body_len)
+        final_size = len(header) + out.body_len
+        if final_size > n:
+            print("Compression bigger than original => store raw.")
+            file_data.tofile(output_file)
+            stats = self._build_stats_raw(n, time.time() - start_t)
+        else:
+            body = out.body.cpu().numpy()
+            with open(output_file, "wb") as f:
+                f.write(header)
+                body.tofile(f)
+            stats = self._calculate_compression_stats(n, final_size, time.time() - start_t)
+        self.last_timing = {"read_s": t_read - start_t, "gpu_s": t_gpu - t_read, "total_s": time.time() - start_t}
+        return stats
+
+    def _fill_chunk_stats(self, out, n, chunk):
+        """same numbers as _init_stats/_update_stats (:457-480) + the END overhead (:393)"""
+        ovh = self.marker_byte_length + 14
+        types = out.types.cpu().numpy()
+        comps = out.comp_lens.cpu().numpy().astype(np.int64)
+        limit = int(out.n_chunks)
+        if out.first_raw >= 0 and not self.per_chunk_raw:
+            limit = int(out.first_raw)
+        t = types[:limit]
+        comp_mask = t != 255
+        origs = np.full(limit, chunk, dtype=np.int64)
+        if limit and limit == int(out.n_chunks):
+            origs[-1] = n - (limit - 1) * chunk
+        usage = {m.type_id: 0 for m in self.compression_methods}
+        for mid in (1, 2, 3, 4):
+            c = int((t == mid).sum())
+            if mid in usage:
+                usage[mid] = c
+        n_comp = int(comp_mask.sum())
+        self.chunk_stats = {
+            "total_chunks": int(out.n_packages),
+            "compressed_chunks": n_comp,
+            "raw_chunks": int(out.n_packages) - n_comp,
+            "method_usage": usage,
+            "bytes_saved": int((origs[comp_mask] - comps[:limit][comp_mask] - ovh).sum()),
+            "original_size": n,
+            "compressed_size_without_overhead": int(comps[:limit][comp_mask].sum()),
+            "overhead_bytes": ovh * n_comp + self.marker_byte_length + 12,
+        }
+
+    def _build_stats_raw(self, original_size, elapsed):
+        tput = original_size / (1024 * 1024 * elapsed) if elapsed > 0 else 0.0
+        chunk_stats = {"total_chunks": 1, "compressed_chunks": 0, "raw_chunks": 1, "method_usage": {},
+                       "bytes_saved": 0, "original_size": original_size,
+                       "compressed_size_without_overhead": original_size, "overhead_bytes": 0}
+        return {"original_size": original_size, "compressed_size": original_size, "ratio": 1.0,
+                "percent_reduction": 0.0, "elapsed_time": elapsed, "throughput_mb_per_sec": tput,
+                "chunk_stats": chunk_stats, "overhead_bytes": 0, "compression_efficiency": 1.0}
+
+    def _calculate_compression_stats(self, orig_size, comp_size, elapsed):
+        if orig_size == 0:
+            ratio, pr = 1.0, 0.0
+        else:
+            ratio = comp_size / orig_size
+            pr = (1.0 - ratio) * 100.0
+        throughput = orig_size / (1024 * 1024 * elapsed) if elapsed > 0 else 0.0
+        eff = 1.0
+        cs = self.chunk_stats
+        if cs["compressed_chunks"] > 0:
+            approx = 0
+            for mid, cnt in cs["method_usage"].items():
+                if mid != 255 and cnt > 0:
+                    approx += (cnt / cs["total_chunks"]) * orig_size
+            if approx > 0:
+                eff = cs["compressed_size_without_overhead"] / approx
+        return {"original_size": orig_size, "compressed_size": comp_size, "ratio": ratio, "percent_reduction": pr,
+                "elapsed_time": elapsed, "throughput_mb_per_sec": throughput, "chunk_stats": cs,
+                "overhead_bytes": cs.get("overhead_bytes", 0), "compression_efficiency": eff}
+
+    # ---- decompress (adaptive_compressor.py:286-301) ----
+    def decompress(self, input_file, output_file):
+        start_t = time.time()
+        engine.require_cuda()
+        cdata = np.fromfile(input_file, dtype=np.uint8)
+        hdr = self._parse_header(cdata.tobytes()[:64] if cdata.size >= 64 else cdata.tobytes())
+        self._init_marker(hdr["marker_bytes"], hdr["marker_length"])
+        body = cdata[hdr["header_size"]:]
+        known = engine.method_mask([m.type_id for m in self.compression_methods if m.type_id != 255])
+        t_body = torch.from_numpy(body).to("cuda") if body.size else torch.empty(0, dtype=torch.uint8, device="cuda")
+        out, status = engine.decompress_device(t_body, hdr["original_size"], self.marker_bytes_aligned, known,
+                                               body_host=body)
+        decompressed = out.cpu().numpy()
+        decompressed.tofile(output_file)
+        self.last_status = status
+        if hashlib.md5(decompressed).digest() != hdr["checksum"]:
+            raise ValueError("Checksum mismatch => possibly corrupted file.")
+        elapsed = time.time() - start_t
+        dsize = int(decompressed.size)
+        return {"compressed_size": int(cdata.size), "decompressed_size": dsize, "elapsed_time": elapsed,
+                "throughput_mb_per_sec": dsize / (1024 * 1024 * elapsed) if elapsed > 0 else 0.0}

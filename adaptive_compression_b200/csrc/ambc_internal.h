@@ -19,3 +19,13 @@ void ambc_count_launch();
         if (e__ != cudaSuccess)                                                                           \
             return ambc_fail(AMBC_E_CUDA, "%s:%d: %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
     } while (0)
+
+// optional per-kernel timing (ambc_enable_timing)
+struct AmbcTiming {
+    bool on = false;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float ms[4] = {0, 0, 0, 0};
+    bool pending_c = false, pending_d = false;
+};
+AmbcTiming &ambc_timing();
+void ambc_timing_mark(int idx, cudaStream_t s);

@@ -18,6 +18,35 @@ int ambc_fail(int code, const char *fmt, ...)
 }
 void ambc_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+static AmbcTiming g_timing;
+AmbcTiming &ambc_timing() { return g_timing; }
+void ambc_timing_mark(int idx, cudaStream_t s)
+{
+    if (!g_timing.on) return;
+    if (!g_timing.ev[idx]) cudaEventCreate(&g_timing.ev[idx]);
+    cudaEventRecord(g_timing.ev[idx], s);
+}
+extern "C" void ambc_enable_timing(int on) { g_timing.on = on != 0; }
+extern "C" int ambc_last_timing(float *ms4)
+{
+    AmbcTiming &t = g_timing;
+    if (!ms4) return AMBC_E_ARG;
+    if (t.pending_c && t.ev[0] && t.ev[3]) {
+        cudaEventSynchronize(t.ev[3]);
+        cudaEventElapsedTime(&t.ms[0], t.ev[0], t.ev[1]);
+        cudaEventElapsedTime(&t.ms[1], t.ev[1], t.ev[2]);
+        cudaEventElapsedTime(&t.ms[2], t.ev[2], t.ev[3]);
+        t.pending_c = false;
+    }
+    if (t.pending_d && t.ev[4] && t.ev[5]) {
+        cudaEventSynchronize(t.ev[5]);
+        cudaEventElapsedTime(&t.ms[3], t.ev[4], t.ev[5]);
+        t.pending_d = false;
+    }
+    for (int i = 0; i < 4; i++) ms4[i] = t.ms[i];
+    return AMBC_OK;
+}
+
 extern "C" const char *ambc_last_error(void) { return g_err; }
 extern "C" int ambc_version(void) { return 100; }
 extern "C" uint64_t ambc_launch_count(void) { return g_launches.load(); }

@@ -406,11 +406,13 @@ extern "C" int ambc_compress_dev(const void *in_dev, uint64_t n, uint32_t chunk,
     if (native) {
         size_t smem = chunkctx_smem_bytes((int)chunk, (int)chunk);
         CUDA_TRY(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ambc_timing_mark(0, stream);
         k_select<<<grid_chunks, AMBC_BLOCK, smem, stream>>>((const uint8_t *)in_dev, n, chunk, method_mask, ovh,
                                                             W + L.slots, L.slot_stride, type, comp,
                                                             &st->first_raw, L.n_chunks);
         ambc_count_launch();
         CUDA_TRY(cudaGetLastError());
+        ambc_timing_mark(1, stream);
         k_sizes<<<(unsigned)L.n_tiles, 256, 0, stream>>>(type, comp, L.n_chunks, chunk, n, ovh, flags, st, tiles);
         ambc_count_launch();
         k_scan_tiles<<<1, 1024, 0, stream>>>(tiles, L.n_tiles, type, comp, L.n_chunks, chunk, n, ovh, flags, st,
@@ -420,6 +422,7 @@ extern "C" int ambc_compress_dev(const void *in_dev, uint64_t n, uint32_t chunk,
                                                            offs);
         ambc_count_launch();
         CUDA_TRY(cudaGetLastError());
+        ambc_timing_mark(2, stream);
         size_t psmem = 32 + (((size_t)chunk + 15) & ~(size_t)15) + 32;
         CUDA_TRY(cudaFuncSetAttribute(k_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
         k_pack<<<grid_chunks, AMBC_BLOCK, psmem, stream>>>((const uint8_t *)in_dev, n, chunk, W + L.slots,
@@ -427,6 +430,8 @@ extern "C" int ambc_compress_dev(const void *in_dev, uint64_t n, uint32_t chunk,
                                                            marker_bytes, (uint8_t *)out_dev, out_cap, L.n_chunks);
         ambc_count_launch();
         CUDA_TRY(cudaGetLastError());
+        ambc_timing_mark(3, stream);
+        ambc_timing().pending_c = ambc_timing().on;
         CUDA_TRY(cudaMemcpyAsync(&h_st, st, sizeof h_st, cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
     } else {

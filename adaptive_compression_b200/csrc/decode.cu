@@ -192,6 +192,7 @@ extern "C" int ambc_decompress_dev(const void *body_dev, uint64_t body_len, cons
         return AMBC_OK;
     }
     if (!body_dev || !table_dev) return ambc_fail(AMBC_E_ARG, "ambc_decompress_dev: null buffer");
+    ambc_timing_mark(4, stream);
     k_zero_tail<<<148, 256, 0, stream>>>(table_dev, n_entries, (uint8_t *)out_dev, orig_size);
     ambc_count_launch();
     const int in_cap = DEC_OUT_CAP; // payloads the reference's encoder emits are < orig_len <= 8192
@@ -202,6 +203,8 @@ extern "C" int ambc_decompress_dev(const void *body_dev, uint64_t body_len, cons
                                                  in_cap, status_dev);
     ambc_count_launch();
     CUDA_TRY(cudaGetLastError());
+    ambc_timing_mark(5, stream);
+    ambc_timing().pending_d = ambc_timing().on;
     return AMBC_OK;
 }
 

@@ -210,6 +210,15 @@ int ambc_find_marker_dev(const void *in_dev, uint64_t n, uint32_t max_len, uint3
 /* fills out_dev[0..n) with bytes [offset, offset+n) of corpus (seed, kind_mask) */
 int ambc_synth_dev(void *out_dev, uint64_t offset, uint64_t n, uint64_t seed, uint32_t kind_mask, void *stream);
 
+/* ------------------------------------------------------------------ */
+/* measurement support (bench.py): per-kernel device times              */
+/* ------------------------------------------------------------------ */
+/* when enabled, ambc_compress_dev / ambc_decompress_dev bracket their kernels with CUDA events
+ * on the caller's stream; ambc_last_timing returns the most recent call's milliseconds:
+ * ms[0] k_select, ms[1] size scan (3 small kernels), ms[2] k_pack, ms[3] k_decode (+tail zero). */
+void ambc_enable_timing(int on);
+int ambc_last_timing(float *ms4);
+
 /* pinned host memory helpers for callers without their own allocator */
 void *ambc_host_alloc(uint64_t bytes);
 void ambc_host_free(void *p);

@@ -33,7 +33,7 @@ static void *compress_worker(void *arg)
 {
     slice_job *j = (slice_job *)arg;
     long cands[1] = { j->chunk };
-    j->out_len = orc_compress_body(j->data, j->total, cands, 1, j->methods, j->n_methods, k_marker, 4, 1,
+    j->out_len = orc_compress_body(j->data, j->total, cands, 1, j->methods, j->n_methods, k_marker, 4, 0,
                                    j->out, NULL, NULL, NULL, 0, &j->n_pkgs);
     return NULL;
 }

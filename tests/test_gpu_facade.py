@@ -1,0 +1,153 @@
+"""GPU: the reference-facing Python surface (AdaptiveCompressor, CompressionMethod plug-ins, CLI)
+produces the reference's own files (golden sha256), stats and errors."""
+import hashlib
+import os
+import subprocess
+import sys
+
+import pytest
+
+import inputs
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def sha(b):
+    return hashlib.sha256(b).hexdigest()
+
+
+def _compressor(cfg):
+    from adaptive_compression_b200 import AdaptiveCompressor
+    return AdaptiveCompressor(chunk_size=cfg["chunk_size"], methods=cfg.get("method_ids"),
+                              per_chunk_raw=bool(cfg.get("per_chunk_raw")),
+                              use_marker_search=bool(cfg.get("found_marker")))
+
+
+def test_files_equal_reference_files(golden, tmp_path):
+    """.ambc written by the facade == the file the unmodified reference wrote (sha256), stats equal"""
+    cases = {c[0]: c for c in inputs.container_cases()}
+    for row in golden["container_kat"]:
+        name, data, _ = cases[row["name"]]
+        src, dst, back = tmp_path / "in.bin", tmp_path / "out.ambc", tmp_path / "back.bin"
+        src.write_bytes(data)
+        c = _compressor(row["cfg"])
+        stats = c.compress(str(src), str(dst))
+        out = dst.read_bytes()
+        assert len(out) == row["ambc_len"] and sha(out) == row["ambc_sha256"], name
+        g = row["stats"]
+        for k in ("original_size", "compressed_size", "ratio", "percent_reduction", "overhead_bytes",
+                  "compression_efficiency"):
+            assert stats[k] == pytest.approx(g[k], rel=1e-12, abs=1e-12), (name, k, stats[k], g[k])
+        gcs = g["chunk_stats"]
+        for k in ("total_chunks", "compressed_chunks", "raw_chunks", "bytes_saved", "original_size",
+                  "compressed_size_without_overhead", "overhead_bytes"):
+            assert stats["chunk_stats"][k] == gcs[k], (name, k, stats["chunk_stats"][k], gcs[k])
+        assert {str(k): v for k, v in stats["chunk_stats"]["method_usage"].items()} == gcs["method_usage"], name
+        if not row["stored_verbatim"]:
+            d = c.decompress(str(dst), str(back))
+            assert back.read_bytes() == data, name
+            assert d["decompressed_size"] == len(data) and d["compressed_size"] == len(out)
+            assert O.decompress_file(out) == data  # and the oracle's reference decoder reads our file
+
+
+def test_error_conventions(tmp_path):
+    from adaptive_compression_b200 import AdaptiveCompressor
+    data = inputs.mixed_file(4, 4096, 11)
+    src, dst, back = tmp_path / "a", tmp_path / "a.ambc", tmp_path / "b"
+    src.write_bytes(data)
+    c = AdaptiveCompressor()
+    c.compress(str(src), str(dst))
+    good = bytearray(dst.read_bytes())
+    bad = bytearray(good); bad[0] = ord("X")
+    dst.write_bytes(bad)
+    with pytest.raises(ValueError, match="Magic mismatch"):
+        c.decompress(str(dst), str(back))
+    bad = bytearray(good); bad[4] = 9
+    dst.write_bytes(bad)
+    with pytest.raises(ValueError, match="Unsupported version: 9"):
+        c.decompress(str(dst), str(back))
+    bad = bytearray(good); bad[47] ^= 1
+    dst.write_bytes(bad)
+    with pytest.raises(ValueError, match="Marker mismatch in chunk header."):
+        c.decompress(str(dst), str(back))
+    bad = bytearray(good); bad[47 + 18 + 30] ^= 0x55  # payload corruption -> checksum error after the write
+    dst.write_bytes(bad)
+    with pytest.raises(ValueError, match="Checksum mismatch"):
+        c.decompress(str(dst), str(back))
+    assert back.exists()
+    with pytest.raises(NotImplementedError):
+        c2 = AdaptiveCompressor(); c2.CHUNK_SIZE_CANDIDATES = [8192, 4096]; c2.compress(str(src), str(dst))
+
+
+def test_plugin_objects():
+    from adaptive_compression_b200 import (DeltaCompression, DictionaryCompression, HuffmanCompression,
+                                           NoCompression, RLECompression)
+    A = inputs.survey_inputs()["A"]  # compression_methods.py:719 self-test input
+    sizes = {}
+    for cls in (RLECompression, DictionaryCompression, HuffmanCompression, DeltaCompression, NoCompression):
+        m = cls()
+        p = m.compress(A)
+        sizes[m.type_id] = len(p)
+        assert m.decompress(p, len(A)) == A
+        assert m.should_use(A) in (True, False)
+        assert m.calculate_overhead() == 0
+    assert sizes == {1: 322, 2: 74, 3: 123, 4: 420, 255: 420}  # SURVEY.md §4 self-test sizes
+    with pytest.raises(IndexError):
+        HuffmanCompression().compress(b"z" * 300)
+    with pytest.raises(ValueError):
+        HuffmanCompression().compress(bytes(range(256)) * 4)
+    assert RLECompression().compress(b"") == b"" and NoCompression().decompress(b"abc", 5) == b"abc\0\0"
+
+
+def test_cli_roundtrip(tmp_path):
+    data = inputs.mixed_file(6, 4096, 21) + inputs.text(500, 22)
+    src, dst, back = tmp_path / "in.csv", tmp_path / "o.ambc", tmp_path / "b.csv"
+    src.write_bytes(data)
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "main.py"), "compress", str(src), str(dst), "--chunk-size",
+                        "4096", "--disable-methods", "deflate,bzip2,lzma", "--no-history"], capture_output=True,
+                       text=True, env=env, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Compression completed successfully." in r.stdout
+    want, raw, _ = O.compress_file(data, 4096)
+    assert dst.read_bytes() == want
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "main.py"), "decompress", str(dst), str(back)],
+                       capture_output=True, text=True, env=env, cwd=str(tmp_path))
+    assert r.returncode == 0 and back.read_bytes() == data, r.stdout + r.stderr
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "main.py"), "decompress", str(src), str(back)],
+                       capture_output=True, text=True, env=env, cwd=str(tmp_path))
+    assert r.returncode == 1 and "Error during decompression: Magic mismatch" in r.stdout
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "main.py"), "compress", str(src), str(dst), "--methods",
+                        "rle", "--chunk-size", "1024", "--no-history"], capture_output=True, text=True, env=env,
+                       cwd=str(tmp_path))
+    assert r.returncode == 0
+    want, raw, _ = O.compress_file(data, 1024, (1,))
+    assert dst.read_bytes() == want
+
+
+def test_host_buffer_abi(tmp_path):
+    """ambc_compress_host / ambc_decompress_host (the e2e entry points) on numpy buffers"""
+    import ctypes as C
+    import numpy as np
+    from adaptive_compression_b200 import _lib as L
+    lib = L.lib()
+    data = np.frombuffer(inputs.mixed_file(20, 4096, 31) + inputs.text(999, 32), dtype=np.uint8)
+    bound = lib.ambc_compress_bound(data.size, 4096, 4)
+    body = np.empty(bound, dtype=np.uint8)
+    mt = np.empty(data.size // 4096 + 2, dtype=np.uint8)
+    mc = np.empty(data.size // 4096 + 2, dtype=np.uint32)
+    res = L.CompressResult()
+    L.check(lib.ambc_compress_host(C.c_void_p(data.ctypes.data), data.size, 4096, L.NATIVE_MASK, 0, b"\xff\xff\x00\x00", 4,
+                                   C.c_void_p(body.ctypes.data), bound, C.c_void_p(mt.ctypes.data),
+                                   C.c_void_p(mc.ctypes.data), C.byref(res)))
+    want, pm = O.compress_body(data.tobytes(), 4096)
+    assert body[:res.body_len].tobytes() == want
+    k = res.first_raw if res.first_raw >= 0 else res.n_chunks
+    assert [int(x) for x in mt[:k]] == [p[0] for p in pm[:k]] and len(pm) == res.n_packages
+    back = np.empty(data.size, dtype=np.uint8)
+    st = (C.c_uint32 * 2)()
+    L.check(lib.ambc_decompress_host(C.c_void_p(body.ctypes.data), res.body_len, b"\xff\xff\x00\x00", 4, L.NATIVE_MASK,
+                                     C.c_void_p(back.ctypes.data), data.size, st))
+    assert (back == data).all() and list(st) == [0, 0]
