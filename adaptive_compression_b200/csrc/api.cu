@@ -47,6 +47,16 @@ extern "C" int ambc_last_timing(float *ms4)
     return AMBC_OK;
 }
 
+int ambc_lz_levels_compress(const int *levels, int n);
+int ambc_lz_levels_codec(const int *levels, int n);
+// experiment knob (not part of include/ambc.h): n-gram levels of the Dictionary match search
+extern "C" int ambc_set_lz_levels(const int *levels, int n)
+{
+    if (ambc_lz_levels_compress(levels, n) || ambc_lz_levels_codec(levels, n))
+        return ambc_fail(AMBC_E_ARG, "ambc_set_lz_levels: need ascending levels starting at 3, each <= 16, at most 8");
+    return AMBC_OK;
+}
+
 extern "C" const char *ambc_last_error(void) { return g_err; }
 extern "C" int ambc_version(void) { return 100; }
 extern "C" uint64_t ambc_launch_count(void) { return g_launches.load(); }

@@ -24,8 +24,13 @@ struct ChunkCtx {
     uint32_t *bmask;   // run-boundary bitmap, ceil(n/32) words
     uint32_t *reach;   // token-start bitmap, ceil(n/32) words
     uint8_t *estart;   // per 32-block chain entry offset
-    int *red;          // 16 ints of reduction scratch (8-byte aligned)
+    int *red;          // 32 ints of reduction scratch (8-byte aligned)
 };
+
+// scratch region X: LZ per-warp bucket counters, or 16 KiB for the other users
+#define AMBC_XBYTES ((AMBC_WARPS * AMBC_NBUCKET * 2) > 16384 ? (AMBC_WARPS * AMBC_NBUCKET * 2) : 16384)
+#define AMBC_BPT (AMBC_NBUCKET / AMBC_BLOCK) // buckets per thread in the counter scan
+static_assert(AMBC_BPT >= 2 && AMBC_BPT % 2 == 0 && AMBC_BPT * AMBC_BLOCK == AMBC_NBUCKET, "bucket scan layout");
 
 // shared-memory bytes of a ChunkCtx for chunk size N and payload capacity pcap
 __host__ __device__ inline size_t r16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -38,13 +43,13 @@ __host__ __device__ inline size_t chunkctx_smem_bytes(int N, int pcap)
            + r16((size_t)pcap) + 16           // pay
            + r16(sorted_b)                    // sorted
            + r16(2 * (AMBC_NBUCKET + 1))      // bstart
-           + 16384 + 64                       // X
+           + AMBC_XBYTES + 64                 // X
            + r16((size_t)N)                   // mlen
            + r16(2 * (size_t)N)               // mpos
            + 1024                             // hist
            + r16(nb * 4) * 2                  // bmask, reach
            + r16(nb)                          // estart
-           + 64;                              // red
+           + 128;                             // red
 }
 
 __device__ inline void chunkctx_carve(ChunkCtx &c, uint8_t *base, int N, int pcap)
@@ -57,7 +62,7 @@ __device__ inline void chunkctx_carve(ChunkCtx &c, uint8_t *base, int N, int pca
     c.pay = p; p += r16((size_t)pcap) + 16;
     c.sorted = (uint16_t *)p; p += r16(sorted_b);
     c.bstart = (uint16_t *)p; p += r16(2 * (AMBC_NBUCKET + 1));
-    c.X = p; p += 16384 + 64;
+    c.X = p; p += AMBC_XBYTES + 64;
     c.mlen = p; p += r16((size_t)N);
     c.mpos = (uint16_t *)p; p += r16(2 * (size_t)N);
     c.hist = (uint32_t *)p; p += 1024;
@@ -321,9 +326,48 @@ __device__ inline int chunk_delta_encode(ChunkCtx &c)
 // ---------------------------------------------------------------------------------------
 // Dictionary / greedy LZ77 (compression_methods.py:195-234, 283-313)
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t lz_hash(uint32_t trigram)
+// Levels of the top-down match search: n-gram lengths, ascending.  A position is searched in
+// the bucket of its LZ_LEVELS[k]-gram only if no earlier position shares its
+// LZ_LEVELS[k+1]-gram, so its longest match is at most LZ_LEVELS[k+1]-1 bytes and the ascending
+// scan can stop at the first candidate of that length.  Any level set starting at 3 is exact;
+// the set only changes how many candidates are visited.
+// (tunable at run time for experiments: ambc_set_lz_levels / env AMBC_LZ_LEVELS)
+#define LZ_MAX_LEVELS 8
+static __device__ __constant__ int LZ_LEVELS[LZ_MAX_LEVELS] = {3, 4, 6, 10, 0, 0, 0, 0};
+static __device__ __constant__ int LZ_NLEVELS = 4;
+// per-translation-unit setter (the constants are TU-local without relocatable device code)
+static inline int lz_levels_upload(const int *levels, int n)
 {
-    return (trigram * 2654435761u) >> (32 - AMBC_HB);
+    int buf[LZ_MAX_LEVELS] = {0};
+    if (n < 1 || n > LZ_MAX_LEVELS || levels[0] != 3) return -1;
+    for (int i = 0; i < n; i++) {
+        if (levels[i] > 16 || (i && levels[i] <= levels[i - 1])) return -1;
+        buf[i] = levels[i];
+    }
+    if (cudaMemcpyToSymbol(LZ_LEVELS, buf, sizeof buf) != cudaSuccess) return -1;
+    if (cudaMemcpyToSymbol(LZ_NLEVELS, &n, sizeof n) != cudaSuccess) return -1;
+    return 0;
+}
+
+// hash of the L-gram at shared-memory address s (L <= 16)
+__device__ __forceinline__ uint32_t lz_hash_l(const uint8_t *s, int L)
+{
+    uintptr_t a = (uintptr_t)s;
+    const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3) * 8;
+    uint32_t w0 = w[0], w1 = w[1];
+    uint32_t x = __funnelshift_r(w0, w1, sh);
+    if (L < 4) return ((x & 0xFFFFFFu) * 2654435761u) >> (32 - AMBC_HB);
+    uint32_t h = x * 2654435761u;
+    int rem = L - 4, k = 1;
+    while (rem > 0) {
+        uint32_t w2 = w[k + 1];
+        x = __funnelshift_r(w1, w2, sh);
+        if (rem < 4) x &= (1u << (8 * rem)) - 1;
+        h = (h ^ (h >> 15) ^ x) * 2246822519u;
+        w1 = w2; k++; rem -= 4;
+    }
+    return (h ^ (h >> 13)) * 3266489917u >> (32 - AMBC_HB);
 }
 
 // Lower bound of the Dictionary payload for n bytes: the first token is a literal, every
@@ -335,127 +379,226 @@ __host__ __device__ inline int lz_lower_bound(int n)
     return 2 + 4 * ((n - 1) / 32) + (2 * r < 4 ? 2 * r : 4);
 }
 
+// Stable bucket sort of positions [0, P) by the hash of their L-gram: c.sorted (ascending
+// positions inside each bucket) and c.bstart.  Uses c.X as [AMBC_WARPS][AMBC_NBUCKET] counters.
+// Collective.
+__device__ inline void lz_bucket_sort(ChunkCtx &c, int P, int L)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint16_t *cnt = (uint16_t *)c.X;
+    for (int i = tid; i < AMBC_WARPS * AMBC_NBUCKET * 2 / 16; i += AMBC_BLOCK)
+        ((uint4 *)cnt)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    const int Q = ((P + AMBC_BLOCK - 1) / AMBC_BLOCK) * 32; // positions per warp
+    const int wbeg = wid * Q, wend = min(P, wbeg + Q);
+    uint16_t *mycnt = cnt + wid * AMBC_NBUCKET;
+    for (int base = wbeg; base < wend; base += 32) { // pass 1: per-warp bucket counts
+        int p = base + lane;
+        bool valid = p < wend;
+        uint32_t h = valid ? lz_hash_l(c.sd + p, L) : (uint32_t)(AMBC_NBUCKET + lane);
+        uint32_t peers = __match_any_sync(FULL_MASK, h);
+        uint32_t prior = valid ? mycnt[h] : 0;
+        __syncwarp();
+        if (valid && lane == 31 - __clz(peers)) mycnt[h] = (uint16_t)(prior + __popc(peers));
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // exclusive scan in (bucket-major, warp-minor) order; thread owns AMBC_BPT buckets
+        constexpr int NW = AMBC_BPT / 2; // 32-bit words (two u16 counters) per warp row
+        uint32_t v[AMBC_WARPS][NW];
+#pragma unroll
+        for (int w = 0; w < AMBC_WARPS; w++) {
+            const uint32_t *src = (const uint32_t *)(cnt + w * AMBC_NBUCKET + AMBC_BPT * tid);
+#pragma unroll
+            for (int k = 0; k < NW; k++) v[w][k] = src[k];
+        }
+        uint32_t run = 0;
+#pragma unroll
+        for (int hh = 0; hh < AMBC_BPT; hh++) {
+#pragma unroll
+            for (int w = 0; w < AMBC_WARPS; w++) {
+                uint32_t word = v[w][hh >> 1];
+                uint32_t x = (hh & 1) ? (word >> 16) : (word & 0xFFFF);
+                v[w][hh >> 1] = (hh & 1) ? ((word & 0xFFFF) | (run << 16)) : ((word & 0xFFFF0000u) | run);
+                run += x;
+            }
+        }
+        int tot;
+        uint32_t off = (uint32_t)block_excl_scan((int)run, c.red, &tot);
+        uint32_t off2 = off | (off << 16);
+#pragma unroll
+        for (int w = 0; w < AMBC_WARPS; w++) {
+            uint32_t *dst = (uint32_t *)(cnt + w * AMBC_NBUCKET + AMBC_BPT * tid);
+#pragma unroll
+            for (int k = 0; k < NW; k++) { v[w][k] += off2; dst[k] = v[w][k]; }
+        }
+        uint32_t *bs = (uint32_t *)(c.bstart + AMBC_BPT * tid);
+#pragma unroll
+        for (int k = 0; k < NW; k++) bs[k] = v[0][k];
+        if (tid == 0) c.bstart[AMBC_NBUCKET] = (uint16_t)P;
+    }
+    __syncthreads();
+    for (int base = wbeg; base < wend; base += 32) { // pass 2: ordered scatter
+        int p = base + lane;
+        bool valid = p < wend;
+        uint32_t h = valid ? lz_hash_l(c.sd + p, L) : (uint32_t)(AMBC_NBUCKET + lane);
+        uint32_t peers = __match_any_sync(FULL_MASK, h);
+        uint32_t prior = valid ? mycnt[h] : 0;
+        __syncwarp();
+        if (valid) {
+            c.sorted[prior + __popc(peers & ((1u << lane) - 1))] = (uint16_t)p;
+            if (lane == 31 - __clz(peers)) mycnt[h] = (uint16_t)(prior + __popc(peers));
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+}
+
+#ifndef LZ_COOP_THRESHOLD
+#define LZ_COOP_THRESHOLD 24 // buckets with more candidates than this are scanned by a whole warp
+#endif
+
+// common-prefix length (bytes, up to 4*nw) of the data at shared address s with the words pw[]
+__device__ __forceinline__ int lz_match_len(const uint8_t *s, const uint32_t (&pw)[8], int nw)
+{
+    uintptr_t a = (uintptr_t)s;
+    const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3) * 8;
+    uint32_t lo_w = w[0];
+    int len = 4 * nw;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (k < nw) {
+            uint32_t hi_w = w[k + 1];
+            uint32_t x = __funnelshift_r(lo_w, hi_w, sh) ^ pw[k];
+            if (x) { len = 4 * k + ((__ffs(x) - 1) >> 3); break; }
+            lo_w = hi_w;
+        }
+    }
+    return len;
+}
+
 // Payload -> c.pay (as far as pcap allows).  Returns the exact payload length.  Collective.
 __device__ inline int chunk_lz_encode(ChunkCtx &c)
 {
-    const int n = c.n, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int P = n - 2; // positions that start a trigram: 0 .. n-3
-    uint16_t *cnt = (uint16_t *)c.X; // [AMBC_WARPS][AMBC_NBUCKET]
-
-    if (P > 0) {
-        // ---- stable bucket sort of positions by trigram hash ----------------------------
-        for (int i = tid; i < AMBC_WARPS * AMBC_NBUCKET * 2 / 16; i += AMBC_BLOCK)
-            ((uint4 *)cnt)[i] = make_uint4(0, 0, 0, 0);
-        __syncthreads();
-        const int Q = ((P + AMBC_BLOCK - 1) / AMBC_BLOCK) * 32; // positions per warp
-        const int wbeg = wid * Q, wend = min(P, wbeg + Q);
-        uint16_t *mycnt = cnt + wid * AMBC_NBUCKET;
-        for (int base = wbeg; base < wend; base += 32) { // pass 1: per-warp bucket counts
-            int p = base + lane;
-            bool valid = p < wend;
-            uint32_t h = valid ? lz_hash(lds_u32u(c.sd + p) & 0xFFFFFFu) : (uint32_t)(AMBC_NBUCKET + lane);
-            uint32_t peers = __match_any_sync(FULL_MASK, h);
-            uint32_t prior = valid ? mycnt[h] : 0;
-            __syncwarp();
-            if (valid && lane == 31 - __clz(peers)) mycnt[h] = (uint16_t)(prior + __popc(peers));
-            __syncwarp();
-        }
-        __syncthreads();
-        {   // exclusive scan in (bucket-major, warp-minor) order; thread owns 16 buckets
-            uint32_t v[AMBC_WARPS][8];
-#pragma unroll
-            for (int w = 0; w < AMBC_WARPS; w++) {
-                const uint4 *src = (const uint4 *)(cnt + w * AMBC_NBUCKET + 16 * tid);
-                uint4 a = src[0], b = src[1];
-                v[w][0] = a.x; v[w][1] = a.y; v[w][2] = a.z; v[w][3] = a.w;
-                v[w][4] = b.x; v[w][5] = b.y; v[w][6] = b.z; v[w][7] = b.w;
-            }
-            uint32_t run = 0;
-#pragma unroll
-            for (int hh = 0; hh < 16; hh++) {
-#pragma unroll
-                for (int w = 0; w < AMBC_WARPS; w++) {
-                    uint32_t word = v[w][hh >> 1];
-                    uint32_t x = (hh & 1) ? (word >> 16) : (word & 0xFFFF);
-                    v[w][hh >> 1] = (hh & 1) ? ((word & 0xFFFF) | (run << 16)) : ((word & 0xFFFF0000u) | run);
-                    run += x;
-                }
-            }
-            int tot;
-            uint32_t off = (uint32_t)block_excl_scan((int)run, c.red, &tot);
-            uint32_t off2 = off | (off << 16);
-#pragma unroll
-            for (int w = 0; w < AMBC_WARPS; w++) {
-#pragma unroll
-                for (int k = 0; k < 8; k++) v[w][k] += off2;
-                uint4 *dst = (uint4 *)(cnt + w * AMBC_NBUCKET + 16 * tid);
-                dst[0] = make_uint4(v[w][0], v[w][1], v[w][2], v[w][3]);
-                dst[1] = make_uint4(v[w][4], v[w][5], v[w][6], v[w][7]);
-            }
-            uint4 *bs = (uint4 *)(c.bstart + 16 * tid);
-            bs[0] = make_uint4(v[0][0], v[0][1], v[0][2], v[0][3]);
-            bs[1] = make_uint4(v[0][4], v[0][5], v[0][6], v[0][7]);
-            if (tid == 0) c.bstart[AMBC_NBUCKET] = (uint16_t)P;
-        }
-        __syncthreads();
-        for (int base = wbeg; base < wend; base += 32) { // pass 2: ordered scatter
-            int p = base + lane;
-            bool valid = p < wend;
-            uint32_t h = valid ? lz_hash(lds_u32u(c.sd + p) & 0xFFFFFFu) : (uint32_t)(AMBC_NBUCKET + lane);
-            uint32_t peers = __match_any_sync(FULL_MASK, h);
-            uint32_t prior = valid ? mycnt[h] : 0;
-            __syncwarp();
-            if (valid) {
-                c.sorted[prior + __popc(peers & ((1u << lane) - 1))] = (uint16_t)p;
-                if (lane == 31 - __clz(peers)) mycnt[h] = (uint16_t)(prior + __popc(peers));
-            }
-            __syncwarp();
-        }
-        __syncthreads();
-
-        // ---- earliest-longest match for every position (thread per sorted slot) ----------
-        for (int s = tid; s < P; s += AMBC_BLOCK) {
-            const int p = c.sorted[s];
-            const uint32_t w0 = lds_u32u(c.sd + p);
-            const int b0 = c.bstart[lz_hash(w0 & 0xFFFFFFu)];
-            const int cap = min(32, n - p);
-            int best = 0, bpos = 0;
-            if (b0 < s) {
-                uint32_t pw[8];
-                pw[0] = w0;
-#pragma unroll
-                for (int k = 1; k < 8; k++) pw[k] = lds_u32u(c.sd + p + 4 * k);
-                const int lo = p - 4096; // window_size (:294)
-                for (int j = b0; j < s; j++) {
-                    const int i = c.sorted[j];
-                    if (i < lo) continue;
-                    uint32_t x = lds_u32u(c.sd + i) ^ pw[0];
-                    if (x & 0xFFFFFFu) continue; // hash collision: different trigram
-                    int len;
-                    if (x) len = 3;
-                    else {
-                        len = 4;
-#pragma unroll
-                        for (int k = 1; k < 8; k++) {
-                            x = lds_u32u(c.sd + i + 4 * k) ^ pw[k];
-                            if (x) { len = 4 * k + ((__ffs(x) - 1) >> 3); break; }
-                            len = 4 * k + 4;
-                        }
-                    }
-                    len = min(len, cap);
-                    if (len > best) { // strictly longer: earliest wins ties (:309-311)
-                        best = len; bpos = i;
-                        if (len == cap) break;
-                    }
-                }
-            }
-            c.mlen[p] = (uint8_t)best;
-            c.mpos[p] = (uint16_t)bpos;
-        }
-    }
-    for (int p = max(P, 0) + tid; p < n; p += AMBC_BLOCK) c.mlen[p] = 0;
-    for (int p = n + tid; p < (int)r16((size_t)n); p += AMBC_BLOCK) c.mlen[p] = 0;
+    const int n = c.n, tid = threadIdx.x, lane = tid & 31;
+    for (int p = tid * 16; p < (int)r16((size_t)n); p += AMBC_BLOCK * 16)
+        *(uint4 *)(c.mlen + p) = make_uint4(0, 0, 0, 0);
     __syncthreads();
+
+    // ---- earliest-longest match for every position, longest n-gram level first -----------
+    for (int li = LZ_NLEVELS - 1; li >= 0; li--) {
+        const int L = LZ_LEVELS[li];
+        const int U = (li == LZ_NLEVELS - 1) ? 32 : LZ_LEVELS[li + 1] - 1;
+        const int P = n - L + 1; // positions that have a whole L-gram
+        if (P < 2) continue;
+        lz_bucket_sort(c, P, L);
+        const int nwU = (U + 3) >> 2;
+        // deferred queue for long buckets (scanned warp-cooperatively below): slots as u16 in c.pay
+        uint16_t *defq = (uint16_t *)c.pay;
+        const int qcap = c.pcap >> 1;
+        volatile int *qn = c.red + 28, *qhead = c.red + 29;
+        if (tid == 0) { *qn = 0; *qhead = 0; }
+        __syncthreads();
+        const int Pr = (P + 31) & ~31; // whole warps iterate together (ballot below)
+        for (int s = tid; s < Pr; s += AMBC_BLOCK) {
+            int p = 0, b0 = 0;
+            bool todo = false;
+            if (s < P) {
+                p = c.sorted[s];
+                if (!c.mlen[p]) { // not resolved at a longer level
+                    b0 = c.bstart[lz_hash_l(c.sd + p, L)];
+                    todo = b0 < s;
+                }
+            }
+            bool defer = todo && (s - b0 > LZ_COOP_THRESHOLD);
+            uint32_t dmask = __ballot_sync(FULL_MASK, defer);
+            if (dmask) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd((int *)qn, __popc(dmask));
+                base = __shfl_sync(FULL_MASK, base, 0);
+                int slot = base + __popc(dmask & ((1u << lane) - 1));
+                if (defer) {
+                    if (slot < qcap) defq[slot] = (uint16_t)s;
+                    else defer = false; // queue full: scan it here
+                }
+            }
+            if (!todo || defer) continue;
+            const int cap = min(U, n - p); // lookahead_size 32 / end of data (:295, :304-305)
+            uint32_t pw[8];
+            {
+                uintptr_t a = (uintptr_t)(c.sd + p);
+                const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
+                const uint32_t sh = (uint32_t)(a & 3) * 8;
+                uint32_t lo_w = w[0];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    if (k < nwU) { uint32_t hi_w = w[k + 1]; pw[k] = __funnelshift_r(lo_w, hi_w, sh); lo_w = hi_w; }
+                    else pw[k] = 0;
+                }
+            }
+            const int lo = p - 4096; // window_size (:294)
+            int best = 0, bpos = 0;
+            for (int j = b0; j < s; j++) {
+                const int i = c.sorted[j];
+                if (i < lo) continue;
+                int len = lz_match_len(c.sd + i, pw, nwU);
+                len = min(len, cap);
+                if (len >= L && len > best) { // a true L-gram match, strictly longer (:309-311)
+                    best = len; bpos = i;
+                    if (len == cap) break;
+                }
+            }
+            if (best) { c.mlen[p] = (uint8_t)best; c.mpos[p] = (uint16_t)bpos; }
+        }
+        __syncthreads();
+        // long buckets: one warp per slot, 32 candidates per step, ascending, same tie rule
+        const int nq = min(*qn, qcap);
+        for (;;) {
+            int q = 0;
+            if (lane == 0) q = atomicAdd((int *)qhead, 1);
+            q = __shfl_sync(FULL_MASK, q, 0);
+            if (q >= nq) break;
+            const int s = defq[q];
+            const int p = c.sorted[s];
+            const int b0 = c.bstart[lz_hash_l(c.sd + p, L)];
+            const int cap = min(U, n - p);
+            uint32_t pw[8];
+            {
+                uintptr_t a = (uintptr_t)(c.sd + p);
+                const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
+                const uint32_t sh = (uint32_t)(a & 3) * 8;
+                uint32_t lo_w = w[0];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    if (k < nwU) { uint32_t hi_w = w[k + 1]; pw[k] = __funnelshift_r(lo_w, hi_w, sh); lo_w = hi_w; }
+                    else pw[k] = 0;
+                }
+            }
+            const int lo = p - 4096;
+            int best = 0, bpos = 0;
+            for (int base = b0; base < s; base += 32) {
+                const int j = base + lane;
+                int i = 0, len = 0;
+                if (j < s) {
+                    i = c.sorted[j];
+                    if (i >= lo) {
+                        len = min(lz_match_len(c.sd + i, pw, nwU), cap);
+                        if (len < L) len = 0;
+                    }
+                }
+                const int m = __reduce_max_sync(FULL_MASK, len);
+                if (m > best) { // the earliest candidate of the new maximum: lowest lane
+                    const int first = __ffs(__ballot_sync(FULL_MASK, len == m)) - 1;
+                    best = m;
+                    bpos = __shfl_sync(FULL_MASK, i, first);
+                    if (best == cap) break;
+                }
+            }
+            if (lane == 0 && best) { c.mlen[p] = (uint8_t)best; c.mpos[p] = (uint16_t)bpos; }
+        }
+        __syncthreads();
+    }
 
     // ---- token chain: pos -> pos + (len>2 ? len : 1) (:211-232), resolved per 32-block ---
     const int nb = (n + 31) >> 5;

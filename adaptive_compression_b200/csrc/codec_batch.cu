@@ -120,3 +120,5 @@ extern "C" int ambc_should_use_batch(const void *in_dev, const uint64_t *in_off_
     CUDA_TRY(cudaGetLastError());
     return AMBC_OK;
 }
+
+int ambc_lz_levels_codec(const int *levels, int n) { return lz_levels_upload(levels, n); }

@@ -3,9 +3,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define AMBC_BLOCK 128              // threads per CTA in the chunk kernels
+#ifndef AMBC_BLOCK
+#define AMBC_BLOCK 256              // threads per CTA in the chunk kernels
+#endif
 #define AMBC_WARPS (AMBC_BLOCK / 32)
-#define AMBC_HB 11                  // LZ trigram hash bits
+#ifndef AMBC_HB
+#define AMBC_HB 10                  // LZ n-gram hash bits
+#endif
 #define AMBC_NBUCKET (1 << AMBC_HB)
 #define AMBC_NMAX 8192              // largest chunk a native method accepts (adaptive_compressor.py:114-127)
 #define AMBC_PAD 64                 // zeroed bytes after the chunk in shared memory

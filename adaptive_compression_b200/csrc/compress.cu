@@ -13,7 +13,6 @@
 #include "ambc_internal.h"
 #include "chunk_codec.cuh"
 
-static_assert(AMBC_NBUCKET == 16 * AMBC_BLOCK, "scan in chunk_lz_encode assumes 16 buckets per thread");
 
 // per-chunk decision ------------------------------------------------------------------------
 struct SelectOut { int type; int len; };
@@ -465,3 +464,5 @@ extern "C" int ambc_compress_dev(const void *in_dev, uint64_t n, uint32_t chunk,
     if (native && !(flags & AMBC_F_PER_CHUNK_RAW) && res->first_raw >= 0) res->usage[0] = 1;
     return AMBC_OK;
 }
+
+int ambc_lz_levels_compress(const int *levels, int n) { return lz_levels_upload(levels, n); }

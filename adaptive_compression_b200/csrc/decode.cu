@@ -126,17 +126,17 @@ __device__ int decode_package(DecCtx &d, uint32_t type, const uint8_t *__restric
                 node = bit ? h.child1[node] : h.child0[node];
                 if (node < h.K) { if (o < cap) dst[o] = (uint8_t)h.lead[node]; o++; node = h.root; }
             }
-            res[8] = (int)o;
+            res[24] = (int)o;
         }
     } else if (threadIdx.x == 0) {
         long r;
         if (type == 1) r = slow_rle(src, comp, orig, dst, cap);
         else if (type == 2) r = lz_walk(src, comp, orig, dst, cap);
         else r = slow_delta(src, comp, orig, dst, cap);
-        res[8] = (int)r;
+        res[24] = (int)r;
     }
     __syncthreads();
-    int r = res[8];
+    int r = res[24];
     __syncthreads();
     return r;
 }

@@ -31,7 +31,7 @@ __host__ __device__ inline size_t dec_x_bytes(int in_cap)
 }
 __host__ __device__ inline size_t decctx_smem_bytes(int in_cap)
 {
-    return dec_r16((size_t)in_cap) + 16 + DEC_OUT_CAP + DEC_OUT_SLACK + dec_x_bytes(in_cap) + 64;
+    return dec_r16((size_t)in_cap) + 16 + DEC_OUT_CAP + DEC_OUT_SLACK + dec_x_bytes(in_cap) + 128;
 }
 __device__ inline void decctx_carve(DecCtx &d, uint8_t *base, int in_cap)
 {
@@ -146,9 +146,9 @@ __device__ inline int lz_walk(const uint8_t *in, long len, long orig, uint8_t *o
 __device__ inline int dec_lz(DecCtx &d, int len, int orig)
 {
     volatile int *res = d.red;
-    if (threadIdx.x == 0) res[8] = lz_walk(d.in, len, orig, d.out, DEC_OUT_CAP + DEC_OUT_SLACK);
+    if (threadIdx.x == 0) res[24] = lz_walk(d.in, len, orig, d.out, DEC_OUT_CAP + DEC_OUT_SLACK);
     __syncthreads();
-    int r = res[8];
+    int r = res[24];
     __syncthreads();
     return r;
 }
@@ -163,7 +163,7 @@ struct HuffDec {
     uint32_t *firstidx;        // [256] first table entry of the symbol
     uint32_t *lastidx;         // [256] last table entry (overlays lut, dead before it is built)
     uint32_t *start;           // [AMBC_BLOCK + 4] subsequence start bits (overlays key)
-    uint32_t *cnt;             // [AMBC_BLOCK] symbols per subsequence (overlays key)
+    uint32_t *cnt;             // [AMBC_BLOCK] symbols per subsequence (overlays firstidx)
     int K, root;
 };
 __device__ inline HuffDec huffdec_scratch(uint8_t *X) // needs 12288 bytes
@@ -178,7 +178,8 @@ __device__ inline HuffDec huffdec_scratch(uint8_t *X) // needs 12288 bytes
     h.firstidx = (uint32_t *)(X + 11264);         // 11264 .. 12288
     h.lastidx = (uint32_t *)(X + 9216);
     h.start = (uint32_t *)(X + 4096);
-    h.cnt = (uint32_t *)(X + 4096 + 4 * (AMBC_BLOCK + 4));
+    h.cnt = (uint32_t *)(X + 11264); // firstidx is dead once the tree is built
+    static_assert(4 * (AMBC_BLOCK + 4) <= 2048 && 4 * AMBC_BLOCK <= 1024, "Huffman decode scratch layout");
     h.K = 0; h.root = 0;
     return h;
 }
