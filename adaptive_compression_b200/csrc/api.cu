@@ -57,6 +57,10 @@ extern "C" int ambc_set_lz_levels(const int *levels, int n)
     return AMBC_OK;
 }
 
+int ambc_lz_coop_compress(int t);
+int ambc_lz_coop_codec(int t);
+extern "C" int ambc_set_lz_coop_threshold(int t) { return (ambc_lz_coop_compress(t) || ambc_lz_coop_codec(t)) ? AMBC_E_CUDA : AMBC_OK; }
+
 extern "C" const char *ambc_last_error(void) { return g_err; }
 extern "C" int ambc_version(void) { return 100; }
 extern "C" uint64_t ambc_launch_count(void) { return g_launches.load(); }

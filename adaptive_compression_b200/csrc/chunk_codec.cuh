@@ -335,6 +335,7 @@ __device__ inline int chunk_delta_encode(ChunkCtx &c)
 #define LZ_MAX_LEVELS 8
 static __device__ __constant__ int LZ_LEVELS[LZ_MAX_LEVELS] = {3, 4, 6, 10, 0, 0, 0, 0};
 static __device__ __constant__ int LZ_NLEVELS = 4;
+static __device__ __constant__ int LZ_COOP_T = 24; // buckets with more candidates are scanned by a whole warp
 // per-translation-unit setter (the constants are TU-local without relocatable device code)
 static inline int lz_levels_upload(const int *levels, int n)
 {
@@ -347,6 +348,10 @@ static inline int lz_levels_upload(const int *levels, int n)
     if (cudaMemcpyToSymbol(LZ_LEVELS, buf, sizeof buf) != cudaSuccess) return -1;
     if (cudaMemcpyToSymbol(LZ_NLEVELS, &n, sizeof n) != cudaSuccess) return -1;
     return 0;
+}
+static inline int lz_coop_upload(int t)
+{
+    return cudaMemcpyToSymbol(LZ_COOP_T, &t, sizeof t) == cudaSuccess ? 0 : -1;
 }
 
 // hash of the L-gram at shared-memory address s (L <= 16)
@@ -454,9 +459,6 @@ __device__ inline void lz_bucket_sort(ChunkCtx &c, int P, int L)
     __syncthreads();
 }
 
-#ifndef LZ_COOP_THRESHOLD
-#define LZ_COOP_THRESHOLD 24 // buckets with more candidates than this are scanned by a whole warp
-#endif
 
 // common-prefix length (bytes, up to 4*nw) of the data at shared address s with the words pw[]
 __device__ __forceinline__ int lz_match_len(const uint8_t *s, const uint32_t (&pw)[8], int nw)
@@ -511,7 +513,7 @@ __device__ inline int chunk_lz_encode(ChunkCtx &c)
                     todo = b0 < s;
                 }
             }
-            bool defer = todo && (s - b0 > LZ_COOP_THRESHOLD);
+            bool defer = todo && (s - b0 > LZ_COOP_T);
             uint32_t dmask = __ballot_sync(FULL_MASK, defer);
             if (dmask) {
                 int base = 0;

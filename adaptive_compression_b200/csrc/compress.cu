@@ -466,3 +466,4 @@ extern "C" int ambc_compress_dev(const void *in_dev, uint64_t n, uint32_t chunk,
 }
 
 int ambc_lz_levels_compress(const int *levels, int n) { return lz_levels_upload(levels, n); }
+int ambc_lz_coop_compress(int t) { return lz_coop_upload(t); }

@@ -3,21 +3,35 @@ process per GPU, torch.distributed (NCCL over NVLink; gloo in the CPU tests) for
 exchanges the path has:
 
   place_shards        all-gather of one 16-byte record per rank -> every rank folds the
-                      "rest of file raw" monoid left to right and learns its fragment's byte
-                      offset in the global body, or that it lies inside the raw tail.
+                      "rest of file raw" monoid left to right (adaptive_compressor.py:586-590) and
+                      learns its fragment's byte offset in the global body, or that it lies inside
+                      the raw tail.
   merge_marker_flags  byte-wise MAX all-reduce of the per-shard n-gram presence flags
                       (NCCL has no bitwise OR; flags are 0/1 bytes).
-"""
+
+A rank compresses its range as if no earlier rank had hit a chunk without a winner; shard_fragment()
+then turns the local body into the bytes this rank contributes to the global body."""
+import struct
+
 import torch
 import torch.distributed as dist
 
 NO_RAW = -1
 
 
+def shard_range(total_bytes, chunk, rank, world):
+    """contiguous chunk range of `rank`: (first_chunk, byte_begin, byte_end)"""
+    n_chunks = (total_bytes + chunk - 1) // chunk
+    per = (n_chunks + world - 1) // world
+    c0 = min(n_chunks, rank * per)
+    c1 = min(n_chunks, c0 + per)
+    return c0, min(total_bytes, c0 * chunk), min(total_bytes, c1 * chunk)
+
+
 def fold_placement(records):
     """records[r] = (fragment_bytes_before_first_raw, first_raw_global_chunk or -1), rank order.
-    -> list of (offset, state): state 'packed' (fragment lands at offset), 'raw_starts_here'
-    (fragment up to its first raw chunk lands at offset, the raw package follows) or 'in_raw_tail'.
+    -> list of (offset, state): 'packed' (whole fragment lands at offset), 'raw_starts_here'
+    (packed part at offset, then the global raw package) or 'in_raw_tail'.
     Monoid: A.B = A if A has a raw chunk else (A.bytes + B.bytes, B.first_raw)."""
     out = []
     offset = 0
@@ -35,16 +49,58 @@ def fold_placement(records):
     return out
 
 
+def _device():
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
 def place_shards(fragment_bytes, first_raw_local, first_chunk_global, world):
     """all-gather the placement records; returns (this rank's (offset, state), all records)"""
     rank = dist.get_rank()
-    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
     fr = first_chunk_global + first_raw_local if first_raw_local >= 0 else NO_RAW
-    mine = torch.tensor([int(fragment_bytes), int(fr)], dtype=torch.int64, device=dev)
-    allr = torch.empty(2 * world, dtype=torch.int64, device=dev)
+    mine = torch.tensor([int(fragment_bytes), int(fr)], dtype=torch.int64, device=_device())
+    allr = torch.empty(2 * world, dtype=torch.int64, device=mine.device)
     dist.all_gather_into_tensor(allr, mine)
     recs = [tuple(x) for x in allr.view(world, 2).cpu().tolist()]
     return fold_placement(recs)[rank], recs
+
+
+def packed_bytes(body_len, n_local, first_raw_local, chunk, marker_bytes=4):
+    """bytes of the local body that precede its first raw chunk (END and local raw package removed)"""
+    end = marker_bytes + 12
+    if first_raw_local < 0:
+        return body_len - end
+    return body_len - end - (marker_bytes + 14) - (n_local - first_raw_local * chunk)
+
+
+def shard_fragment(local_body, local_input, first_raw_local, first_chunk_global, chunk, total_bytes, records, rank,
+                   marker=b"\xff\xff\x00\x00"):
+    """-> (global byte offset, 1-D uint8 tensor) this rank contributes to the global body (the END
+    package is appended by the last rank).  local_body / local_input are tensors on any device."""
+    mb = len(marker)
+    ovh = mb + 14
+    plan = fold_placement(records)
+    offset, state = plan[rank]
+    n_local = local_input.numel()
+    pk = packed_bytes(local_body.numel(), n_local, first_raw_local, chunk, mb)
+    last = rank == len(records) - 1
+    end_pkg = torch.tensor(list(marker + bytes(12)), dtype=torch.uint8, device=local_body.device)
+    g = next((fr for _, fr in records if fr >= 0), NO_RAW)  # global first raw chunk
+    if state == "packed":
+        frag = local_body[:pk]
+    elif state == "raw_starts_here":
+        rawlen = total_bytes - g * chunk
+        if rawlen > 0xFFFFFFFF:
+            raise struct.error("'I' format requires 0 <= number <= 4294967295")  # adaptive_compressor.py:617-619
+        hdr = marker + bytes([255, 0]) + struct.pack("<III", rawlen, rawlen, rawlen)
+        hdr_t = torch.tensor(list(hdr), dtype=torch.uint8, device=local_body.device)
+        frag = torch.cat([local_body[:pk], hdr_t, local_input[first_raw_local * chunk:]])
+    else:
+        packed_total = sum(nb for nb, _ in records[:next(i for i, (_, fr) in enumerate(records) if fr >= 0) + 1])
+        offset = packed_total + ovh + (first_chunk_global * chunk - g * chunk)
+        frag = local_input
+    if last:
+        frag = torch.cat([frag, end_pkg])
+    return offset, frag
 
 
 def merge_marker_flags(flags):

@@ -185,7 +185,8 @@ def run_b200(args):
                                       C.c_void_p(t_out.data_ptr()), bound, C.c_void_p(t_work.data_ptr()),
                                       t_work.numel(), C.byref(res), stream))
         if world > 1:  # shard placement: all-gather of (bytes before first raw, first raw chunk)
-            return D.place_shards(res.body_len - 16, res.first_raw, rank * (n // CHUNK), world)
+            return D.place_shards(D.packed_bytes(res.body_len, n, res.first_raw, CHUNK), res.first_raw,
+                                  rank * (n // CHUNK), world)
         return None
 
     compress()

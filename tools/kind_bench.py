@@ -8,6 +8,7 @@ n = 64 << 20
 names = ['csv', 'log', 'runs', 'lowcard', 'binrec', 'random', 'text']
 level_sets = [[int(x) for x in s.split(',')] for s in (sys.argv[1:] or ['3', '3,4,8'])]
 lib.ambc_enable_timing(1)
+T=int(os.environ.get('COOP_T','24')); lib.ambc_set_lz_coop_threshold(T); print('coop T',T)
 for k in (0, 1, 2, 3, 4, 6, 5):
     t = engine.synth(n, 0, kind_mask=1 << k)
     row = [names[k]]
