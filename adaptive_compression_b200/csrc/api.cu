@@ -61,6 +61,14 @@ int ambc_lz_coop_compress(int t);
 int ambc_lz_coop_codec(int t);
 extern "C" int ambc_set_lz_coop_threshold(int t) { return (ambc_lz_coop_compress(t) || ambc_lz_coop_codec(t)) ? AMBC_E_CUDA : AMBC_OK; }
 
+int ambc_lz_force_buckets_compress(int on);
+int ambc_lz_force_buckets_codec(int on);
+// test knob (not part of include/ambc.h): force the window-aware bucket search for every chunk size
+extern "C" int ambc_set_lz_force_buckets(int on)
+{
+    return (ambc_lz_force_buckets_compress(on) || ambc_lz_force_buckets_codec(on)) ? AMBC_E_CUDA : AMBC_OK;
+}
+
 extern "C" const char *ambc_last_error(void) { return g_err; }
 extern "C" int ambc_version(void) { return 100; }
 extern "C" uint64_t ambc_launch_count(void) { return g_launches.load(); }

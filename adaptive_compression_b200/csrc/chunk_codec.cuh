@@ -25,7 +25,16 @@ struct ChunkCtx {
     uint32_t *reach;   // token-start bitmap, ceil(n/32) words
     uint8_t *estart;   // per 32-block chain entry offset
     int *red;          // 32 ints of reduction scratch (8-byte aligned)
+    // names-based match search (lz_names.cuh), chunks of at most LZ2_NMAX bytes; T == nullptr: absent
+    uint32_t *T;       // LZ2_TSLOTS hash slots (32 KiB); also participant list / slot memo in its upper part
+    uint16_t *nameA;   // LZ2_NMAX first-occurrence names (two buffers, alternating levels)
+    uint16_t *nameB;
+    uint32_t *fol;     // 2 x LZ2_NMAX/32 "has a later occurrence" bits
 };
+
+#define LZ2_NMAX 4096
+#define LZ2_TSLOTS 8192
+#define LZ2_BYTES (LZ2_TSLOTS * 4 + 2 * LZ2_NMAX * 2 + 2 * (LZ2_NMAX / 32) * 4)
 
 // scratch region X: LZ per-warp bucket counters, or 16 KiB for the other users
 #define AMBC_XBYTES ((AMBC_WARPS * AMBC_NBUCKET * 2) > 16384 ? (AMBC_WARPS * AMBC_NBUCKET * 2) : 16384)
@@ -49,7 +58,8 @@ __host__ __device__ inline size_t chunkctx_smem_bytes(int N, int pcap)
            + 1024                             // hist
            + r16(nb * 4) * 2                  // bmask, reach
            + r16(nb)                          // estart
-           + 128;                             // red
+           + 128                              // red
+           + LZ2_BYTES;                       // T, nameA, nameB, fol
 }
 
 __device__ inline void chunkctx_carve(ChunkCtx &c, uint8_t *base, int N, int pcap)
@@ -69,10 +79,53 @@ __device__ inline void chunkctx_carve(ChunkCtx &c, uint8_t *base, int N, int pca
     c.bmask = (uint32_t *)p; p += r16(nb * 4);
     c.reach = (uint32_t *)p; p += r16(nb * 4);
     c.estart = p; p += r16(nb);
-    c.red = (int *)p;
+    c.red = (int *)p; p += 128;
+    c.T = (uint32_t *)p; p += LZ2_TSLOTS * 4;
+    c.nameA = (uint16_t *)p; p += LZ2_NMAX * 2;
+    c.nameB = (uint16_t *)p; p += LZ2_NMAX * 2;
+    c.fol = (uint32_t *)p;
     c.pcap = pcap;
     c.n = 0;
 }
+
+// Compact layout for the chunk kernel at N <= LZ2_NMAX, payload capacity N: everything that is
+// dead while the match search runs (trigram set / Huffman scratch X, Huffman bit words `sorted`,
+// the payload buffer, the bucket starts of the fallback search) overlays the 32 KiB hash table.
+__host__ __device__ inline size_t chunkctx_fast_smem_bytes(int N)
+{
+    size_t nb = (size_t)(N + 31) / 32;
+    return r16((size_t)N) + AMBC_PAD + LZ2_TSLOTS * 4 + 2 * LZ2_NMAX * 2 + 2 * (LZ2_NMAX / 32) * 4
+           + r16((size_t)N) + r16(2 * (size_t)N) + 1024 + r16(nb * 4) * 2 + r16(nb) + 128;
+}
+__device__ inline void chunkctx_carve_fast(ChunkCtx &c, uint8_t *base, int N)
+{
+    size_t nb = (size_t)(N + 31) / 32;
+    uint8_t *p = base;
+    c.sd = p; p += r16((size_t)N) + AMBC_PAD;
+    c.T = (uint32_t *)p;
+    {   // overlays of the table region: X | sorted | pay | bstart  (<= 32 KiB for N <= 4096)
+        uint8_t *q = p;
+        c.X = q; q += AMBC_XBYTES + 64;
+        c.sorted = (uint16_t *)q; q += r16(2 * (size_t)(N + 2) > (size_t)N + 16 ? 2 * (size_t)(N + 2) : (size_t)N + 16);
+        c.pay = q; q += r16((size_t)N) + 16;
+        c.bstart = (uint16_t *)q;
+    }
+    p += LZ2_TSLOTS * 4;
+    c.nameA = (uint16_t *)p; p += LZ2_NMAX * 2;
+    c.nameB = (uint16_t *)p; p += LZ2_NMAX * 2;
+    c.fol = (uint32_t *)p; p += 2 * (LZ2_NMAX / 32) * 4;
+    c.mlen = p; p += r16((size_t)N);
+    c.mpos = (uint16_t *)p; p += r16(2 * (size_t)N);
+    c.hist = (uint32_t *)p; p += 1024;
+    c.bmask = (uint32_t *)p; p += r16(nb * 4);
+    c.reach = (uint32_t *)p; p += r16(nb * 4);
+    c.estart = p; p += r16(nb);
+    c.red = (int *)p;
+    c.pcap = N;
+    c.n = 0;
+}
+static_assert(AMBC_XBYTES + 64 + ((2 * (LZ2_NMAX + 2) + 15) & ~15) + LZ2_NMAX + 16 + 2 * (AMBC_NBUCKET + 1) <= LZ2_TSLOTS * 4,
+              "overlays must fit the table region");
 
 // Stage chunk [src, src+n) in c.sd and zero the pad.  Ends with __syncthreads().
 __device__ inline void chunk_load(ChunkCtx &c, const uint8_t *__restrict__ src, int n)
@@ -336,6 +389,7 @@ __device__ inline int chunk_delta_encode(ChunkCtx &c)
 static __device__ __constant__ int LZ_LEVELS[LZ_MAX_LEVELS] = {3, 4, 6, 10, 0, 0, 0, 0};
 static __device__ __constant__ int LZ_NLEVELS = 4;
 static __device__ __constant__ int LZ_COOP_T = 24; // buckets with more candidates are scanned by a whole warp
+static __device__ __constant__ int LZ_FORCE_BUCKETS = 0; // test knob: always use the bucket search
 // per-translation-unit setter (the constants are TU-local without relocatable device code)
 static inline int lz_levels_upload(const int *levels, int n)
 {
@@ -352,6 +406,10 @@ static inline int lz_levels_upload(const int *levels, int n)
 static inline int lz_coop_upload(int t)
 {
     return cudaMemcpyToSymbol(LZ_COOP_T, &t, sizeof t) == cudaSuccess ? 0 : -1;
+}
+static inline int lz_force_buckets_upload(int on)
+{
+    return cudaMemcpyToSymbol(LZ_FORCE_BUCKETS, &on, sizeof on) == cudaSuccess ? 0 : -1;
 }
 
 // hash of the L-gram at shared-memory address s (L <= 16)
@@ -480,14 +538,13 @@ __device__ __forceinline__ int lz_match_len(const uint8_t *s, const uint32_t (&p
     return len;
 }
 
-// Payload -> c.pay (as far as pcap allows).  Returns the exact payload length.  Collective.
-__device__ inline int chunk_lz_encode(ChunkCtx &c)
+#include "lz_names.cuh"
+
+// Earliest-longest match for every position by scanning n-gram buckets (any chunk size up to
+// AMBC_NMAX; honours the 4096-byte window).  c.mlen must be zero.  Collective.
+__device__ inline void lz_match_all_buckets(ChunkCtx &c)
 {
     const int n = c.n, tid = threadIdx.x, lane = tid & 31;
-    for (int p = tid * 16; p < (int)r16((size_t)n); p += AMBC_BLOCK * 16)
-        *(uint4 *)(c.mlen + p) = make_uint4(0, 0, 0, 0);
-    __syncthreads();
-
     // ---- earliest-longest match for every position, longest n-gram level first -----------
     for (int li = LZ_NLEVELS - 1; li >= 0; li--) {
         const int L = LZ_LEVELS[li];
@@ -601,6 +658,27 @@ __device__ inline int chunk_lz_encode(ChunkCtx &c)
         }
         __syncthreads();
     }
+}
+
+__device__ __forceinline__ void lz_zero_mlen(ChunkCtx &c)
+{
+    for (int p = threadIdx.x * 16; p < (int)r16((size_t)c.n); p += AMBC_BLOCK * 16)
+        *(uint4 *)(c.mlen + p) = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+}
+
+// Payload -> c.pay (as far as pcap allows).  Returns the exact payload length.  Collective.
+__device__ inline int chunk_lz_encode(ChunkCtx &c)
+{
+    const int n = c.n, tid = threadIdx.x;
+    lz_zero_mlen(c);
+    bool done = false;
+    if (c.T && n <= LZ2_NMAX && !LZ_FORCE_BUCKETS) {
+        done = lz2_match_all(c);
+        if (!done) lz_zero_mlen(c); // a table overflowed (pathological key skew): redo with the bucket search
+    }
+    if (!done) lz_match_all_buckets(c);
+    __syncthreads();
 
     // ---- token chain: pos -> pos + (len>2 ? len : 1) (:211-232), resolved per 32-block ---
     const int nb = (n + 31) >> 5;

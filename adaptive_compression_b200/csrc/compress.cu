@@ -94,7 +94,8 @@ k_select(const uint8_t *__restrict__ in, uint64_t total, uint32_t N, uint32_t ma
 {
     extern __shared__ uint4 smem4[];
     ChunkCtx c;
-    chunkctx_carve(c, (uint8_t *)smem4, (int)N, (int)N);
+    if (N <= LZ2_NMAX) chunkctx_carve_fast(c, (uint8_t *)smem4, (int)N);
+    else chunkctx_carve(c, (uint8_t *)smem4, (int)N, (int)N);
     for (uint64_t i = blockIdx.x; i < n_chunks; i += gridDim.x) {
         uint64_t off = i * (uint64_t)N;
         int n = (int)min((uint64_t)N, total - off);
@@ -403,7 +404,7 @@ extern "C" int ambc_compress_dev(const void *in_dev, uint64_t n, uint32_t chunk,
     unsigned grid_chunks = (unsigned)min<uint64_t>(L.n_chunks, 0x7fffffffull);
 
     if (native) {
-        size_t smem = chunkctx_smem_bytes((int)chunk, (int)chunk);
+        size_t smem = chunk <= LZ2_NMAX ? chunkctx_fast_smem_bytes((int)chunk) : chunkctx_smem_bytes((int)chunk, (int)chunk);
         CUDA_TRY(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ambc_timing_mark(0, stream);
         k_select<<<grid_chunks, AMBC_BLOCK, smem, stream>>>((const uint8_t *)in_dev, n, chunk, method_mask, ovh,
@@ -467,3 +468,4 @@ extern "C" int ambc_compress_dev(const void *in_dev, uint64_t n, uint32_t chunk,
 
 int ambc_lz_levels_compress(const int *levels, int n) { return lz_levels_upload(levels, n); }
 int ambc_lz_coop_compress(int t) { return lz_coop_upload(t); }
+int ambc_lz_force_buckets_compress(int on) { return lz_force_buckets_upload(on); }

@@ -164,3 +164,20 @@ def test_decode_corrupted_fuzz(eng):
             if g != want:
                 bad.append((mid, i, len(p), o, _fmt(g), _fmt(want)))
     assert not bad, bad[:20]
+
+
+def test_encode_lz_bucket_search_fallback(eng):
+    """the window-aware bucket search (chunks > 4096 bytes, and the fallback of the names search)
+    forced for every size: same payloads as the oracle"""
+    from adaptive_compression_b200 import _lib as L
+    lib = L.lib()
+    r = np.random.RandomState(555)
+    kinds = sorted(inputs.KINDS)
+    datas = [inputs.make(kinds[r.randint(len(kinds))], int(r.choice([3, 100, 1000, 4096])), 50000 + i) for i in range(60)]
+    assert lib.ambc_set_lz_force_buckets(1) == 0
+    try:
+        got = eng.codec_encode_batch(2, datas)
+    finally:
+        assert lib.ambc_set_lz_force_buckets(0) == 0
+    bad = [(i, len(d)) for i, (d, g) in enumerate(zip(datas, got)) if g != O.compress(2, d, lz_fast=True)]
+    assert not bad, bad
