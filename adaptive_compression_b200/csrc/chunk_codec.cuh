@@ -89,8 +89,9 @@ __device__ inline void chunkctx_carve(ChunkCtx &c, uint8_t *base, int N, int pca
 }
 
 // Compact layout for the chunk kernel at N <= LZ2_NMAX, payload capacity N: everything that is
-// dead while the match search runs (trigram set / Huffman scratch X, Huffman bit words `sorted`,
-// the payload buffer, the bucket starts of the fallback search) overlays the 32 KiB hash table.
+// dead while the names search runs (trigram set / Huffman scratch / fallback-search counters X,
+// Huffman bit words `sorted`, the payload buffer, the bucket starts of the fallback search)
+// overlays the hash table and the two name buffers.
 __host__ __device__ inline size_t chunkctx_fast_smem_bytes(int N)
 {
     size_t nb = (size_t)(N + 31) / 32;
@@ -103,7 +104,7 @@ __device__ inline void chunkctx_carve_fast(ChunkCtx &c, uint8_t *base, int N)
     uint8_t *p = base;
     c.sd = p; p += r16((size_t)N) + AMBC_PAD;
     c.T = (uint32_t *)p;
-    {   // overlays of the table region: X | sorted | pay | bstart  (<= 32 KiB for N <= 4096)
+    {   // overlays of the table + names region (48 KiB): X | sorted | pay | bstart
         uint8_t *q = p;
         c.X = q; q += AMBC_XBYTES + 64;
         c.sorted = (uint16_t *)q; q += r16(2 * (size_t)(N + 2) > (size_t)N + 16 ? 2 * (size_t)(N + 2) : (size_t)N + 16);
@@ -124,8 +125,9 @@ __device__ inline void chunkctx_carve_fast(ChunkCtx &c, uint8_t *base, int N)
     c.pcap = N;
     c.n = 0;
 }
-static_assert(AMBC_XBYTES + 64 + ((2 * (LZ2_NMAX + 2) + 15) & ~15) + LZ2_NMAX + 16 + 2 * (AMBC_NBUCKET + 1) <= LZ2_TSLOTS * 4,
-              "overlays must fit the table region");
+static_assert(AMBC_XBYTES + 64 + ((2 * (LZ2_NMAX + 2) + 15) & ~15) + LZ2_NMAX + 16 + 2 * (AMBC_NBUCKET + 1) <=
+                  LZ2_TSLOTS * 4 + 2 * LZ2_NMAX * 2,
+              "overlays must fit the table + names region");
 
 // Stage chunk [src, src+n) in c.sd and zero the pad.  Ends with __syncthreads().
 __device__ inline void chunk_load(ChunkCtx &c, const uint8_t *__restrict__ src, int n)

@@ -5,6 +5,13 @@
 
 #define RAW_PIECE 65536u
 
+// Dictionary packages decoded one warp per package by k_decode_lz (see below)
+__device__ __forceinline__ bool dlz_eligible(const ambc_pkg &e)
+{
+    return e.type == 2 && e.comp_len <= DLZ_MAX_COMP && e.orig_len <= 4096;
+}
+
+
 // nominal number of bytes the reference appends for a package, knowable without decoding
 static inline uint64_t nominal_out(uint32_t type, bool known, uint32_t comp, uint32_t orig)
 {
@@ -150,6 +157,7 @@ k_decode(const uint8_t *__restrict__ body, const ambc_pkg *__restrict__ table, u
     decctx_carve(d, (uint8_t *)smem4, in_cap);
     for (uint64_t i = blockIdx.x; i < n_entries; i += gridDim.x) {
         const ambc_pkg e = table[i];
+        if (dlz_eligible(e)) continue; // decoded by k_decode_lz, one warp per package
         uint8_t *dst = out + e.dst_off;
         int produced = decode_package(d, e.type, body + e.src_off, e.comp_len, e.orig_len, dst, e.out_len);
         // nominal length the index assumed for this package (see nominal_out)
@@ -166,6 +174,36 @@ k_decode(const uint8_t *__restrict__ body, const ambc_pkg *__restrict__ table, u
             if (threadIdx.x == 0 && status) atomicAdd(&status[1], 1u);
         }
         __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(DLZ_WARPS * 32)
+k_decode_lz(const uint8_t *__restrict__ body, const ambc_pkg *__restrict__ table, uint64_t n_entries,
+            uint8_t *__restrict__ out, uint32_t *status)
+{
+    extern __shared__ uint4 smem4[];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *buf = (uint8_t *)smem4 + (size_t)w * DLZ_OUT;
+    for (uint64_t i = (uint64_t)blockIdx.x * DLZ_WARPS + w; i < n_entries; i += (uint64_t)gridDim.x * DLZ_WARPS) {
+        const ambc_pkg e = table[i];
+        if (!dlz_eligible(e)) continue;
+        uint8_t *dst = out + e.dst_off;
+        const int produced = dec_lz_warp(body + e.src_off, (int)e.comp_len, (int)e.orig_len, buf);
+        const uint32_t nominal = e.comp_len == 0 ? 0 : e.orig_len;
+        uint32_t good = produced < 0 ? 0u : min((uint32_t)produced, e.out_len);
+        // smem -> global, 16-byte stores when the destination allows
+        if ((((uintptr_t)dst) & 15) == 0) {
+            const uint32_t nv = good >> 4;
+            for (uint32_t k = lane; k < nv; k += 32) ((uint4 *)dst)[k] = ((const uint4 *)buf)[k];
+            for (uint32_t k = (nv << 4) + lane; k < good; k += 32) dst[k] = buf[k];
+        } else {
+            for (uint32_t k = lane; k < good; k += 32) dst[k] = buf[k];
+        }
+        if (produced < 0 || (uint32_t)produced != nominal) {
+            for (uint32_t k = good + lane; k < e.out_len; k += 32) dst[k] = 0;
+            if (lane == 0 && status) atomicAdd(&status[produced < 0 ? 0 : 1], 1u);
+        }
+        __syncwarp();
     }
 }
 
@@ -202,6 +240,14 @@ extern "C" int ambc_decompress_dev(const void *body_dev, uint64_t body_len, cons
     k_decode<<<grid, AMBC_BLOCK, smem, stream>>>((const uint8_t *)body_dev, table_dev, n_entries, (uint8_t *)out_dev,
                                                  in_cap, status_dev);
     ambc_count_launch();
+    {
+        size_t lsmem = (size_t)DLZ_WARPS * DLZ_OUT;
+        CUDA_TRY(cudaFuncSetAttribute(k_decode_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
+        unsigned lgrid = (unsigned)min<uint64_t>((n_entries + DLZ_WARPS - 1) / DLZ_WARPS, 148ull * 24);
+        k_decode_lz<<<lgrid, DLZ_WARPS * 32, lsmem, stream>>>((const uint8_t *)body_dev, table_dev, n_entries,
+                                                             (uint8_t *)out_dev, status_dev);
+        ambc_count_launch();
+    }
     CUDA_TRY(cudaGetLastError());
     ambc_timing_mark(5, stream);
     ambc_timing().pending_d = ambc_timing().on;

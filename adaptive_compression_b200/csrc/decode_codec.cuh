@@ -143,10 +143,146 @@ __device__ inline int lz_walk(const uint8_t *in, long len, long orig, uint8_t *o
     return (int)(o < orig ? o : orig);
 }
 
+#define DLZ_WARPS 8
+#define DLZ_OUT (4096 + 512)
+#define DLZ_MAX_COMP 8192
+
+// ---- warp-per-package Dictionary decode ----------------------------------------------------
+// Tokens of a well-formed payload start at even offsets ("slots"): [0, byte] or
+// [flag != 0, dist lo, dist hi, len] (compression_methods.py:236-281).  Slot i+1 is the second
+// half of a match token iff slot i starts one, so the token-start mask of 32 slots follows from
+// the non-zero-flag mask with one add-carry (the recurrence skipped[i+1] = flag[i] & !skipped[i]).
+// One warp: a prefix sum of token output lengths places every token; literals are stored at
+// once, matches are copied in order, 32 bytes per step.  Anything irregular (distance 0 or
+// reaching before the start of the output) replays the package with the serial walk, which
+// restates the reference's quirks exactly.
+
+__device__ __forceinline__ uint32_t dlz_skipped(uint32_t M, uint32_t &carry)
+{
+    const uint32_t b = M & ~carry;
+    const uint32_t follows = (b << 1) | carry;
+    const uint32_t even = 0x55555555u;
+    const uint32_t odd_starts = b & ~even & ~follows;
+    const uint32_t seq = odd_starts + b;
+    carry = seq < b ? 1u : 0u; // add overflow
+    return (even ^ (seq << 1)) & follows;
+}
+
+// returns bytes produced (before truncation to `cap` by the caller) or -1; out = this warp's buffer
+__device__ int dec_lz_warp(const uint8_t *__restrict__ in, int len, int orig, uint8_t *out)
+{
+    if (len <= 0) return 0;
+    const int lane = threadIdx.x & 31;
+    const int nfull = len >= 4 ? (len - 2) >> 1 : 0; // slots whose token is complete whatever its kind
+    uint32_t carry = 0, tail_skipped = 0;
+    int o = 0;
+    bool stop = false, irregular = false;
+    // software pipeline: token bytes of the next 32 slots are loaded while this window is decoded
+    uint32_t nf = 0, nb1 = 0, nb2 = 0, nb3 = 0;
+    {
+        const int slot = lane;
+        if (slot < nfull) { const uint8_t *q = in + 2 * slot; nf = q[0]; nb1 = q[1]; nb2 = q[2]; nb3 = q[3]; }
+    }
+    for (int base = 0; base < nfull && !stop; base += 32) {
+        const uint32_t f = nf, b1 = nb1, b2 = nb2, b3 = nb3;
+        {
+            const int slot = base + 32 + lane;
+            nf = nb1 = nb2 = nb3 = 0;
+            if (slot < nfull) { const uint8_t *q = in + 2 * slot; nf = q[0]; nb1 = q[1]; nb2 = q[2]; nb3 = q[3]; }
+        }
+        const int slot = base + lane;
+        const uint32_t valid = __ballot_sync(FULL_MASK, slot < nfull);
+        const uint32_t M = __ballot_sync(FULL_MASK, f != 0) & valid;
+        const uint32_t skipped = dlz_skipped(M, carry);
+        // is the first slot after the full region the second half of a match token?
+        tail_skipped = nfull - base < 32 ? (skipped >> (nfull - base)) & 1u : carry;
+        const uint32_t S = ~skipped & valid;
+        const bool is_start = (S >> lane) & 1u;
+        const bool is_match = is_start && f != 0;
+        const int mlen = (int)b3, dist = (int)(b1 | (b2 << 8));
+        const int v = is_start ? (is_match ? mlen : 1) : 0;
+        int inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(FULL_MASK, inc, d);
+            if (lane >= d) inc += t;
+        }
+        const int off = o + inc - v;
+        const bool exec = is_start && off < orig; // the walk stops once orig_len bytes exist (:249)
+        if (__ballot_sync(FULL_MASK, is_start && !exec)) stop = true;
+        if (exec && !is_match) out[off] = (uint8_t)b1;
+        const bool bad = exec && is_match && (dist == 0 || dist > off);
+        if (__ballot_sync(FULL_MASK, bad)) { irregular = true; break; }
+        uint32_t mm = __ballot_sync(FULL_MASK, exec && is_match);
+        __syncwarp();
+        while (mm) {
+            const int i = __ffs(mm) - 1;
+            mm &= mm - 1;
+            const int moff = __shfl_sync(FULL_MASK, off, i);
+            const int mdist = __shfl_sync(FULL_MASK, dist, i);
+            const int ml = __shfl_sync(FULL_MASK, mlen, i);
+            const uint8_t *srcp = out + moff - mdist;
+            if (mdist >= ml) {
+                for (int t = lane; t < ml; t += 32) out[moff + t] = srcp[t];
+            } else { // overlapping copy = periodic extension of the last `dist` bytes
+                for (int t = lane; t < ml; t += 32) out[moff + t] = srcp[t % mdist];
+            }
+            __syncwarp();
+        }
+        const int tot = __shfl_sync(FULL_MASK, inc, 31);
+        if (stop) { // o = end of the last executed token
+            const int endv = exec ? off + v : 0;
+            int m = endv;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(FULL_MASK, m, d));
+            o = max(m, o);
+        } else o += tot;
+    }
+    int result;
+    if (irregular) {
+        int r = 0;
+        if (lane == 0) r = lz_walk(in, len, orig, out, DLZ_OUT);
+        result = __shfl_sync(FULL_MASK, r, 0);
+    } else {
+        if (!stop) { // the last <= 3 bytes: incomplete tokens, serial rules
+            int r = o;
+            if (lane == 0) {
+                long pos = 2L * nfull + (tail_skipped ? 2 : 0);
+                long oo = o;
+                while (pos < len && oo < orig) {
+                    uint8_t flag = in[pos++];
+                    if (flag == 0) {
+                        if (pos < len) { uint8_t vb = in[pos++]; if (oo < DLZ_OUT) out[oo] = vb; oo++; }
+                    } else if (pos + 2 < len) {
+                        r = -2; break; // cannot happen: a complete match token lies in the full region
+                    }
+                }
+                if (r != -2) r = (int)oo;
+            }
+            o = __shfl_sync(FULL_MASK, r, 0);
+            if (o == -2) {
+                int r2 = 0;
+                if (lane == 0) r2 = lz_walk(in, len, orig, out, DLZ_OUT);
+                o = __shfl_sync(FULL_MASK, r2, 0);
+                __syncwarp();
+                return o;
+            }
+        }
+        result = o < orig ? o : orig;
+    }
+    __syncwarp();
+    return result;
+}
+
 __device__ inline int dec_lz(DecCtx &d, int len, int orig)
 {
     volatile int *res = d.red;
-    if (threadIdx.x == 0) res[24] = lz_walk(d.in, len, orig, d.out, DEC_OUT_CAP + DEC_OUT_SLACK);
+    if (orig <= 4096) { // warp 0 decodes, same code as k_decode_lz
+        if (threadIdx.x < 32) {
+            int r = dec_lz_warp(d.in, len, orig, d.out);
+            if (threadIdx.x == 0) res[24] = r;
+        }
+    } else if (threadIdx.x == 0) res[24] = lz_walk(d.in, len, orig, d.out, DEC_OUT_CAP + DEC_OUT_SLACK);
     __syncthreads();
     int r = res[24];
     __syncthreads();

@@ -11,67 +11,69 @@
 //   name_4      hash of the 4 raw bytes (verified against the data),
 //   name_3      only for heads of name_4 (a 4-byte match implies the 3-byte one),
 //   name_2k     from the pair (name_k[p], name_k[p + k])                        (k = 4, 8, 16),
-//   name_{k+j}  from the pair (name_k[p], name_k[p + j]), 0 < j < k, only for positions that
-//               are heads at 2k and whose k-gram occurs elsewhere (everybody else either has a
-//               match of >= 2k bytes or no k-byte match at all).
+//   name_{k+j}  from the pair (name_k[p], name_k[p + j]), 0 < j < k, only for "participants":
+//               heads at 2k whose k-gram occurs elsewhere (everybody else either has a match of
+//               >= 2k bytes or no k-byte match at all).  The lengths of a bracket are visited in
+//               binary-search order; a participant enters length m of the interval (lo, hi) only
+//               if it is a head at hi and its lo-gram occurs elsewhere -- the first occurrence of
+//               any m-gram that somebody matches always satisfies both.
 // Every "first occurrence of a key" is one open-addressing insert with atomicMin on the position;
-// keys are verified through the name arrays, so the result is exact for any hash function.
+// a later arrival at a key clears the slot's `single` bit ("this gram occurs more than once").
+// Keys are verified through the name arrays, so the result is exact for any hash function.
+// Names carry bit 15 = "the class has more than one member".
 // Block-collective; returns false when a table overflowed (caller falls back to the bucket search).
 #pragma once
 
 #define LZ2_EMPTY 0xFFFFFFFFu
 #define LZ2_GOLD 2654435761u
-#define LZ2_RSLOTS 4096          // table slots of a refinement pass (plist / islot live above them)
+#define LZ2_NS 0x8000u           // name flag: the gram occurs at more than one position
+#define LZ2_RSLOTS 4096          // table slots of a refinement pass
 #define LZ2_PART_TARGET 1365     // expected entries per refinement pass (load factor 1/3)
+#define LZ2_BIN_MAXP 2048        // participants the binary-order refinement handles
+#define LZ2_ISLOTS 4096          // slot memo entries
 
-__device__ __forceinline__ void lz2_clear(uint32_t *T, int slots)
+// slot value = tag << 16 | position << 1 | single: the claiming insert stores single = 1, every
+// later arrival at the same key clears it (atomicMin with an even value, or atomicAnd)
+__device__ __forceinline__ void lz2_clear(ChunkCtx &c, int slots)
 {
     for (int i = threadIdx.x * 4; i < slots; i += AMBC_BLOCK * 4)
-        *(uint4 *)(T + i) = make_uint4(LZ2_EMPTY, LZ2_EMPTY, LZ2_EMPTY, LZ2_EMPTY);
+        *(uint4 *)(c.T + i) = make_uint4(LZ2_EMPTY, LZ2_EMPTY, LZ2_EMPTY, LZ2_EMPTY);
 }
+__device__ __forceinline__ uint32_t lz2_slot_pos(uint32_t v) { return (v >> 1) & 0x7FFFu; }
+__device__ __forceinline__ uint32_t lz2_slot_name(uint32_t v) { return ((v >> 1) & 0xFFFu) | ((v & 1u) ? 0u : LZ2_NS); }
 
-__device__ __forceinline__ bool lz2_ns(const uint16_t *S, const uint32_t *fol, int p)
+// first occurrence of the raw key `w` (bytes of sd + p under kmask): insert p, return the slot
+__device__ __forceinline__ uint32_t lz2_insert_raw(ChunkCtx &c, uint32_t w, uint32_t kmask, int p)
 {
-    return S[p] != p || ((fol[p >> 5] >> (p & 31)) & 1u);
-}
-
-// first occurrence of the raw key `w` (the low `bytes` bytes at sd + p): insert p, return the slot
-__device__ __forceinline__ uint32_t lz2_insert_raw(uint32_t *T, const uint8_t *sd, uint32_t w, uint32_t kmask, int p)
-{
-    volatile uint32_t *V = T;
     uint32_t s = (w * LZ2_GOLD) >> (32 - 13);
+    const uint32_t val = ((uint32_t)p << 1) | 1u;
     for (;;) {
-        uint32_t q = V[s];
-        if (q == LZ2_EMPTY) {
-            q = atomicCAS(&T[s], LZ2_EMPTY, (uint32_t)p);
-            if (q == LZ2_EMPTY) return s;
-        }
-        if ((lds_u32u(sd + q) & kmask) == w) {
-            if ((uint32_t)p < q) atomicMin(&T[s], (uint32_t)p);
+        const uint32_t q = atomicCAS(&c.T[s], LZ2_EMPTY, val);
+        if (q == LZ2_EMPTY) return s;
+        if ((lds_u32u(c.sd + lz2_slot_pos(q)) & kmask) == w) {
+            if (val < q) atomicMin(&c.T[s], val & ~1u);
+            else if (q & 1u) atomicAnd(&c.T[s], ~1u);
             return s;
         }
         s = (s + 1) & (LZ2_TSLOTS - 1);
     }
 }
 
-// first occurrence of the key (S[p], S[p + j], tag) in a table of (mask + 1) slots.
+// first occurrence of the key (S[p] = a, S[p + j] = b, tag) in a table of (mask + 1) slots.
 // Returns the slot, or 0xFFFF and sets *overflow when the table is full.
-__device__ __forceinline__ uint32_t lz2_insert_pair(uint32_t *T, uint32_t mask, uint32_t h, const uint16_t *S,
+__device__ __forceinline__ uint32_t lz2_insert_pair(ChunkCtx &c, uint32_t mask, uint32_t h, const uint16_t *S,
                                                     uint32_t a, uint32_t b, int p, int j, uint32_t tag, int *overflow)
 {
-    volatile uint32_t *V = T;
     uint32_t s = h & mask;
-    const uint32_t val = (tag << 16) | (uint32_t)p;
+    const uint32_t val = (tag << 16) | ((uint32_t)p << 1) | 1u;
     for (uint32_t probes = 0; probes <= mask; probes++) {
-        uint32_t q = V[s];
-        if (q == LZ2_EMPTY) {
-            q = atomicCAS(&T[s], LZ2_EMPTY, val);
-            if (q == LZ2_EMPTY) return s;
-        }
+        const uint32_t q = atomicCAS(&c.T[s], LZ2_EMPTY, val);
+        if (q == LZ2_EMPTY) return s;
         if ((q >> 16) == tag) {
-            const uint32_t qp = q & 0xFFFFu;
+            const uint32_t qp = lz2_slot_pos(q);
             if (S[qp] == a && S[qp + j] == b) {
-                if (val < q) atomicMin(&T[s], val);
+                if (val < q) atomicMin(&c.T[s], val & ~1u);
+                else if (q & 1u) atomicAnd(&c.T[s], ~1u);
                 return s;
             }
         }
@@ -81,17 +83,16 @@ __device__ __forceinline__ uint32_t lz2_insert_pair(uint32_t *T, uint32_t mask, 
     return 0xFFFFu;
 }
 
-// name_4 for every position (D), follower bits (folD), matches of length 4.  Returns "any match".
-__device__ inline int lz2_level4(ChunkCtx &c, uint16_t *D, uint32_t *folD)
+// name_4 (D) for every position, matches of length 4.  Returns "any match".
+__device__ inline int lz2_level4(ChunkCtx &c, uint16_t *D)
 {
     const int n = c.n, tid = threadIdx.x;
-    lz2_clear(c.T, LZ2_TSLOTS);
-    for (int i = tid; i < LZ2_NMAX / 32; i += AMBC_BLOCK) folD[i] = 0;
+    lz2_clear(c, LZ2_TSLOTS);
     __syncthreads();
     const int P = n - 3;
     for (int p = tid; p < n; p += AMBC_BLOCK) {
         uint32_t slot = 0xFFFFu;
-        if (p < P) slot = lz2_insert_raw(c.T, c.sd, lds_u32u(c.sd + p), 0xFFFFFFFFu, p);
+        if (p < P) slot = lz2_insert_raw(c, lds_u32u(c.sd + p), 0xFFFFFFFFu, p);
         D[p] = (uint16_t)slot;
     }
     __syncthreads();
@@ -99,13 +100,9 @@ __device__ inline int lz2_level4(ChunkCtx &c, uint16_t *D, uint32_t *folD)
     for (int p = tid; p < n; p += AMBC_BLOCK) {
         const uint32_t slot = D[p];
         uint32_t nm = (uint32_t)p;
-        if (slot != 0xFFFFu) nm = c.T[slot];
+        if (slot != 0xFFFFu) nm = lz2_slot_name(c.T[slot]);
         D[p] = (uint16_t)nm;
-        if (nm < (uint32_t)p) {
-            c.mlen[p] = 4; c.mpos[p] = (uint16_t)nm;
-            atomicOr(&folD[nm >> 5], 1u << (nm & 31));
-            nonhead = 1;
-        }
+        if ((nm & 0xFFFu) < (uint32_t)p) { c.mlen[p] = 4; c.mpos[p] = (uint16_t)(nm & 0xFFFu); nonhead = 1; }
     }
     return __syncthreads_or(nonhead);
 }
@@ -114,19 +111,19 @@ __device__ inline int lz2_level4(ChunkCtx &c, uint16_t *D, uint32_t *folD)
 __device__ inline void lz2_level3(ChunkCtx &c, const uint16_t *N4, uint16_t *tmp)
 {
     const int n = c.n, tid = threadIdx.x;
-    lz2_clear(c.T, LZ2_TSLOTS);
+    lz2_clear(c, LZ2_TSLOTS);
     __syncthreads();
     for (int p = tid; p < n; p += AMBC_BLOCK) {
         uint32_t slot = 0xFFFFu;
-        if (p + 3 <= n && N4[p] == p) // (positions past n - 4 are their own name)
-            slot = lz2_insert_raw(c.T, c.sd, lds_u32u(c.sd + p) & 0xFFFFFFu, 0xFFFFFFu, p);
+        if (p + 3 <= n && (N4[p] & 0xFFFu) == p) // (positions past n - 4 are their own name)
+            slot = lz2_insert_raw(c, lds_u32u(c.sd + p) & 0xFFFFFFu, 0xFFFFFFu, p);
         tmp[p] = (uint16_t)slot;
     }
     __syncthreads();
     for (int p = tid; p < n; p += AMBC_BLOCK) {
         const uint32_t slot = tmp[p];
         if (slot != 0xFFFFu) {
-            const uint32_t nm = c.T[slot];
+            const uint32_t nm = lz2_slot_pos(c.T[slot]);
             if (nm < (uint32_t)p) { c.mlen[p] = 3; c.mpos[p] = (uint16_t)nm; }
         }
     }
@@ -135,20 +132,21 @@ __device__ inline void lz2_level3(ChunkCtx &c, const uint16_t *N4, uint16_t *tmp
 
 // name_2k (D) from name_k (S).  Positions whose k-gram at p or at p + k occurs nowhere else are
 // heads by construction and do not enter the table.  Returns "any match of 2k bytes".
-__device__ inline int lz2_double(ChunkCtx &c, const uint16_t *S, uint16_t *D, const uint32_t *folS, uint32_t *folD, int k)
+__device__ inline int lz2_double(ChunkCtx &c, const uint16_t *S, uint16_t *D, int k)
 {
     const int n = c.n, tid = threadIdx.x;
-    lz2_clear(c.T, LZ2_TSLOTS);
-    for (int i = tid; i < LZ2_NMAX / 32; i += AMBC_BLOCK) folD[i] = 0;
+    lz2_clear(c, LZ2_TSLOTS);
     __syncthreads();
     const int P = n - 2 * k + 1;
     int dummy = 0;
     for (int p = tid; p < n; p += AMBC_BLOCK) {
         uint32_t slot = 0xFFFFu;
-        if (p < P && lz2_ns(S, folS, p) && lz2_ns(S, folS, p + k)) {
+        if (p < P) {
             const uint32_t a = S[p], b = S[p + k];
-            const uint32_t h = ((a | (b << 12)) * LZ2_GOLD) >> (32 - 13);
-            slot = lz2_insert_pair(c.T, LZ2_TSLOTS - 1, h, S, a, b, p, k, 0u, &dummy);
+            if (a & b & LZ2_NS) {
+                const uint32_t h = ((a | (b << 16)) * LZ2_GOLD) >> (32 - 13);
+                slot = lz2_insert_pair(c, LZ2_TSLOTS - 1, h, S, a, b, p, k, 0u, &dummy);
+            }
         }
         D[p] = (uint16_t)slot;
     }
@@ -157,51 +155,54 @@ __device__ inline int lz2_double(ChunkCtx &c, const uint16_t *S, uint16_t *D, co
     for (int p = tid; p < n; p += AMBC_BLOCK) {
         const uint32_t slot = D[p];
         uint32_t nm = (uint32_t)p;
-        if (slot != 0xFFFFu) nm = c.T[slot] & 0xFFFFu;
+        if (slot != 0xFFFFu) nm = lz2_slot_name(c.T[slot]);
         D[p] = (uint16_t)nm;
-        if (nm < (uint32_t)p) {
-            c.mlen[p] = (uint8_t)(2 * k); c.mpos[p] = (uint16_t)nm;
-            atomicOr(&folD[nm >> 5], 1u << (nm & 31));
+        if ((nm & 0xFFFu) < (uint32_t)p) {
+            c.mlen[p] = (uint8_t)(2 * k); c.mpos[p] = (uint16_t)(nm & 0xFFFu);
             nonhead = 1;
         }
     }
     return __syncthreads_or(nonhead);
 }
 
-// lengths k+1 .. 2k-1.  S = name_k, D = name_2k, folS = follower bits of level k.
-// Returns false on table overflow.
-__device__ inline bool lz2_refine(ChunkCtx &c, const uint16_t *S, const uint16_t *D, const uint32_t *folS, int k)
+// ---- lengths k+1 .. 2k-1 --------------------------------------------------------------------
+// participant list: heads of their 2k-gram whose k-gram occurs elsewhere, with room for k+1 bytes
+__device__ inline int lz2_participants(ChunkCtx &c, const uint16_t *S, const uint16_t *D, int k, uint16_t *plist, int cap)
 {
     const int n = c.n, tid = threadIdx.x, lane = tid & 31;
-    uint16_t *plist = (uint16_t *)(c.T + LZ2_RSLOTS);        // 4096 entries
-    uint16_t *islot = plist + LZ2_NMAX;                      // 4096 entries
     volatile int *cnt = c.red + 30;
-    volatile int *ovf = c.red + 31;
-    if (tid == 0) { *cnt = 0; *ovf = 0; }
+    if (tid == 0) *cnt = 0;
     __syncthreads();
-    // participants: heads of their 2k-gram whose k-gram occurs elsewhere, with room for k+1 bytes
     const int Pmax = n - k - 1;
     for (int p0 = 0; p0 <= Pmax; p0 += AMBC_BLOCK) {
         const int p = p0 + tid;
-        const bool pred = p <= Pmax && D[p] == p && lz2_ns(S, folS, p);
+        const bool pred = p <= Pmax && (D[p] & 0xFFFu) == p && (S[p] & LZ2_NS);
         const uint32_t m = __ballot_sync(FULL_MASK, pred);
         if (m) {
             int base = 0;
             if (lane == 0) base = atomicAdd((int *)cnt, __popc(m));
             base = __shfl_sync(FULL_MASK, base, 0);
-            if (pred) plist[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)p;
+            const int at = base + __popc(m & ((1u << lane) - 1));
+            if (pred && at < cap) plist[at] = (uint16_t)p;
         }
     }
     __syncthreads();
-    const int np = *cnt;
-    if (np == 0) return true;
+    return *cnt;
+}
+
+// every participant enters every length (np > LZ2_BIN_MAXP, and the fallback of the binary order)
+__device__ inline bool lz2_refine_flat(ChunkCtx &c, const uint16_t *S, int k, int np, const uint16_t *plist, uint16_t *islot)
+{
+    const int n = c.n, tid = threadIdx.x;
+    volatile int *ovf = c.red + 31;
+    if (tid == 0) *ovf = 0;
     // pass = (group of nj consecutive lengths) x (one of R key partitions)
     int G = LZ2_PART_TARGET / np, R = 1;
     if (G < 1) { G = 1; while (R * LZ2_PART_TARGET < np) R <<= 1; }
     for (int j0 = 1; j0 < k; j0 += G) {
         const int nj = min(G, k - j0);
         for (int r = 0; r < R; r++) {
-            lz2_clear(c.T, LZ2_RSLOTS);
+            lz2_clear(c, LZ2_RSLOTS);
             __syncthreads();
             int overflow = 0;
             for (int jj = 0; jj < nj; jj++) {
@@ -209,25 +210,29 @@ __device__ inline bool lz2_refine(ChunkCtx &c, const uint16_t *S, const uint16_t
                 for (int pi = tid; pi < np; pi += AMBC_BLOCK) {
                     const int p = plist[pi];
                     uint32_t slot = 0xFFFFu;
-                    if (p + k + j <= n && lz2_ns(S, folS, p + j)) {
+                    if (p + k + j <= n) {
                         const uint32_t a = S[p], b = S[p + j];
-                        const uint32_t h = (a | (b << 12) | ((uint32_t)jj << 24)) * LZ2_GOLD;
-                        if (((h >> 16) & (uint32_t)(R - 1)) == (uint32_t)r)
-                            slot = lz2_insert_pair(c.T, LZ2_RSLOTS - 1, h >> 20, S, a, b, p, j, (uint32_t)jj, &overflow);
+                        if (b & LZ2_NS) {
+                            const uint32_t h = ((a | (b << 16)) + (uint32_t)jj * 0x9E3779B9u) * LZ2_GOLD;
+                            if (((h >> 16) & (uint32_t)(R - 1)) == (uint32_t)r)
+                                slot = lz2_insert_pair(c, LZ2_RSLOTS - 1, h >> 20, S, a, b, p, j, (uint32_t)jj, &overflow);
+                        }
                     }
                     islot[jj * np + pi] = (uint16_t)slot;
                 }
             }
             if (overflow) *ovf = 1;
             __syncthreads();
-            for (int jj = 0; jj < nj; jj++) { // ascending lengths; one thread owns all lengths of a participant
-                const int L = k + j0 + jj;
-                for (int pi = tid; pi < np; pi += AMBC_BLOCK) {
+            for (int pi = tid; pi < np; pi += AMBC_BLOCK) { // one thread owns all lengths of a participant
+                const int p = plist[pi];
+                for (int jj = nj - 1; jj >= 0; jj--) {       // longest first: a match implies the shorter ones
                     const uint32_t slot = islot[jj * np + pi];
-                    if (slot != 0xFFFFu) {
-                        const int p = plist[pi];
-                        const uint32_t nm = c.T[slot] & 0xFFFFu;
-                        if (nm < (uint32_t)p && L > (int)c.mlen[p]) { c.mlen[p] = (uint8_t)L; c.mpos[p] = (uint16_t)nm; }
+                    if (slot == 0xFFFFu) continue;
+                    const uint32_t nm = lz2_slot_pos(c.T[slot]);
+                    if (nm < (uint32_t)p) {
+                        const int L = k + j0 + jj;
+                        if (L > (int)c.mlen[p]) { c.mlen[p] = (uint8_t)L; c.mpos[p] = (uint16_t)nm; }
+                        break;
                     }
                 }
             }
@@ -238,21 +243,113 @@ __device__ inline bool lz2_refine(ChunkCtx &c, const uint16_t *S, const uint16_t
     return true;
 }
 
+// binary-search order over the lengths of the bracket; returns 0 = done, 1 = use the flat method, -1 = overflow
+__device__ inline int lz2_refine_binary(ChunkCtx &c, const uint16_t *S, int k, int np, const uint16_t *plist,
+                                        uint8_t *mem, uint8_t *mem2, uint16_t *islot)
+{
+    const int n = c.n, tid = threadIdx.x;
+    volatile int *ovf = c.red + 31;
+    if (tid == 0) *ovf = 0;
+    for (int pi = tid; pi < np; pi += AMBC_BLOCK) { mem[pi] = 1; mem2[pi] = 0; }
+    __syncthreads();
+    for (int step = k >> 1; step >= 1; step >>= 1) {
+        // node t of this round: length k + (2t+1) * step inside the interval of half-width `step`
+        int cntl = 0;
+        for (int pi = tid; pi < np; pi += AMBC_BLOCK) cntl += __popc((uint32_t)mem[pi]);
+        int E;
+        const int base = block_excl_scan(cntl, c.red, &E);
+        if (E > LZ2_ISLOTS) return 1;
+        if (E == 0) return 0;
+        int R = 1;
+        while (R * LZ2_PART_TARGET < E) R <<= 1;
+        for (int r = 0; r < R; r++) {
+            lz2_clear(c, LZ2_RSLOTS);
+            __syncthreads();
+            int overflow = 0, idx = base;
+            for (int pi = tid; pi < np; pi += AMBC_BLOCK) {
+                const int p = plist[pi];
+                uint32_t m = mem[pi];
+                const uint32_t a = S[p];
+                while (m) {
+                    const int t = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int j = (2 * t + 1) * step;
+                    uint32_t slot = 0xFFFEu; // 0xFFFE: unique by construction (head, no follower)
+                    if (p + k + j <= n) {
+                        const uint32_t b = S[p + j];
+                        if (b & LZ2_NS) {
+                            const uint32_t h = ((a | (b << 16)) + (uint32_t)t * 0x9E3779B9u) * LZ2_GOLD;
+                            slot = 0xFFFFu;  // 0xFFFF: belongs to another partition pass
+                            if (((h >> 16) & (uint32_t)(R - 1)) == (uint32_t)r)
+                                slot = lz2_insert_pair(c, LZ2_RSLOTS - 1, h >> 20, S, a, b, p, j, (uint32_t)t, &overflow);
+                        }
+                    }
+                    islot[idx++] = (uint16_t)slot;
+                }
+            }
+            if (overflow) *ovf = 1;
+            __syncthreads();
+            idx = base;
+            for (int pi = tid; pi < np; pi += AMBC_BLOCK) {
+                const int p = plist[pi];
+                uint32_t m = mem[pi], nm2 = mem2[pi];
+                while (m) {
+                    const int t = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t slot = islot[idx++];
+                    if (slot == 0xFFFFu) continue;
+                    if (slot == 0xFFFEu) { if (r == 0) nm2 |= 1u << (2 * t); continue; }
+                    const uint32_t v = c.T[slot];
+                    const uint32_t nm = lz2_slot_pos(v);
+                    if (nm < (uint32_t)p) {
+                        const int L = k + (2 * t + 1) * step;
+                        if (L > (int)c.mlen[p]) { c.mlen[p] = (uint8_t)L; c.mpos[p] = (uint16_t)nm; }
+                    } else nm2 |= 1u << (2 * t);               // head at m: lengths below m remain
+                    if (!(v & 1u)) nm2 |= 1u << (2 * t + 1);  // occurs elsewhere: lengths above m remain
+                }
+                mem2[pi] = (uint8_t)nm2;
+            }
+            __syncthreads();
+            if (*ovf) return -1;
+        }
+        for (int pi = tid; pi < np; pi += AMBC_BLOCK) { mem[pi] = mem2[pi]; mem2[pi] = 0; }
+        __syncthreads();
+    }
+    return 0;
+}
+
+// S = name_k, D = name_2k.  Returns false on table overflow.
+__device__ inline bool lz2_refine(ChunkCtx &c, const uint16_t *S, const uint16_t *D, int k)
+{
+    uint8_t *R0 = (uint8_t *)(c.T + LZ2_RSLOTS); // 16 KiB above the pass table
+    uint16_t *plist = (uint16_t *)R0;
+    const int np = lz2_participants(c, S, D, k, plist, LZ2_NMAX);
+    if (np == 0) return true;
+    if (np <= LZ2_BIN_MAXP && k > 4) {
+        // plist 4 KiB | mem 2 KiB | mem2 2 KiB | islot 8 KiB
+        const int rc = lz2_refine_binary(c, S, k, np, plist, R0 + 4096, R0 + 6144, (uint16_t *)(R0 + 8192));
+        if (rc == 0) return true;
+        if (rc < 0) return false;
+        __syncthreads();
+    }
+    if (np <= LZ2_BIN_MAXP) return lz2_refine_flat(c, S, k, np, plist, (uint16_t *)(R0 + 8192));
+    return lz2_refine_flat(c, S, k, np, plist, plist + LZ2_NMAX);
+}
+
 // mlen / mpos for every position of the chunk (c.mlen zeroed by the caller).  n <= LZ2_NMAX.
 __device__ inline bool lz2_match_all(ChunkCtx &c)
 {
     uint16_t *A = c.nameA, *B = c.nameB;
-    uint32_t *f0 = c.fol, *f1 = c.fol + LZ2_NMAX / 32;
     if (c.n < 3) return true;
-    const int any4 = lz2_level4(c, A, f0);
+    const int any4 = lz2_level4(c, A);
     lz2_level3(c, A, B);
     if (!any4) return true;
-    const int any8 = lz2_double(c, A, B, f0, f1, 4);
-    if (!lz2_refine(c, A, B, f0, 4)) return false;
+    const int any8 = lz2_double(c, A, B, 4);
+    if (!lz2_refine(c, A, B, 4)) return false;
     if (!any8) return true;
-    const int any16 = lz2_double(c, B, A, f1, f0, 8);
-    if (!lz2_refine(c, B, A, f1, 8)) return false;
+    const int any16 = lz2_double(c, B, A, 8);
+    if (!lz2_refine(c, B, A, 8)) return false;
     if (!any16) return true;
-    lz2_double(c, A, B, f0, f1, 16);
-    return lz2_refine(c, A, B, f0, 16);
+    lz2_double(c, A, B, 16);
+    return lz2_refine(c, A, B, 16);
 }
