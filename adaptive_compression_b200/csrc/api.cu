@@ -108,6 +108,8 @@ struct HostCtx {
     cudaStream_t stream = nullptr;
     std::vector<ambc_pkg> host_table;
 };
+int ambc_index_vector(const uint8_t *body, uint64_t body_len, const uint8_t *marker, uint32_t mb, uint64_t orig_size,
+                      uint32_t known_mask, std::vector<ambc_pkg> &v, uint64_t *n_entries, uint64_t *out_bytes);
 static std::mutex g_mu;
 static HostCtx g_ctx[16];
 
@@ -169,12 +171,8 @@ extern "C" int ambc_decompress_host(const void *body_host, uint64_t body_len, co
     // start the body upload first; the index walk on the host overlaps with it
     if ((rc = c->in.ensure(body_len + 64))) return rc;
     if (body_len) CUDA_TRY(cudaMemcpyAsync(c->in.p, body_host, body_len, cudaMemcpyHostToDevice, c->stream));
-    rc = ambc_index_host((const uint8_t *)body_host, body_len, marker, marker_bytes, orig_size, known_mask, nullptr, 0,
-                         &ne, &covered);
-    if (rc) { cudaStreamSynchronize(c->stream); return rc; }
-    c->host_table.resize(ne ? ne : 1);
-    rc = ambc_index_host((const uint8_t *)body_host, body_len, marker, marker_bytes, orig_size, known_mask,
-                         c->host_table.data(), ne, &ne, &covered);
+    rc = ambc_index_vector((const uint8_t *)body_host, body_len, marker, marker_bytes, orig_size, known_mask,
+                           c->host_table, &ne, &covered);
     if (rc) { cudaStreamSynchronize(c->stream); return rc; }
     if ((rc = c->out.ensure(orig_size + 64))) return rc;
     if ((rc = c->table.ensure(ne * sizeof(ambc_pkg) + 64))) return rc;

@@ -2,6 +2,7 @@
 // Replaces AdaptiveCompressor._adaptive_decompress (adaptive_compressor.py:396-454).
 #include "ambc_internal.h"
 #include "decode_codec.cuh"
+#include <vector>
 
 #define RAW_PIECE 65536u
 
@@ -23,9 +24,10 @@ static inline uint64_t nominal_out(uint32_t type, bool known, uint32_t comp, uin
     }
 }
 
-extern "C" int ambc_index_host(const uint8_t *body, uint64_t body_len, const uint8_t *marker, uint32_t mb,
-                               uint64_t orig_size, uint32_t known_mask, ambc_pkg *table, uint64_t table_cap,
-                               uint64_t *n_entries, uint64_t *out_bytes)
+// the walk itself; emit(entry) returns false when the caller's table is full
+template <class Emit>
+static int index_walk(const uint8_t *body, uint64_t body_len, const uint8_t *marker, uint32_t mb, uint64_t orig_size,
+                      uint32_t known_mask, Emit emit, uint64_t *n_entries, uint64_t *out_bytes)
 {
     if (!marker || mb < 1 || mb > 4 || (body_len && !body)) return ambc_fail(AMBC_E_ARG, "ambc_index_host: bad argument");
     uint64_t pos = 0, o = 0, ne = 0;
@@ -44,31 +46,27 @@ extern "C" int ambc_index_host(const uint8_t *body, uint64_t body_len, const uin
         bool known = type == 255 || (type < 32 && ((known_mask >> type) & 1u));
         uint64_t nominal = nominal_out(type, known, comp, orig);
         uint64_t room = orig_size > o ? orig_size - o : 0;
-        uint64_t emit = nominal < room ? nominal : room;
-        if (emit) {
+        uint64_t emitn = nominal < room ? nominal : room;
+        if (emitn) {
             if (!known || type == 255) {
                 // plain bytes (+ zero pad): pieces of at most 64 KiB
                 uint64_t done = 0;
-                while (done < emit) {
-                    uint64_t piece = emit - done < RAW_PIECE ? emit - done : RAW_PIECE;
+                while (done < emitn) {
+                    uint64_t piece = emitn - done < RAW_PIECE ? emitn - done : RAW_PIECE;
                     uint64_t have = comp > done ? comp - done : 0; // payload bytes left for this piece
-                    if (table) {
-                        if (ne >= table_cap) return ambc_fail(AMBC_E_CAPACITY, "ambc_index_host: table too small");
-                        ambc_pkg &e = table[ne];
-                        e.src_off = pos + done; e.dst_off = o + done;
-                        e.comp_len = (uint32_t)(have < piece ? have : piece);
-                        e.orig_len = (uint32_t)piece; e.type = 255; e.out_len = (uint32_t)piece;
-                    }
+                    ambc_pkg e;
+                    e.src_off = pos + done; e.dst_off = o + done;
+                    e.comp_len = (uint32_t)(have < piece ? have : piece);
+                    e.orig_len = (uint32_t)piece; e.type = 255; e.out_len = (uint32_t)piece;
+                    if (!emit(e, ne)) return ambc_fail(AMBC_E_CAPACITY, "ambc_index_host: table too small");
                     ne++;
                     done += piece;
                 }
             } else {
-                if (table) {
-                    if (ne >= table_cap) return ambc_fail(AMBC_E_CAPACITY, "ambc_index_host: table too small");
-                    ambc_pkg &e = table[ne];
-                    e.src_off = pos; e.dst_off = o; e.comp_len = comp; e.orig_len = orig; e.type = type;
-                    e.out_len = (uint32_t)emit;
-                }
+                ambc_pkg e;
+                e.src_off = pos; e.dst_off = o; e.comp_len = comp; e.orig_len = orig; e.type = type;
+                e.out_len = (uint32_t)emitn;
+                if (!emit(e, ne)) return ambc_fail(AMBC_E_CAPACITY, "ambc_index_host: table too small");
                 ne++;
             }
         }
@@ -79,6 +77,33 @@ extern "C" int ambc_index_host(const uint8_t *body, uint64_t body_len, const uin
     if (n_entries) *n_entries = ne;
     if (out_bytes) *out_bytes = o < orig_size ? o : orig_size;
     return AMBC_OK;
+}
+
+extern "C" int ambc_index_host(const uint8_t *body, uint64_t body_len, const uint8_t *marker, uint32_t mb,
+                               uint64_t orig_size, uint32_t known_mask, ambc_pkg *table, uint64_t table_cap,
+                               uint64_t *n_entries, uint64_t *out_bytes)
+{
+    return index_walk(body, body_len, marker, mb, orig_size, known_mask,
+                      [&](const ambc_pkg &e, uint64_t i) {
+                          if (!table) return true; // counting pass
+                          if (i >= table_cap) return false;
+                          table[i] = e;
+                          return true;
+                      },
+                      n_entries, out_bytes);
+}
+
+// one walk into a growing vector (ambc_decompress_host)
+int ambc_index_vector(const uint8_t *body, uint64_t body_len, const uint8_t *marker, uint32_t mb, uint64_t orig_size,
+                      uint32_t known_mask, std::vector<ambc_pkg> &v, uint64_t *n_entries, uint64_t *out_bytes)
+{
+    return index_walk(body, body_len, marker, mb, orig_size, known_mask,
+                      [&](const ambc_pkg &e, uint64_t i) {
+                          if (i >= v.size()) v.resize(v.size() < 1024 ? 4096 : v.size() * 2);
+                          v[i] = e;
+                          return true;
+                      },
+                      n_entries, out_bytes);
 }
 
 // ---- kernel ----------------------------------------------------------------------------------

@@ -127,7 +127,7 @@ class ClockSampler:
                     self.rows.append(parts)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.1)
+            time.sleep(0.02)
 
     def __enter__(self):
         self.th.start()
@@ -277,6 +277,12 @@ def run_b200(args):
         if os.path.exists(pk_path):
             peaks = json.load(open(pk_path))
             peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        traffic = args.traffic
+        tr_path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if traffic is None and os.path.exists(tr_path):
+            tr = json.load(open(tr_path))
+            if tr.get("bytes_per_gpu") == n and tr.get("chunk") == CHUNK:  # same launch shape as the capture
+                traffic = tr["traffic_bytes_per_launch"]
         payload = int(res.payload_bytes)
         sel_ms = statistics.mean(ksel)
         algo_bytes = n + payload  # k_select reads the shard once and writes every winning payload once
@@ -292,7 +298,7 @@ def run_b200(args):
             "kernel_ms": {"k_select": sel_ms, "size_scan": statistics.mean(kscan), "k_pack": statistics.mean(kpack),
                           "k_decode": statistics.mean(kdec), "host_index_walk_ms": t_index * 1e3},
             "roofline": {"bound": "hbm", "kernel": "k_select", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": args.traffic, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes,
                          "decode": {"kernel": "k_decode", "achieved": (body_len + n) / (statistics.mean(kdec) * 1e-3) / 1e9,
                                     "frac": (body_len + n) / (statistics.mean(kdec) * 1e-3) / 1e9 / peak}},
