@@ -26,15 +26,18 @@ struct ChunkCtx {
     uint8_t *estart;   // per 32-block chain entry offset
     int *red;          // 32 ints of reduction scratch (8-byte aligned)
     // names-based match search (lz_names.cuh), chunks of at most LZ2_NMAX bytes; T == nullptr: absent
-    uint32_t *T;       // LZ2_TSLOTS hash slots (32 KiB); also participant list / slot memo in its upper part
+    uint32_t *T;       // LZ2_TSLOTS hash slots (32 KiB)
     uint16_t *nameA;   // LZ2_NMAX first-occurrence names (two buffers, alternating levels)
     uint16_t *nameB;
-    uint32_t *fol;     // 2 x LZ2_NMAX/32 "has a later occurrence" bits
+    uint8_t *L;        // LZ2_LBYTES of list memory: participant list | slot memo | node-membership masks
+    uint32_t *wq;      // per-warp staging queues, 64 entries x 2 words each
 };
 
 #define LZ2_NMAX 4096
 #define LZ2_TSLOTS 8192
-#define LZ2_BYTES (LZ2_TSLOTS * 4 + 2 * LZ2_NMAX * 2 + 2 * (LZ2_NMAX / 32) * 4)
+#define LZ2_LBYTES 32768
+#define LZ2_QBYTES (AMBC_WARPS * 512)
+#define LZ2_BYTES (LZ2_TSLOTS * 4 + 2 * LZ2_NMAX * 2 + LZ2_LBYTES + LZ2_QBYTES)
 
 // scratch region X: LZ per-warp bucket counters, or 16 KiB for the other users
 #define AMBC_XBYTES ((AMBC_WARPS * AMBC_NBUCKET * 2) > 16384 ? (AMBC_WARPS * AMBC_NBUCKET * 2) : 16384)
@@ -83,7 +86,8 @@ __device__ inline void chunkctx_carve(ChunkCtx &c, uint8_t *base, int N, int pca
     c.T = (uint32_t *)p; p += LZ2_TSLOTS * 4;
     c.nameA = (uint16_t *)p; p += LZ2_NMAX * 2;
     c.nameB = (uint16_t *)p; p += LZ2_NMAX * 2;
-    c.fol = (uint32_t *)p;
+    c.L = p; p += LZ2_LBYTES;
+    c.wq = (uint32_t *)p;
     c.pcap = pcap;
     c.n = 0;
 }
@@ -95,7 +99,7 @@ __device__ inline void chunkctx_carve(ChunkCtx &c, uint8_t *base, int N, int pca
 __host__ __device__ inline size_t chunkctx_fast_smem_bytes(int N)
 {
     size_t nb = (size_t)(N + 31) / 32;
-    return r16((size_t)N) + AMBC_PAD + LZ2_TSLOTS * 4 + 2 * LZ2_NMAX * 2 + 2 * (LZ2_NMAX / 32) * 4
+    return r16((size_t)N) + AMBC_PAD + LZ2_TSLOTS * 4 + 2 * LZ2_NMAX * 2 + LZ2_LBYTES + LZ2_QBYTES
            + r16((size_t)N) + r16(2 * (size_t)N) + 1024 + r16(nb * 4) * 2 + r16(nb) + 128;
 }
 __device__ inline void chunkctx_carve_fast(ChunkCtx &c, uint8_t *base, int N)
@@ -114,7 +118,8 @@ __device__ inline void chunkctx_carve_fast(ChunkCtx &c, uint8_t *base, int N)
     p += LZ2_TSLOTS * 4;
     c.nameA = (uint16_t *)p; p += LZ2_NMAX * 2;
     c.nameB = (uint16_t *)p; p += LZ2_NMAX * 2;
-    c.fol = (uint32_t *)p; p += 2 * (LZ2_NMAX / 32) * 4;
+    c.L = p; p += LZ2_LBYTES;
+    c.wq = (uint32_t *)p; p += LZ2_QBYTES;
     c.mlen = p; p += r16((size_t)N);
     c.mpos = (uint16_t *)p; p += r16(2 * (size_t)N);
     c.hist = (uint32_t *)p; p += 1024;

@@ -1,6 +1,6 @@
 // codec_batch.cu -- CompressionMethod plug-in entry points (compression_methods.py:7-67):
 // compress() and should_use() of the four native methods over a batch of independent items.
-#define AMBC_BLOCK 256 // encoder CTAs: 8 warps per chunk (512 measured no faster: barrier-bound phases)
+#define AMBC_BLOCK 512 // encoder CTAs: 16 warps per chunk, 2 CTAs per SM (100 KB of shared memory each)
 #include "ambc_internal.h"
 #include "chunk_codec.cuh"
 

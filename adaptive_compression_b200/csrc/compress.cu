@@ -10,7 +10,7 @@
 //              exclusive scan of package sizes with the "rest of file raw" rule: everything
 //              from the first chunk without a winner onward is ONE raw package.
 //   k_pack     one CTA per chunk: 18-byte package header + payload to the final offset.
-#define AMBC_BLOCK 256 // encoder CTAs: 8 warps per chunk (512 measured no faster: barrier-bound phases)
+#define AMBC_BLOCK 512 // encoder CTAs: 16 warps per chunk, 2 CTAs per SM (100 KB of shared memory each)
 #include "ambc_internal.h"
 #include "chunk_codec.cuh"
 
@@ -89,7 +89,7 @@ __device__ SelectOut select_chunk(ChunkCtx &c, uint32_t mask, int ovh)
 }
 
 #ifndef KSEL_MINB
-#define KSEL_MINB 3
+#define KSEL_MINB 2
 #endif
 __global__ void __launch_bounds__(AMBC_BLOCK, KSEL_MINB)
 k_select(const uint8_t *__restrict__ in, uint64_t total, uint32_t N, uint32_t mask, uint32_t ovh,

@@ -27,10 +27,10 @@
 #define LZ2_EMPTY 0xFFFFFFFFu
 #define LZ2_GOLD 2654435761u
 #define LZ2_NS 0x8000u           // name flag: the gram occurs at more than one position
-#define LZ2_RSLOTS 4096          // table slots of a refinement pass
-#define LZ2_PART_TARGET 1365     // expected entries per refinement pass (load factor 1/3)
-#define LZ2_BIN_MAXP 2048        // participants the binary-order refinement handles
-#define LZ2_ISLOTS 4096          // slot memo entries
+#define LZ2_RSLOTS LZ2_TSLOTS     // table slots of a refinement pass
+#define LZ2_RSHIFT 19            // 32 - log2(LZ2_RSLOTS)
+#define LZ2_PART_TARGET 3072     // entries per refinement pass (load factor 3/8)
+#define LZ2_ISLOTS 8192          // slot memo entries
 
 // slot value = tag << 16 | position << 1 | single: the claiming insert stores single = 1, every
 // later arrival at the same key clears it (atomicMin with an even value, or atomicAnd)
@@ -215,7 +215,7 @@ __device__ inline bool lz2_refine_flat(ChunkCtx &c, const uint16_t *S, int k, in
                         if (b & LZ2_NS) {
                             const uint32_t h = ((a | (b << 16)) + (uint32_t)jj * 0x9E3779B9u) * LZ2_GOLD;
                             if (((h >> 16) & (uint32_t)(R - 1)) == (uint32_t)r)
-                                slot = lz2_insert_pair(c, LZ2_RSLOTS - 1, h >> 20, S, a, b, p, j, (uint32_t)jj, &overflow);
+                                slot = lz2_insert_pair(c, LZ2_RSLOTS - 1, h >> LZ2_RSHIFT, S, a, b, p, j, (uint32_t)jj, &overflow);
                         }
                     }
                     islot[jj * np + pi] = (uint16_t)slot;
@@ -281,7 +281,7 @@ __device__ inline int lz2_refine_binary(ChunkCtx &c, const uint16_t *S, int k, i
                             const uint32_t h = ((a | (b << 16)) + (uint32_t)t * 0x9E3779B9u) * LZ2_GOLD;
                             slot = 0xFFFFu;  // 0xFFFF: belongs to another partition pass
                             if (((h >> 16) & (uint32_t)(R - 1)) == (uint32_t)r)
-                                slot = lz2_insert_pair(c, LZ2_RSLOTS - 1, h >> 20, S, a, b, p, j, (uint32_t)t, &overflow);
+                                slot = lz2_insert_pair(c, LZ2_RSLOTS - 1, h >> LZ2_RSHIFT, S, a, b, p, j, (uint32_t)t, &overflow);
                         }
                     }
                     islot[idx++] = (uint16_t)slot;
@@ -321,19 +321,18 @@ __device__ inline int lz2_refine_binary(ChunkCtx &c, const uint16_t *S, int k, i
 // S = name_k, D = name_2k.  Returns false on table overflow.
 __device__ inline bool lz2_refine(ChunkCtx &c, const uint16_t *S, const uint16_t *D, int k)
 {
-    uint8_t *R0 = (uint8_t *)(c.T + LZ2_RSLOTS); // 16 KiB above the pass table
-    uint16_t *plist = (uint16_t *)R0;
+    // list memory: plist 8 KiB | islot 16 KiB | mem 4 KiB | mem2 4 KiB
+    uint16_t *plist = (uint16_t *)c.L;
+    uint16_t *islot = (uint16_t *)(c.L + 8192);
     const int np = lz2_participants(c, S, D, k, plist, LZ2_NMAX);
     if (np == 0) return true;
-    if (np <= LZ2_BIN_MAXP && k > 4) {
-        // plist 4 KiB | mem 2 KiB | mem2 2 KiB | islot 8 KiB
-        const int rc = lz2_refine_binary(c, S, k, np, plist, R0 + 4096, R0 + 6144, (uint16_t *)(R0 + 8192));
+    if (k > 4) {
+        const int rc = lz2_refine_binary(c, S, k, np, plist, c.L + 24576, c.L + 28672, islot);
         if (rc == 0) return true;
         if (rc < 0) return false;
         __syncthreads();
     }
-    if (np <= LZ2_BIN_MAXP) return lz2_refine_flat(c, S, k, np, plist, (uint16_t *)(R0 + 8192));
-    return lz2_refine_flat(c, S, k, np, plist, plist + LZ2_NMAX);
+    return lz2_refine_flat(c, S, k, np, plist, islot);
 }
 
 // mlen / mpos for every position of the chunk (c.mlen zeroed by the caller).  n <= LZ2_NMAX.
