@@ -103,13 +103,21 @@ struct DevBuf {
         return AMBC_OK;
     }
 };
+#define AMBC_MAX_PIECES 64
 struct HostCtx {
     DevBuf in, out, work, table, status;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy = nullptr, d2h = nullptr;
+    cudaEvent_t piece_ev[AMBC_MAX_PIECES] = {};
+    cudaEvent_t ring_ev[4] = {};
+    bool ring_used[4] = {false, false, false, false};
     std::vector<ambc_pkg> host_table;
 };
 int ambc_index_vector(const uint8_t *body, uint64_t body_len, const uint8_t *marker, uint32_t mb, uint64_t orig_size,
                       uint32_t known_mask, std::vector<ambc_pkg> &v, uint64_t *n_entries, uint64_t *out_bytes);
+int ambc_compress_dev_impl(const void *in_dev, uint64_t n, uint32_t chunk, uint32_t method_mask, uint32_t flags,
+                           const uint8_t *marker, uint32_t marker_bytes, void *out_dev, uint64_t out_cap,
+                           void *work_dev, uint64_t work_bytes, ambc_compress_result *res, cudaStream_t stream,
+                           const cudaEvent_t *piece_ready, uint64_t piece_chunks, uint32_t n_pieces);
 static std::mutex g_mu;
 static HostCtx g_ctx[16];
 
@@ -123,6 +131,12 @@ static int host_ctx(HostCtx **out)
     if (!c->stream) {
         e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
         if (e != cudaSuccess) return ambc_fail(AMBC_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+        e = cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return ambc_fail(AMBC_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+        e = cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return ambc_fail(AMBC_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+        for (int i = 0; i < AMBC_MAX_PIECES; i++) cudaEventCreateWithFlags(&c->piece_ev[i], cudaEventDisableTiming);
+        for (int i = 0; i < 4; i++) cudaEventCreateWithFlags(&c->ring_ev[i], cudaEventDisableTiming);
     }
     *out = c;
     return AMBC_OK;
@@ -142,10 +156,26 @@ extern "C" int ambc_compress_host(const void *in_host, uint64_t n, uint32_t chun
     if ((rc = c->in.ensure(n + 64))) return rc;
     if ((rc = c->out.ensure(bound))) return rc;
     if ((rc = c->work.ensure(wbytes))) return rc;
-    if (n) CUDA_TRY(cudaMemcpyAsync(c->in.p, in_host, n, cudaMemcpyHostToDevice, c->stream));
-    rc = ambc_compress_dev(c->in.p, n, chunk, method_mask, flags, marker, marker_bytes, c->out.p, bound, c->work.p,
-                           c->work.cap, res, c->stream);
-    if (rc) return rc;
+    // upload in pieces on a second stream; k_select of piece k starts as soon as piece k is resident
+    const uint64_t piece_bytes_target = 64ull << 20;
+    uint64_t piece_chunks = chunk <= piece_bytes_target ? piece_bytes_target / chunk : 1;
+    uint64_t n_chunks = (n + chunk - 1) / chunk;
+    uint64_t n_pieces = piece_chunks ? (n_chunks + piece_chunks - 1) / piece_chunks : 0;
+    if (n_pieces > AMBC_MAX_PIECES) { piece_chunks = (n_chunks + AMBC_MAX_PIECES - 1) / AMBC_MAX_PIECES; n_pieces = (n_chunks + piece_chunks - 1) / piece_chunks; }
+    if (n_pieces > 1) {
+        for (uint64_t k = 0; k < n_pieces; k++) {
+            uint64_t b0 = k * piece_chunks * chunk, b1 = min<uint64_t>(n, b0 + piece_chunks * chunk);
+            CUDA_TRY(cudaMemcpyAsync((uint8_t *)c->in.p + b0, (const uint8_t *)in_host + b0, b1 - b0, cudaMemcpyHostToDevice, c->copy));
+            CUDA_TRY(cudaEventRecord(c->piece_ev[k], c->copy));
+        }
+        rc = ambc_compress_dev_impl(c->in.p, n, chunk, method_mask, flags, marker, marker_bytes, c->out.p, bound, c->work.p,
+                                    c->work.cap, res, c->stream, c->piece_ev, piece_chunks, (uint32_t)n_pieces);
+    } else {
+        if (n) CUDA_TRY(cudaMemcpyAsync(c->in.p, in_host, n, cudaMemcpyHostToDevice, c->stream));
+        rc = ambc_compress_dev(c->in.p, n, chunk, method_mask, flags, marker, marker_bytes, c->out.p, bound, c->work.p,
+                               c->work.cap, res, c->stream);
+    }
+    if (rc) { cudaStreamSynchronize(c->copy); return rc; }
     if (res->body_len > out_cap) return ambc_fail(AMBC_E_CAPACITY, "ambc_compress_host: out_cap %llu < body %llu",
                                                   (unsigned long long)out_cap, (unsigned long long)res->body_len);
     CUDA_TRY(cudaMemcpyAsync(out_host, c->out.p, res->body_len, cudaMemcpyDeviceToHost, c->stream));
@@ -159,6 +189,59 @@ extern "C" int ambc_compress_host(const void *in_host, uint64_t n, uint32_t chun
     return AMBC_OK;
 }
 
+int ambc_index_stream(const uint8_t *body, uint64_t body_len, const uint8_t *marker, uint32_t mb, uint64_t orig_size,
+                      uint32_t known_mask, void (*sink)(void *, const ambc_pkg &), void *user, uint64_t *n_entries,
+                      uint64_t *out_bytes);
+int ambc_decode_launch(const void *body_dev, const ambc_pkg *table_dev, uint64_t n_entries, void *out_dev,
+                       uint32_t *status_dev, cudaStream_t stream);
+
+// state of the piece-wise decode that runs while the host walks the package chain
+struct DecPipe {
+    HostCtx *c;
+    uint8_t *out_host;
+    uint64_t piece_entries, filled = 0, flushed_entries = 0;
+    int rc = AMBC_OK;
+    int ev = 0, ring = 0;
+};
+#define DEC_PIECE_ENTRIES 16384
+#define DEC_RING 4 // device table pieces in flight
+
+static void decpipe_flush(DecPipe &d)
+{
+    if (d.rc || d.filled == 0) return;
+    HostCtx *c = d.c;
+    // ring of device table pieces: slot r is free again once the kernels of its previous piece ran
+    ambc_pkg *tab_dev = (ambc_pkg *)c->table.p + (uint64_t)d.ring * DEC_PIECE_ENTRIES;
+    if (c->ring_used[d.ring]) cudaEventSynchronize(c->ring_ev[d.ring]);
+    const ambc_pkg *src = c->host_table.data();
+    cudaError_t e = cudaMemcpyAsync(tab_dev, src, d.filled * sizeof(ambc_pkg), cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) { d.rc = ambc_fail(AMBC_E_CUDA, "table upload: %s", cudaGetErrorString(e)); return; }
+    d.rc = ambc_decode_launch(c->in.p, tab_dev, d.filled, c->out.p, (uint32_t *)c->status.p, c->stream);
+    if (d.rc) return;
+    // results of this piece go home on the copy stream while the walk and the next kernels continue
+    const uint64_t d0 = src[0].dst_off, d1 = src[d.filled - 1].dst_off + src[d.filled - 1].out_len;
+    cudaEvent_t ev = c->piece_ev[d.ev];
+    d.ev = (d.ev + 1) % AMBC_MAX_PIECES;
+    cudaEventRecord(ev, c->stream);
+    cudaEventRecord(c->ring_ev[d.ring], c->stream);
+    c->ring_used[d.ring] = true;
+    d.ring = (d.ring + 1) % DEC_RING;
+    cudaStreamWaitEvent(c->d2h, ev, 0);
+    e = cudaMemcpyAsync(d.out_host + d0, (uint8_t *)c->out.p + d0, d1 - d0, cudaMemcpyDeviceToHost, c->d2h);
+    if (e != cudaSuccess) { d.rc = ambc_fail(AMBC_E_CUDA, "result download: %s", cudaGetErrorString(e)); return; }
+    d.flushed_entries += d.filled;
+    d.filled = 0;
+}
+
+static void decpipe_sink(void *user, const ambc_pkg &e)
+{
+    DecPipe &d = *(DecPipe *)user;
+    if (d.rc) return;
+    d.c->host_table[d.filled++] = e;
+    if (d.filled == d.piece_entries) decpipe_flush(d);
+}
+
+
 extern "C" int ambc_decompress_host(const void *body_host, uint64_t body_len, const uint8_t *marker,
                                     uint32_t marker_bytes, uint32_t known_mask, void *out_host, uint64_t orig_size,
                                     uint32_t *status)
@@ -167,25 +250,31 @@ extern "C" int ambc_decompress_host(const void *body_host, uint64_t body_len, co
     HostCtx *c;
     int rc = host_ctx(&c);
     if (rc) return rc;
+    if (!marker || marker_bytes < 1 || marker_bytes > 4) return ambc_fail(AMBC_E_ARG, "ambc_decompress_host: bad marker");
     uint64_t ne = 0, covered = 0;
-    // start the body upload first; the index walk on the host overlaps with it
+    // the body upload, the host walk of the package chain, the decode kernels and the download of
+    // finished pieces all overlap: the walk hands DEC_PIECE_ENTRIES packages at a time to the GPU
     if ((rc = c->in.ensure(body_len + 64))) return rc;
-    if (body_len) CUDA_TRY(cudaMemcpyAsync(c->in.p, body_host, body_len, cudaMemcpyHostToDevice, c->stream));
-    rc = ambc_index_vector((const uint8_t *)body_host, body_len, marker, marker_bytes, orig_size, known_mask,
-                           c->host_table, &ne, &covered);
-    if (rc) { cudaStreamSynchronize(c->stream); return rc; }
     if ((rc = c->out.ensure(orig_size + 64))) return rc;
-    if ((rc = c->table.ensure(ne * sizeof(ambc_pkg) + 64))) return rc;
     if ((rc = c->status.ensure(64))) return rc;
+    if ((rc = c->table.ensure((uint64_t)DEC_RING * DEC_PIECE_ENTRIES * sizeof(ambc_pkg) + 64))) return rc;
+    for (int i = 0; i < DEC_RING; i++) c->ring_used[i] = false;
+    if (c->host_table.size() < DEC_PIECE_ENTRIES) c->host_table.resize(DEC_PIECE_ENTRIES);
+    if (body_len) CUDA_TRY(cudaMemcpyAsync(c->in.p, body_host, body_len, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemsetAsync(c->status.p, 0, 8, c->stream));
-    if (ne) CUDA_TRY(cudaMemcpyAsync(c->table.p, c->host_table.data(), ne * sizeof(ambc_pkg), cudaMemcpyHostToDevice, c->stream));
-    rc = ambc_decompress_dev(c->in.p, body_len, (const ambc_pkg *)c->table.p, ne, c->out.p, orig_size,
-                             (uint32_t *)c->status.p, c->stream);
-    if (rc) return rc;
-    if (orig_size) CUDA_TRY(cudaMemcpyAsync(out_host, c->out.p, orig_size, cudaMemcpyDeviceToHost, c->stream));
+    DecPipe d;
+    d.c = c; d.out_host = (uint8_t *)out_host; d.piece_entries = DEC_PIECE_ENTRIES;
+    rc = ambc_index_stream((const uint8_t *)body_host, body_len, marker, marker_bytes, orig_size, known_mask,
+                           decpipe_sink, &d, &ne, &covered);
+    if (!rc) { decpipe_flush(d); rc = d.rc; }
+    if (rc) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->d2h); return rc; }
+    if (covered < orig_size) { // zero pad (adaptive_compressor.py:447-449)
+        memset((uint8_t *)out_host + covered, 0, orig_size - covered);
+    }
     uint32_t st[2] = {0, 0};
     CUDA_TRY(cudaMemcpyAsync(st, c->status.p, 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->d2h));
     if (status) { status[0] = st[0]; status[1] = st[1]; }
     return AMBC_OK;
 }

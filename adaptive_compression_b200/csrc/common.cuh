@@ -92,37 +92,39 @@ __device__ __forceinline__ double block_sum_f64(double v, volatile double *red)
 
 // Copy `len` bytes global -> shared.  dst is 16-byte aligned shared memory.  Uses 16-byte
 // vector loads when src is 16-byte aligned, byte loads otherwise (odd chunk sizes).
+template <int BS = AMBC_BLOCK>
 __device__ __forceinline__ void copy_g2s(uint8_t *dst, const uint8_t *__restrict__ src, int len)
 {
     if ((((uintptr_t)src) & 15) == 0) {
         int nv = len >> 4;
         const uint4 *s4 = (const uint4 *)src;
         uint4 *d4 = (uint4 *)dst;
-        for (int i = threadIdx.x; i < nv; i += AMBC_BLOCK) d4[i] = __ldg(s4 + i);
-        for (int i = (nv << 4) + threadIdx.x; i < len; i += AMBC_BLOCK) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < nv; i += BS) d4[i] = __ldg(s4 + i);
+        for (int i = (nv << 4) + threadIdx.x; i < len; i += BS) dst[i] = __ldg(src + i);
     } else {
-        for (int i = threadIdx.x; i < len; i += AMBC_BLOCK) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < len; i += BS) dst[i] = __ldg(src + i);
     }
 }
 
 // Copy `len` bytes shared (any alignment) -> global (any alignment): byte stores up to the
 // first 16-byte boundary of dst, aligned 16-byte stores fed by funnel-shifted shared loads,
 // byte stores for the tail.
+template <int BS = AMBC_BLOCK>
 __device__ __forceinline__ void copy_s2g(uint8_t *__restrict__ dst, const uint8_t *src, int len)
 {
     int head = (int)((16 - ((uintptr_t)dst & 15)) & 15);
     if (head > len) head = len;
-    for (int i = threadIdx.x; i < head; i += AMBC_BLOCK) dst[i] = src[i];
+    for (int i = threadIdx.x; i < head; i += BS) dst[i] = src[i];
     int body = (len - head) >> 4;
     uint4 *d4 = (uint4 *)(dst + head);
     const uint8_t *s = src + head;
-    for (int i = threadIdx.x; i < body; i += AMBC_BLOCK) {
+    for (int i = threadIdx.x; i < body; i += BS) {
         const uint8_t *p = s + (i << 4);
         uint4 v;
         v.x = lds_u32u(p); v.y = lds_u32u(p + 4); v.z = lds_u32u(p + 8); v.w = lds_u32u(p + 12);
         d4[i] = v;
     }
-    for (int i = head + (body << 4) + threadIdx.x; i < len; i += AMBC_BLOCK) dst[i] = src[i];
+    for (int i = head + (body << 4) + threadIdx.x; i < len; i += BS) dst[i] = src[i];
 }
 
 __device__ __forceinline__ void store_u32le(uint8_t *p, uint32_t v)

@@ -94,13 +94,13 @@ __device__ SelectOut select_chunk(ChunkCtx &c, uint32_t mask, int ovh)
 __global__ void __launch_bounds__(AMBC_BLOCK, KSEL_MINB)
 k_select(const uint8_t *__restrict__ in, uint64_t total, uint32_t N, uint32_t mask, uint32_t ovh,
          uint8_t *__restrict__ slots, uint64_t slot_stride, uint8_t *__restrict__ type,
-         uint32_t *__restrict__ comp, unsigned long long *first_raw, uint64_t n_chunks)
+         uint32_t *__restrict__ comp, unsigned long long *first_raw, uint64_t chunk_begin, uint64_t n_chunks)
 {
     extern __shared__ uint4 smem4[];
     ChunkCtx c;
     if (N <= LZ2_NMAX) chunkctx_carve_fast(c, (uint8_t *)smem4, (int)N);
     else chunkctx_carve(c, (uint8_t *)smem4, (int)N, (int)N);
-    for (uint64_t i = blockIdx.x; i < n_chunks; i += gridDim.x) {
+    for (uint64_t i = chunk_begin + blockIdx.x; i < n_chunks; i += gridDim.x) {
         uint64_t off = i * (uint64_t)N;
         int n = (int)min((uint64_t)N, total - off);
         chunk_load(c, in + off, n);
@@ -282,7 +282,8 @@ __device__ __forceinline__ void write_pkg_header(uint8_t *h, uint32_t marker_wor
     store_u32le(h + mb + 10, comp);
 }
 
-__global__ void __launch_bounds__(AMBC_BLOCK)
+#define PACK_BLOCK 128
+__global__ void __launch_bounds__(PACK_BLOCK)
 k_pack(const uint8_t *__restrict__ in, uint64_t total, uint32_t N, const uint8_t *__restrict__ slots,
        uint64_t slot_stride, const uint8_t *__restrict__ type, const uint32_t *__restrict__ comp,
        const unsigned long long *__restrict__ offs, const ScanState *st, uint32_t flags, uint32_t marker_word,
@@ -301,7 +302,7 @@ k_pack(const uint8_t *__restrict__ in, uint64_t total, uint32_t N, const uint8_t
             // inside the single raw package: header once, then plain bytes
             uint64_t pbase = offs[fr]; // == offset of the raw package (sizes beyond fr are 0)
             uint64_t rawlen = total - fr * (uint64_t)N;
-            copy_g2s(buf + 32, in + coff, n);
+            copy_g2s<PACK_BLOCK>(buf + 32, in + coff, n);
             uint8_t *src = buf + 32;
             int len = n;
             if (i == fr) {
@@ -311,15 +312,15 @@ k_pack(const uint8_t *__restrict__ in, uint64_t total, uint32_t N, const uint8_t
             }
             __syncthreads();
             uint64_t dst = (i == fr) ? pbase : pbase + ovh + (coff - fr * (uint64_t)N);
-            copy_s2g(out + dst, src, len);
+            copy_s2g<PACK_BLOCK>(out + dst, src, len);
         } else {
             int t = type[i];
             int len = (int)comp[i];
-            if (t == 255) copy_g2s(buf + 32, in + coff, n);
-            else copy_g2s(buf + 32, slots + i * slot_stride, len);
+            if (t == 255) copy_g2s<PACK_BLOCK>(buf + 32, in + coff, n);
+            else copy_g2s<PACK_BLOCK>(buf + 32, slots + i * slot_stride, len);
             if (threadIdx.x == 0) write_pkg_header(buf + 32 - ovh, marker_word, mb, t, (uint32_t)n, (uint32_t)len);
             __syncthreads();
-            copy_s2g(out + offs[i], buf + 32 - ovh, len + ovh);
+            copy_s2g<PACK_BLOCK>(out + offs[i], buf + 32 - ovh, len + ovh);
         }
         __syncthreads();
     }
@@ -359,12 +360,27 @@ extern "C" uint64_t ambc_compress_bound(uint64_t n, uint32_t chunk, uint32_t mar
     return n + (chunks + 1) * (marker_bytes + 14) + marker_bytes + 12 + 64;
 }
 
+// piece_ready[k] (optional): event after which chunks [k * piece_chunks, (k+1) * piece_chunks) of the
+// input are resident (ambc_compress_host uploads piece-wise so that H2D overlaps k_select)
+int ambc_compress_dev_impl(const void *in_dev, uint64_t n, uint32_t chunk, uint32_t method_mask, uint32_t flags,
+                           const uint8_t *marker, uint32_t marker_bytes, void *out_dev, uint64_t out_cap,
+                           void *work_dev, uint64_t work_bytes, ambc_compress_result *res, cudaStream_t stream,
+                           const cudaEvent_t *piece_ready, uint64_t piece_chunks, uint32_t n_pieces);
+
 extern "C" int ambc_compress_dev(const void *in_dev, uint64_t n, uint32_t chunk, uint32_t method_mask,
                                  uint32_t flags, const uint8_t *marker, uint32_t marker_bytes, void *out_dev,
                                  uint64_t out_cap, void *work_dev, uint64_t work_bytes, ambc_compress_result *res,
                                  void *stream_)
 {
-    cudaStream_t stream = (cudaStream_t)stream_;
+    return ambc_compress_dev_impl(in_dev, n, chunk, method_mask, flags, marker, marker_bytes, out_dev, out_cap, work_dev,
+                                  work_bytes, res, (cudaStream_t)stream_, nullptr, 0, 0);
+}
+
+int ambc_compress_dev_impl(const void *in_dev, uint64_t n, uint32_t chunk, uint32_t method_mask, uint32_t flags,
+                           const uint8_t *marker, uint32_t marker_bytes, void *out_dev, uint64_t out_cap,
+                           void *work_dev, uint64_t work_bytes, ambc_compress_result *res, cudaStream_t stream,
+                           const cudaEvent_t *piece_ready, uint64_t piece_chunks, uint32_t n_pieces)
+{
     if (!res || !marker || marker_bytes < 1 || marker_bytes > 4 || chunk == 0)
         return ambc_fail(AMBC_E_ARG, "ambc_compress_dev: bad argument");
     if ((n && (!in_dev || !work_dev)) || !out_dev) return ambc_fail(AMBC_E_ARG, "ambc_compress_dev: null buffer");
@@ -411,10 +427,22 @@ extern "C" int ambc_compress_dev(const void *in_dev, uint64_t n, uint32_t chunk,
         size_t smem = chunk <= LZ2_NMAX ? chunkctx_fast_smem_bytes((int)chunk) : chunkctx_smem_bytes((int)chunk, (int)chunk);
         CUDA_TRY(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ambc_timing_mark(0, stream);
-        k_select<<<grid_chunks, AMBC_BLOCK, smem, stream>>>((const uint8_t *)in_dev, n, chunk, method_mask, ovh,
-                                                            W + L.slots, L.slot_stride, type, comp,
-                                                            &st->first_raw, L.n_chunks);
-        ambc_count_launch();
+        if (piece_ready && n_pieces > 1 && piece_chunks) {
+            for (uint32_t k = 0; k < n_pieces; k++) {
+                uint64_t c0 = (uint64_t)k * piece_chunks, c1 = min<uint64_t>(L.n_chunks, c0 + piece_chunks);
+                if (c0 >= c1) break;
+                CUDA_TRY(cudaStreamWaitEvent(stream, piece_ready[k], 0));
+                k_select<<<(unsigned)(c1 - c0), AMBC_BLOCK, smem, stream>>>((const uint8_t *)in_dev, n, chunk, method_mask,
+                                                                          ovh, W + L.slots, L.slot_stride, type, comp,
+                                                                          &st->first_raw, c0, c1);
+                ambc_count_launch();
+            }
+        } else {
+            k_select<<<grid_chunks, AMBC_BLOCK, smem, stream>>>((const uint8_t *)in_dev, n, chunk, method_mask, ovh,
+                                                                W + L.slots, L.slot_stride, type, comp,
+                                                                &st->first_raw, 0, L.n_chunks);
+            ambc_count_launch();
+        }
         CUDA_TRY(cudaGetLastError());
         ambc_timing_mark(1, stream);
         k_sizes<<<(unsigned)L.n_tiles, 256, 0, stream>>>(type, comp, L.n_chunks, chunk, n, ovh, flags, st, tiles);
@@ -429,7 +457,7 @@ extern "C" int ambc_compress_dev(const void *in_dev, uint64_t n, uint32_t chunk,
         ambc_timing_mark(2, stream);
         size_t psmem = 32 + (((size_t)chunk + 15) & ~(size_t)15) + 32;
         CUDA_TRY(cudaFuncSetAttribute(k_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-        k_pack<<<grid_chunks, AMBC_BLOCK, psmem, stream>>>((const uint8_t *)in_dev, n, chunk, W + L.slots,
+        k_pack<<<grid_chunks, PACK_BLOCK, psmem, stream>>>((const uint8_t *)in_dev, n, chunk, W + L.slots,
                                                            L.slot_stride, type, comp, offs, st, flags, marker_word,
                                                            marker_bytes, (uint8_t *)out_dev, out_cap, L.n_chunks);
         ambc_count_launch();
@@ -440,6 +468,8 @@ extern "C" int ambc_compress_dev(const void *in_dev, uint64_t n, uint32_t chunk,
         CUDA_TRY(cudaStreamSynchronize(stream));
     } else {
         // one raw package: header + memcpy + END, no kernel needed beyond the copy engine
+        if (piece_ready)
+            for (uint32_t k = 0; k < n_pieces; k++) CUDA_TRY(cudaStreamWaitEvent(stream, piece_ready[k], 0));
         uint64_t body = (uint64_t)ovh + n + marker_bytes + 12;
         if (n > 0xFFFFFFFFull) return ambc_fail(AMBC_E_ARG, "raw package over 4 GiB cannot be framed (u32 fields)");
         if (body > out_cap) return ambc_fail(AMBC_E_CAPACITY, "out too small");

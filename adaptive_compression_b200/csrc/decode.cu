@@ -93,6 +93,15 @@ extern "C" int ambc_index_host(const uint8_t *body, uint64_t body_len, const uin
                       n_entries, out_bytes);
 }
 
+// one walk, entries handed to `sink` in order (ambc_decompress_host decodes piece-wise while walking)
+int ambc_index_stream(const uint8_t *body, uint64_t body_len, const uint8_t *marker, uint32_t mb, uint64_t orig_size,
+                      uint32_t known_mask, void (*sink)(void *, const ambc_pkg &), void *user, uint64_t *n_entries,
+                      uint64_t *out_bytes)
+{
+    return index_walk(body, body_len, marker, mb, orig_size, known_mask,
+                      [&](const ambc_pkg &e, uint64_t) { sink(user, e); return true; }, n_entries, out_bytes);
+}
+
 // one walk into a growing vector (ambc_decompress_host)
 int ambc_index_vector(const uint8_t *body, uint64_t body_len, const uint8_t *marker, uint32_t mb, uint64_t orig_size,
                       uint32_t known_mask, std::vector<ambc_pkg> &v, uint64_t *n_entries, uint64_t *out_bytes)
@@ -243,6 +252,32 @@ __global__ void k_zero_tail(const ambc_pkg *__restrict__ table, uint64_t n_entri
         out[i] = 0;
 }
 
+// launch the decoders for table[0 .. n_entries) (no tail zeroing)
+int ambc_decode_launch(const void *body_dev, const ambc_pkg *table_dev, uint64_t n_entries, void *out_dev,
+                       uint32_t *status_dev, cudaStream_t stream)
+{
+    if (n_entries == 0) return AMBC_OK;
+    const int in_cap = DEC_OUT_CAP; // payloads the reference's encoder emits are < orig_len <= 8192
+    size_t smem = decctx_smem_bytes(in_cap);
+    static bool attr_done = false;
+    size_t lsmem = (size_t)DLZ_WARPS * DLZ_OUT;
+    if (!attr_done) {
+        CUDA_TRY(cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_decode_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
+        attr_done = true;
+    }
+    unsigned grid = (unsigned)min<uint64_t>(n_entries, 0x7fffffffull);
+    k_decode<<<grid, AMBC_BLOCK, smem, stream>>>((const uint8_t *)body_dev, table_dev, n_entries, (uint8_t *)out_dev,
+                                                 in_cap, status_dev);
+    ambc_count_launch();
+    unsigned lgrid = (unsigned)min<uint64_t>((n_entries + DLZ_WARPS - 1) / DLZ_WARPS, 148ull * 24);
+    k_decode_lz<<<lgrid, DLZ_WARPS * 32, lsmem, stream>>>((const uint8_t *)body_dev, table_dev, n_entries,
+                                                         (uint8_t *)out_dev, status_dev);
+    ambc_count_launch();
+    CUDA_TRY(cudaGetLastError());
+    return AMBC_OK;
+}
+
 extern "C" int ambc_decompress_dev(const void *body_dev, uint64_t body_len, const ambc_pkg *table_dev,
                                    uint64_t n_entries, void *out_dev, uint64_t orig_size, uint32_t *status_dev,
                                    void *stream_)
@@ -258,22 +293,8 @@ extern "C" int ambc_decompress_dev(const void *body_dev, uint64_t body_len, cons
     ambc_timing_mark(4, stream);
     k_zero_tail<<<148, 256, 0, stream>>>(table_dev, n_entries, (uint8_t *)out_dev, orig_size);
     ambc_count_launch();
-    const int in_cap = DEC_OUT_CAP; // payloads the reference's encoder emits are < orig_len <= 8192
-    size_t smem = decctx_smem_bytes(in_cap);
-    CUDA_TRY(cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    unsigned grid = (unsigned)min<uint64_t>(n_entries, 0x7fffffffull);
-    k_decode<<<grid, AMBC_BLOCK, smem, stream>>>((const uint8_t *)body_dev, table_dev, n_entries, (uint8_t *)out_dev,
-                                                 in_cap, status_dev);
-    ambc_count_launch();
-    {
-        size_t lsmem = (size_t)DLZ_WARPS * DLZ_OUT;
-        CUDA_TRY(cudaFuncSetAttribute(k_decode_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
-        unsigned lgrid = (unsigned)min<uint64_t>((n_entries + DLZ_WARPS - 1) / DLZ_WARPS, 148ull * 24);
-        k_decode_lz<<<lgrid, DLZ_WARPS * 32, lsmem, stream>>>((const uint8_t *)body_dev, table_dev, n_entries,
-                                                             (uint8_t *)out_dev, status_dev);
-        ambc_count_launch();
-    }
-    CUDA_TRY(cudaGetLastError());
+    int rc = ambc_decode_launch(body_dev, table_dev, n_entries, out_dev, status_dev, stream);
+    if (rc) return rc;
     ambc_timing_mark(5, stream);
     ambc_timing().pending_d = ambc_timing().on;
     return AMBC_OK;

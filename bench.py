@@ -108,26 +108,70 @@ def run_reference(args):
 # clocks
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML (pynvml) every 10 ms,
+    nvidia-smi as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.rows = []      # (sm_mhz, max_mhz, [reason names])
         self.stop = False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES remapping when it is a plain list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:  # noqa: BLE001
+            self.nvml = None
         self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:  # noqa: BLE001
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        names = []
+        for name, attr in (("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                           ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                           ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                           ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap")):
+            bit = getattr(n, attr, 0)
+            if bit and (r & bit):
+                names.append(name)
+        self.rows.append((float(sm), float(mx), names))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        parts = [p.strip() for p in out.strip().split(",")]
+        if len(parts) >= 6 and parts[0].replace(".", "").isdigit():
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            self.rows.append((float(parts[0]), float(parts[1]),
+                              [n for i, n in enumerate(names) if parts[2 + i].lower().startswith("active")]))
 
     def _run(self):
         while not self.stop:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.rows.append(parts)
+                if self.nvml:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:  # noqa: BLE001
-                pass
-            time.sleep(0.02)
+                if self.nvml:
+                    self.nvml = None  # fall back to nvidia-smi
+            time.sleep(0.01)
 
     def __enter__(self):
         self.th.start()
@@ -140,12 +184,9 @@ class ClockSampler:
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        reasons = sorted({n for r in self.rows for n in r[2]})
+        return {"sm_mhz": statistics.median(r[0] for r in self.rows), "sm_max_mhz": max(r[1] for r in self.rows),
+                "reasons": reasons, "samples": len(self.rows), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -251,15 +292,22 @@ def run_b200(args):
     res2 = L.CompressResult()
     st2 = (C.c_uint32 * 2)()
 
+    e2e_split = [0.0, 0.0]
+
     def e2e_once():
+        t_a = time.perf_counter()
         L.check(lib.ambc_compress_host(C.c_void_p(h_in.data_ptr()), n, CHUNK, mask, 0, marker, 4,
                                        C.c_void_p(h_body.data_ptr()), bound, None, None, C.byref(res2)))
+        t_b = time.perf_counter()
         L.check(lib.ambc_decompress_host(C.c_void_p(h_body.data_ptr()), res2.body_len, marker, 4, mask,
                                          C.c_void_p(h_out.data_ptr()), n, st2))
+        e2e_split[0] += t_b - t_a
+        e2e_split[1] += time.perf_counter() - t_b
 
     e2e_once()
     assert torch.equal(h_out, h_in), "e2e round trip mismatch"
     barrier()
+    e2e_split[0] = e2e_split[1] = 0.0
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_once()
@@ -304,8 +352,10 @@ def run_b200(args):
                                     "frac": (body_len + n) / (statistics.mean(kdec) * 1e-3) / 1e9 / peak}},
             "e2e": {"value": total_bytes / te / 1e9, "unit": UNIT, "h2d_bytes_per_step": n + body_len + len(table) * 32,
                     "d2h_bytes_per_step": body_len + n, "ms_per_step": te * 1e3,
-                    "note": "ambc_compress_host + ambc_decompress_host on pinned host buffers; header MD5 "
-                            "(hashlib, ~0.6 GB/s/core, identical in both arms) is outside the chunk path"},
+                    "compress_ms": e2e_split[0] / e2e_steps * 1e3, "decompress_ms": e2e_split[1] / e2e_steps * 1e3,
+                    "note": "ambc_compress_host + ambc_decompress_host on pinned host buffers (piece-wise upload overlapping "
+                            "k_select; host package walk overlapping decode and download); header MD5 (hashlib, "
+                            "~0.6 GB/s/core, identical in both arms) is outside the chunk path"},
             "gpu_launches": int(launches), "clocks": clocks.summary(),
         }
         if world == 1 and not args.no_cpu:
