@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libambc.so")
+LIB_PATH = os.environ.get("AMBC_LIB_PATH") or os.path.join(_HERE, "libambc.so")  # env override: dev experiments only
 
 OK, E_CUDA, E_ARG, E_CAPACITY, E_MARKER, E_TOO_LARGE, E_NO_MARKER = 0, -1, -2, -3, -4, -5, -6
 RLE, DICT, HUFFMAN, DELTA, RAW = 1, 2, 3, 4, 255

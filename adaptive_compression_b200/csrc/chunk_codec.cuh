@@ -549,7 +549,11 @@ __device__ __forceinline__ int lz_match_len(const uint8_t *s, const uint32_t (&p
 
 // Earliest-longest match for every position by scanning n-gram buckets (any chunk size up to
 // AMBC_NMAX; honours the 4096-byte window).  c.mlen must be zero.  Collective.
+#ifdef V_NOINLINE_BUCKETS
+__device__ __noinline__ void lz_match_all_buckets(ChunkCtx &c)
+#else
 __device__ inline void lz_match_all_buckets(ChunkCtx &c)
+#endif
 {
     const int n = c.n, tid = threadIdx.x, lane = tid & 31;
     // ---- earliest-longest match for every position, longest n-gram level first -----------

@@ -29,7 +29,12 @@
 #define LZ2_NS 0x8000u           // name flag: the gram occurs at more than one position
 #define LZ2_RSLOTS LZ2_TSLOTS     // table slots of a refinement pass
 #define LZ2_RSHIFT 19            // 32 - log2(LZ2_RSLOTS)
-#define LZ2_PART_TARGET 3072     // entries per refinement pass (load factor 3/8)
+#ifndef LZ2_PART_TARGET
+#define LZ2_PART_TARGET 4096     // entries per refinement pass (load factor 1/2; measured best of 2048..4096)
+#endif
+#ifndef LZ2_BIN_MINK
+#define LZ2_BIN_MINK 8           // smallest bracket refined in binary-search order
+#endif
 #define LZ2_ISLOTS 8192          // slot memo entries
 
 // slot value = tag << 16 | position << 1 | single: the claiming insert stores single = 1, every
@@ -258,7 +263,7 @@ __device__ inline int lz2_refine_binary(ChunkCtx &c, const uint16_t *S, int k, i
         for (int pi = tid; pi < np; pi += AMBC_BLOCK) cntl += __popc((uint32_t)mem[pi]);
         int E;
         const int base = block_excl_scan(cntl, c.red, &E);
-        if (E > LZ2_ISLOTS) return 1;
+        if (E >= LZ2_ISLOTS) return 1; // (strictly below the slot count: a probe always ends at a free slot)
         if (E == 0) return 0;
         int R = 1;
         while (R * LZ2_PART_TARGET < E) R <<= 1;
@@ -326,7 +331,7 @@ __device__ inline bool lz2_refine(ChunkCtx &c, const uint16_t *S, const uint16_t
     uint16_t *islot = (uint16_t *)(c.L + 8192);
     const int np = lz2_participants(c, S, D, k, plist, LZ2_NMAX);
     if (np == 0) return true;
-    if (k > 4) {
+    if (k >= LZ2_BIN_MINK) {
         const int rc = lz2_refine_binary(c, S, k, np, plist, c.L + 24576, c.L + 28672, islot);
         if (rc == 0) return true;
         if (rc < 0) return false;

@@ -127,3 +127,49 @@ def test_synthetic_corpus_roundtrip_and_oracle(eng):
     import torch
     assert torch.equal(out, t)
     assert o.first_raw == -1, "bench corpus must have a native winner in every chunk"
+
+
+@pytest.mark.parametrize("chunk", [1024, 4096, 16384])
+def test_config3_chunk_sweep_log_corpus(eng, chunk):
+    """BASELINE configs[2]: chunk-size sweep on a log corpus.  1024 / 4096 against the oracle;
+    16384 is degenerate under reference semantics (no native method is eligible above 8192,
+    adaptive_compressor.py:114-127): the body is one raw package"""
+    import torch
+    n = 4 << 20
+    t = eng.synth(n, offset=0, kind_mask=1 << 1)  # log kind only
+    data = t.cpu().numpy().tobytes()
+    o = eng.compress_device(t, chunk)
+    body = o.body.cpu().numpy().tobytes()
+    wbody, wpm = O.compress_body(data, chunk)
+    assert body == wbody
+    assert [tuple(p) for p in eng.package_map(o, n, chunk)] == [tuple(p) for p in wpm]
+    if chunk == 16384:
+        assert o.first_raw == 0 and len(wpm) == 1 and wpm[0][0] == 255 and len(body) == n + 18 + 16
+    out, status = eng.decompress_device(o.body, n)
+    assert status == [0, 0] and torch.equal(out, t)
+
+
+@pytest.mark.parametrize("pcr", [False, True])
+def test_config5_interleaved_segments(eng, pcr):
+    """BASELINE configs[4]: high-entropy / run-heavy / low-cardinality segments interleaved at 4 KiB.
+    Strict semantics send everything after the first chunk without a winner to one raw package
+    (adaptive_compressor.py:586-590); the labelled per-chunk-raw extension switches method per chunk"""
+    import torch
+    from adaptive_compression_b200 import _lib as L
+    parts = []
+    for i in range(96):
+        kind = ("runs", "lowcard", "rand")[i % 3] if i >= 6 else ("runs", "lowcard")[i % 2]
+        parts.append(inputs.make(kind, 4096, 900 + i))
+    data = b"".join(parts)
+    t = eng.to_device(data)
+    o = eng.compress_device(t, 4096, flags=L.F_PER_CHUNK_RAW if pcr else 0)
+    body = o.body.cpu().numpy().tobytes()
+    wbody, wpm = O.compress_body(data, 4096, per_chunk_raw=pcr)
+    assert body == wbody
+    assert [tuple(p) for p in eng.package_map(o, len(data), 4096, per_chunk_raw=pcr)] == [tuple(p) for p in wpm]
+    if pcr:
+        assert {p[0] for p in wpm} >= {1, 3, 255}
+    else:
+        assert o.first_raw == 8 and wpm[-1][0] == 255 and wpm[-1][1] == len(data) - 8 * 4096
+    out, status = eng.decompress_device(o.body, len(data))
+    assert status == [0, 0] and out.cpu().numpy().tobytes() == data
