@@ -29,3 +29,13 @@ struct AmbcTiming {
 };
 AmbcTiming &ambc_timing();
 void ambc_timing_mark(int idx, cudaStream_t s);
+
+// host-buffer compress: where the body goes and what the piece-wise download needs
+struct AmbcPieceOut {
+    void *out_host;        // destination of the body (pinned memory recommended)
+    uint64_t out_cap;
+    void *states;          // pinned, n_pieces * ambc_scan_state_bytes()
+    cudaEvent_t *done;     // one event per piece
+    cudaStream_t d2h;      // download stream
+};
+extern "C" uint64_t ambc_scan_state_bytes(void);

@@ -109,6 +109,8 @@ struct HostCtx {
     cudaStream_t stream = nullptr, copy = nullptr, d2h = nullptr;
     cudaEvent_t piece_ev[AMBC_MAX_PIECES] = {};
     cudaEvent_t ring_ev[4] = {};
+    cudaEvent_t done_ev[AMBC_MAX_PIECES] = {};
+    void *states = nullptr; // pinned scan states, one per piece
     bool ring_used[4] = {false, false, false, false};
     std::vector<ambc_pkg> host_table;
 };
@@ -117,7 +119,8 @@ int ambc_index_vector(const uint8_t *body, uint64_t body_len, const uint8_t *mar
 int ambc_compress_dev_impl(const void *in_dev, uint64_t n, uint32_t chunk, uint32_t method_mask, uint32_t flags,
                            const uint8_t *marker, uint32_t marker_bytes, void *out_dev, uint64_t out_cap,
                            void *work_dev, uint64_t work_bytes, ambc_compress_result *res, cudaStream_t stream,
-                           const cudaEvent_t *piece_ready, uint64_t piece_chunks, uint32_t n_pieces);
+                           const cudaEvent_t *piece_ready, uint64_t piece_chunks, uint32_t n_pieces,
+                           const AmbcPieceOut *po);
 static std::mutex g_mu;
 static HostCtx g_ctx[16];
 
@@ -137,6 +140,7 @@ static int host_ctx(HostCtx **out)
         if (e != cudaSuccess) return ambc_fail(AMBC_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
         for (int i = 0; i < AMBC_MAX_PIECES; i++) cudaEventCreateWithFlags(&c->piece_ev[i], cudaEventDisableTiming);
         for (int i = 0; i < 4; i++) cudaEventCreateWithFlags(&c->ring_ev[i], cudaEventDisableTiming);
+        for (int i = 0; i < AMBC_MAX_PIECES; i++) cudaEventCreateWithFlags(&c->done_ev[i], cudaEventDisableTiming);
     }
     *out = c;
     return AMBC_OK;
@@ -156,12 +160,23 @@ extern "C" int ambc_compress_host(const void *in_host, uint64_t n, uint32_t chun
     if ((rc = c->in.ensure(n + 64))) return rc;
     if ((rc = c->out.ensure(bound))) return rc;
     if ((rc = c->work.ensure(wbytes))) return rc;
-    // upload in pieces on a second stream; k_select of piece k starts as soon as piece k is resident
+    // upload in pieces on a second stream; select / scan / pack of piece k start as soon as piece k is
+    // resident, and finished body bytes are downloaded while later pieces compute
     const uint64_t piece_bytes_target = 64ull << 20;
     uint64_t piece_chunks = chunk <= piece_bytes_target ? piece_bytes_target / chunk : 1;
+    piece_chunks = (piece_chunks + 2047) / 2048 * 2048; // whole scan tiles
     uint64_t n_chunks = (n + chunk - 1) / chunk;
-    uint64_t n_pieces = piece_chunks ? (n_chunks + piece_chunks - 1) / piece_chunks : 0;
-    if (n_pieces > AMBC_MAX_PIECES) { piece_chunks = (n_chunks + AMBC_MAX_PIECES - 1) / AMBC_MAX_PIECES; n_pieces = (n_chunks + piece_chunks - 1) / piece_chunks; }
+    uint64_t n_pieces = (n_chunks + piece_chunks - 1) / piece_chunks;
+    if (n_pieces > AMBC_MAX_PIECES) {
+        piece_chunks = ((n_chunks + AMBC_MAX_PIECES - 1) / AMBC_MAX_PIECES + 2047) / 2048 * 2048;
+        n_pieces = (n_chunks + piece_chunks - 1) / piece_chunks;
+    }
+    if (!c->states) {
+        if (cudaMallocHost(&c->states, AMBC_MAX_PIECES * ambc_scan_state_bytes()) != cudaSuccess)
+            return ambc_fail(AMBC_E_CUDA, "cudaMallocHost failed");
+    }
+    AmbcPieceOut po;
+    po.out_host = out_host; po.out_cap = out_cap; po.states = c->states; po.done = c->done_ev; po.d2h = c->d2h;
     if (n_pieces > 1) {
         for (uint64_t k = 0; k < n_pieces; k++) {
             uint64_t b0 = k * piece_chunks * chunk, b1 = min<uint64_t>(n, b0 + piece_chunks * chunk);
@@ -169,16 +184,13 @@ extern "C" int ambc_compress_host(const void *in_host, uint64_t n, uint32_t chun
             CUDA_TRY(cudaEventRecord(c->piece_ev[k], c->copy));
         }
         rc = ambc_compress_dev_impl(c->in.p, n, chunk, method_mask, flags, marker, marker_bytes, c->out.p, bound, c->work.p,
-                                    c->work.cap, res, c->stream, c->piece_ev, piece_chunks, (uint32_t)n_pieces);
+                                    c->work.cap, res, c->stream, c->piece_ev, piece_chunks, (uint32_t)n_pieces, &po);
     } else {
         if (n) CUDA_TRY(cudaMemcpyAsync(c->in.p, in_host, n, cudaMemcpyHostToDevice, c->stream));
-        rc = ambc_compress_dev(c->in.p, n, chunk, method_mask, flags, marker, marker_bytes, c->out.p, bound, c->work.p,
-                               c->work.cap, res, c->stream);
+        rc = ambc_compress_dev_impl(c->in.p, n, chunk, method_mask, flags, marker, marker_bytes, c->out.p, bound, c->work.p,
+                                    c->work.cap, res, c->stream, nullptr, 0, 0, &po);
     }
     if (rc) { cudaStreamSynchronize(c->copy); return rc; }
-    if (res->body_len > out_cap) return ambc_fail(AMBC_E_CAPACITY, "ambc_compress_host: out_cap %llu < body %llu",
-                                                  (unsigned long long)out_cap, (unsigned long long)res->body_len);
-    CUDA_TRY(cudaMemcpyAsync(out_host, c->out.p, res->body_len, cudaMemcpyDeviceToHost, c->stream));
     if (map_type && res->n_chunks)
         CUDA_TRY(cudaMemcpyAsync(map_type, (uint8_t *)c->work.p + res->map_type_off, res->n_chunks,
                                  cudaMemcpyDeviceToHost, c->stream));

@@ -130,6 +130,7 @@ struct ScanState {
     unsigned long long n_packages;
     unsigned long long payload_bytes;
     unsigned long long usage[5];
+    unsigned long long carry;      // body bytes before the chunks not yet scanned (piece-wise runs)
 };
 
 __device__ __forceinline__ uint64_t pkg_size(uint64_t i, const uint8_t *type, const uint32_t *comp, uint32_t N,
@@ -142,13 +143,14 @@ __device__ __forceinline__ uint64_t pkg_size(uint64_t i, const uint8_t *type, co
 }
 
 __global__ void __launch_bounds__(256)
-k_sizes(const uint8_t *__restrict__ type, const uint32_t *__restrict__ comp, uint64_t n_chunks, uint32_t N,
-        uint64_t total, uint32_t ovh, uint32_t flags, const ScanState *st, unsigned long long *tile_sum)
+k_sizes(const uint8_t *__restrict__ type, const uint32_t *__restrict__ comp, uint64_t chunk_begin, uint64_t n_chunks,
+        uint32_t N, uint64_t total, uint32_t ovh, uint32_t flags, const ScanState *st, unsigned long long *tile_sum)
 {
+    // chunks [chunk_begin, n_chunks); chunk_begin is a multiple of SCAN_TILE; tile_sum is indexed globally
     __shared__ unsigned long long red[8];
     const bool pcr = flags & 1u;
     const uint64_t fr = st->first_raw;
-    uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE;
+    uint64_t base = chunk_begin + (uint64_t)blockIdx.x * SCAN_TILE;
     unsigned long long s = 0;
     for (int k = threadIdx.x; k < SCAN_TILE; k += 256) {
         uint64_t i = base + k;
@@ -160,22 +162,24 @@ k_sizes(const uint8_t *__restrict__ type, const uint32_t *__restrict__ comp, uin
     if (threadIdx.x == 0) {
         unsigned long long t = 0;
         for (int i = 0; i < 8; i++) t += red[i];
-        tile_sum[blockIdx.x] = t;
+        tile_sum[base / SCAN_TILE] = t;
     }
 }
 
 // single CTA: exclusive scan of the tile sums in place, body length, END package, stats
 __global__ void __launch_bounds__(1024)
-k_scan_tiles(unsigned long long *tile_sum, uint64_t n_tiles, const uint8_t *__restrict__ type,
-             const uint32_t *__restrict__ comp, uint64_t n_chunks, uint32_t N, uint64_t total, uint32_t ovh,
-             uint32_t flags, ScanState *st, uint8_t *out, uint64_t out_cap, uint32_t marker_word, uint32_t mb)
+k_scan_tiles(unsigned long long *tile_sum, uint64_t tile_begin, uint64_t n_tiles, int is_last,
+             const uint8_t *__restrict__ type, const uint32_t *__restrict__ comp, uint64_t n_chunks, uint32_t N,
+             uint64_t total, uint32_t ovh, uint32_t flags, ScanState *st, uint8_t *out, uint64_t out_cap,
+             uint32_t marker_word, uint32_t mb)
 {
+    // tiles [tile_begin, n_tiles), continuing from st->carry; the last call closes the body
     __shared__ unsigned long long wsum[32];
     __shared__ unsigned long long carry_s;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    if (tid == 0) carry_s = 0;
+    if (tid == 0) carry_s = st->carry;
     __syncthreads();
-    for (uint64_t base = 0; base < n_tiles; base += 1024) {
+    for (uint64_t base = tile_begin; base < n_tiles; base += 1024) {
         uint64_t i = base + tid;
         unsigned long long v = i < n_tiles ? tile_sum[i] : 0, inc = v;
         for (int d = 1; d < 32; d <<= 1) {
@@ -192,7 +196,8 @@ k_scan_tiles(unsigned long long *tile_sum, uint64_t n_tiles, const uint8_t *__re
         if (tid == 1023) carry_s = carry + wbase + inc;
         __syncthreads();
     }
-    if (tid == 0) {
+    if (tid == 0) st->carry = carry_s;
+    if (tid == 0 && is_last) {
         const bool pcr = flags & 1u;
         unsigned long long body = carry_s;
         unsigned long long fr = st->first_raw;
@@ -214,9 +219,9 @@ k_scan_tiles(unsigned long long *tile_sum, uint64_t n_tiles, const uint8_t *__re
 }
 
 __global__ void __launch_bounds__(256)
-k_offsets(const uint8_t *__restrict__ type, const uint32_t *__restrict__ comp, uint64_t n_chunks, uint32_t N,
-          uint64_t total, uint32_t ovh, uint32_t flags, ScanState *st, const unsigned long long *tile_base,
-          unsigned long long *offs)
+k_offsets(const uint8_t *__restrict__ type, const uint32_t *__restrict__ comp, uint64_t chunk_begin, uint64_t n_chunks,
+          uint32_t N, uint64_t total, uint32_t ovh, uint32_t flags, ScanState *st,
+          const unsigned long long *tile_base, unsigned long long *offs)
 {
     // one tile per CTA, 8 chunks per thread
     __shared__ unsigned long long wsum[8];
@@ -225,7 +230,7 @@ k_offsets(const uint8_t *__restrict__ type, const uint32_t *__restrict__ comp, u
     const uint64_t fr = st->first_raw;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     if (tid < 6) ustat[tid] = 0;
-    uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)tid * 8;
+    uint64_t base = chunk_begin + (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)tid * 8;
     unsigned long long v[8], s = 0;
     unsigned long long usage[5] = {0, 0, 0, 0, 0}, pbytes = 0;
 #pragma unroll
@@ -248,7 +253,7 @@ k_offsets(const uint8_t *__restrict__ type, const uint32_t *__restrict__ comp, u
     __syncthreads();
     unsigned long long wbase = 0;
     for (int k = 0; k < w; k++) wbase += wsum[k];
-    unsigned long long run = tile_base[blockIdx.x] + wbase + inc - s;
+    unsigned long long run = tile_base[chunk_begin / SCAN_TILE + blockIdx.x] + wbase + inc - s;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         uint64_t i = base + k;
@@ -287,15 +292,15 @@ __global__ void __launch_bounds__(PACK_BLOCK)
 k_pack(const uint8_t *__restrict__ in, uint64_t total, uint32_t N, const uint8_t *__restrict__ slots,
        uint64_t slot_stride, const uint8_t *__restrict__ type, const uint32_t *__restrict__ comp,
        const unsigned long long *__restrict__ offs, const ScanState *st, uint32_t flags, uint32_t marker_word,
-       uint32_t mb, uint8_t *__restrict__ out, uint64_t out_cap, uint64_t n_chunks)
+       uint32_t mb, uint8_t *__restrict__ out, uint64_t out_cap, uint64_t chunk_begin, uint64_t n_chunks, int check_cap)
 {
     extern __shared__ uint4 smem4[];
     uint8_t *buf = (uint8_t *)smem4; // [32 header area][payload]
     const bool pcr = flags & 1u;
     const uint64_t fr = st->first_raw;
     const uint32_t ovh = mb + 14;
-    if (st->body_len > out_cap) return;
-    for (uint64_t i = blockIdx.x; i < n_chunks; i += gridDim.x) {
+    if (check_cap && st->body_len > out_cap) return;
+    for (uint64_t i = chunk_begin + blockIdx.x; i < n_chunks; i += gridDim.x) {
         uint64_t coff = i * (uint64_t)N;
         int n = (int)min((uint64_t)N, total - coff);
         if (!pcr && i >= fr) {
@@ -365,7 +370,9 @@ extern "C" uint64_t ambc_compress_bound(uint64_t n, uint32_t chunk, uint32_t mar
 int ambc_compress_dev_impl(const void *in_dev, uint64_t n, uint32_t chunk, uint32_t method_mask, uint32_t flags,
                            const uint8_t *marker, uint32_t marker_bytes, void *out_dev, uint64_t out_cap,
                            void *work_dev, uint64_t work_bytes, ambc_compress_result *res, cudaStream_t stream,
-                           const cudaEvent_t *piece_ready, uint64_t piece_chunks, uint32_t n_pieces);
+                           const cudaEvent_t *piece_ready, uint64_t piece_chunks, uint32_t n_pieces,
+                           const AmbcPieceOut *po);
+extern "C" uint64_t ambc_scan_state_bytes(void) { return sizeof(ScanState); }
 
 extern "C" int ambc_compress_dev(const void *in_dev, uint64_t n, uint32_t chunk, uint32_t method_mask,
                                  uint32_t flags, const uint8_t *marker, uint32_t marker_bytes, void *out_dev,
@@ -373,13 +380,14 @@ extern "C" int ambc_compress_dev(const void *in_dev, uint64_t n, uint32_t chunk,
                                  void *stream_)
 {
     return ambc_compress_dev_impl(in_dev, n, chunk, method_mask, flags, marker, marker_bytes, out_dev, out_cap, work_dev,
-                                  work_bytes, res, (cudaStream_t)stream_, nullptr, 0, 0);
+                                  work_bytes, res, (cudaStream_t)stream_, nullptr, 0, 0, nullptr);
 }
 
 int ambc_compress_dev_impl(const void *in_dev, uint64_t n, uint32_t chunk, uint32_t method_mask, uint32_t flags,
                            const uint8_t *marker, uint32_t marker_bytes, void *out_dev, uint64_t out_cap,
                            void *work_dev, uint64_t work_bytes, ambc_compress_result *res, cudaStream_t stream,
-                           const cudaEvent_t *piece_ready, uint64_t piece_chunks, uint32_t n_pieces)
+                           const cudaEvent_t *piece_ready, uint64_t piece_chunks, uint32_t n_pieces,
+                           const AmbcPieceOut *po)
 {
     if (!res || !marker || marker_bytes < 1 || marker_bytes > 4 || chunk == 0)
         return ambc_fail(AMBC_E_ARG, "ambc_compress_dev: bad argument");
@@ -408,6 +416,10 @@ int ambc_compress_dev_impl(const void *in_dev, uint64_t n, uint32_t chunk, uint3
         if (out_cap < marker_bytes + 12) return ambc_fail(AMBC_E_CAPACITY, "out too small");
         CUDA_TRY(cudaMemcpyAsync(out_dev, endp, marker_bytes + 12, cudaMemcpyHostToDevice, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
+        if (po && po->out_host) {
+            if (po->out_cap < marker_bytes + 12) return ambc_fail(AMBC_E_CAPACITY, "ambc_compress_host: out_cap too small");
+            memcpy(po->out_host, endp, marker_bytes + 12);
+        }
         res->body_len = marker_bytes + 12;
         res->first_raw = -1;
         return AMBC_OK;
@@ -425,47 +437,78 @@ int ambc_compress_dev_impl(const void *in_dev, uint64_t n, uint32_t chunk, uint3
 
     if (native) {
         size_t smem = chunk <= LZ2_NMAX ? chunkctx_fast_smem_bytes((int)chunk) : chunkctx_smem_bytes((int)chunk, (int)chunk);
-        CUDA_TRY(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ambc_timing_mark(0, stream);
-        if (piece_ready && n_pieces > 1 && piece_chunks) {
-            for (uint32_t k = 0; k < n_pieces; k++) {
-                uint64_t c0 = (uint64_t)k * piece_chunks, c1 = min<uint64_t>(L.n_chunks, c0 + piece_chunks);
-                if (c0 >= c1) break;
-                CUDA_TRY(cudaStreamWaitEvent(stream, piece_ready[k], 0));
-                k_select<<<(unsigned)(c1 - c0), AMBC_BLOCK, smem, stream>>>((const uint8_t *)in_dev, n, chunk, method_mask,
-                                                                          ovh, W + L.slots, L.slot_stride, type, comp,
-                                                                          &st->first_raw, c0, c1);
-                ambc_count_launch();
-            }
-        } else {
-            k_select<<<grid_chunks, AMBC_BLOCK, smem, stream>>>((const uint8_t *)in_dev, n, chunk, method_mask, ovh,
-                                                                W + L.slots, L.slot_stride, type, comp,
-                                                                &st->first_raw, 0, L.n_chunks);
-            ambc_count_launch();
-        }
-        CUDA_TRY(cudaGetLastError());
-        ambc_timing_mark(1, stream);
-        k_sizes<<<(unsigned)L.n_tiles, 256, 0, stream>>>(type, comp, L.n_chunks, chunk, n, ovh, flags, st, tiles);
-        ambc_count_launch();
-        k_scan_tiles<<<1, 1024, 0, stream>>>(tiles, L.n_tiles, type, comp, L.n_chunks, chunk, n, ovh, flags, st,
-                                             (uint8_t *)out_dev, out_cap, marker_word, marker_bytes);
-        ambc_count_launch();
-        k_offsets<<<(unsigned)L.n_tiles, 256, 0, stream>>>(type, comp, L.n_chunks, chunk, n, ovh, flags, st, tiles,
-                                                           offs);
-        ambc_count_launch();
-        CUDA_TRY(cudaGetLastError());
-        ambc_timing_mark(2, stream);
         size_t psmem = 32 + (((size_t)chunk + 15) & ~(size_t)15) + 32;
+        CUDA_TRY(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute(k_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-        k_pack<<<grid_chunks, PACK_BLOCK, psmem, stream>>>((const uint8_t *)in_dev, n, chunk, W + L.slots,
-                                                           L.slot_stride, type, comp, offs, st, flags, marker_word,
-                                                           marker_bytes, (uint8_t *)out_dev, out_cap, L.n_chunks);
-        ambc_count_launch();
-        CUDA_TRY(cudaGetLastError());
+        // piece-wise run (host-buffer path): select / scan / pack of piece k are queued behind the
+        // upload of piece k; the finished body bytes of a piece go home while later pieces compute
+        const bool pieces = piece_ready && n_pieces > 1 && piece_chunks && piece_chunks % SCAN_TILE == 0;
+        if (!pieces && piece_ready)
+            for (uint32_t k = 0; k < n_pieces; k++) CUDA_TRY(cudaStreamWaitEvent(stream, piece_ready[k], 0));
+        const uint32_t np = pieces ? n_pieces : 1;
+        const bool stream_out = pieces && po && po->out_host && po->states && po->done;
+        for (uint32_t k = 0; k < np; k++) {
+            const uint64_t c0 = pieces ? (uint64_t)k * piece_chunks : 0;
+            const uint64_t c1 = pieces ? min<uint64_t>(L.n_chunks, c0 + piece_chunks) : L.n_chunks;
+            if (c0 >= c1) break;
+            const bool last = c1 == L.n_chunks;
+            const unsigned gch = (unsigned)min<uint64_t>(c1 - c0, 0x7fffffffull);
+            const unsigned gt = (unsigned)((c1 - c0 + SCAN_TILE - 1) / SCAN_TILE);
+            if (pieces) CUDA_TRY(cudaStreamWaitEvent(stream, piece_ready[k], 0));
+            if (k == 0) ambc_timing_mark(0, stream);
+            k_select<<<gch, AMBC_BLOCK, smem, stream>>>((const uint8_t *)in_dev, n, chunk, method_mask, ovh, W + L.slots,
+                                                        L.slot_stride, type, comp, &st->first_raw, c0, c1);
+            ambc_count_launch();
+            if (last) ambc_timing_mark(1, stream);
+            k_sizes<<<gt, 256, 0, stream>>>(type, comp, c0, c1, chunk, n, ovh, flags, st, tiles);
+            ambc_count_launch();
+            k_scan_tiles<<<1, 1024, 0, stream>>>(tiles, c0 / SCAN_TILE, (c1 + SCAN_TILE - 1) / SCAN_TILE, last ? 1 : 0, type,
+                                                 comp, L.n_chunks, chunk, n, ovh, flags, st, (uint8_t *)out_dev, out_cap,
+                                                 marker_word, marker_bytes);
+            ambc_count_launch();
+            k_offsets<<<gt, 256, 0, stream>>>(type, comp, c0, c1, chunk, n, ovh, flags, st, tiles, offs);
+            ambc_count_launch();
+            if (last) ambc_timing_mark(2, stream);
+            k_pack<<<gch, PACK_BLOCK, psmem, stream>>>((const uint8_t *)in_dev, n, chunk, W + L.slots, L.slot_stride, type,
+                                                       comp, offs, st, flags, marker_word, marker_bytes, (uint8_t *)out_dev,
+                                                       out_cap, c0, c1, pieces ? 0 : 1);
+            ambc_count_launch();
+            CUDA_TRY(cudaGetLastError());
+            if (stream_out) {
+                CUDA_TRY(cudaMemcpyAsync((uint8_t *)po->states + (size_t)k * sizeof(ScanState), st, sizeof(ScanState),
+                                         cudaMemcpyDeviceToHost, stream));
+                CUDA_TRY(cudaEventRecord(po->done[k], stream));
+            }
+        }
         ambc_timing_mark(3, stream);
         ambc_timing().pending_c = ambc_timing().on;
+        uint64_t sent = 0;
+        if (stream_out) {
+            // bytes [sent, carry_k) are final after piece k as long as no chunk lacked a winner
+            for (uint32_t k = 0; k + 1 < np; k++) {
+                CUDA_TRY(cudaEventSynchronize(po->done[k]));
+                const ScanState *hs = (const ScanState *)((const uint8_t *)po->states + (size_t)k * sizeof(ScanState));
+                if (hs->first_raw != ~0ull || hs->carry > po->out_cap) break;
+                if (hs->carry > sent) {
+                    CUDA_TRY(cudaMemcpyAsync((uint8_t *)po->out_host + sent, (const uint8_t *)out_dev + sent, hs->carry - sent,
+                                             cudaMemcpyDeviceToHost, po->d2h));
+                    sent = hs->carry;
+                }
+            }
+        }
         CUDA_TRY(cudaMemcpyAsync(&h_st, st, sizeof h_st, cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
+        if (po && po->out_host) {
+            if (h_st.body_len > po->out_cap || h_st.body_len > out_cap) {
+                cudaStreamSynchronize(po->d2h);
+                return ambc_fail(AMBC_E_CAPACITY, "ambc_compress_host: out_cap %llu < body %llu",
+                                 (unsigned long long)po->out_cap, (unsigned long long)h_st.body_len);
+            }
+            CUDA_TRY(cudaMemcpyAsync((uint8_t *)po->out_host + sent, (const uint8_t *)out_dev + sent, h_st.body_len - sent,
+                                     cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            CUDA_TRY(cudaStreamSynchronize(po->d2h));
+        }
     } else {
         // one raw package: header + memcpy + END, no kernel needed beyond the copy engine
         if (piece_ready)
@@ -485,6 +528,10 @@ int ambc_compress_dev_impl(const void *in_dev, uint64_t n, uint32_t chunk, uint3
         CUDA_TRY(cudaMemcpyAsync(o + ovh, in_dev, n, cudaMemcpyDeviceToDevice, stream));
         CUDA_TRY(cudaMemcpyAsync(o + ovh + n, endp, marker_bytes + 12, cudaMemcpyHostToDevice, stream));
         CUDA_TRY(cudaMemsetAsync(type, 255, L.n_chunks, stream));
+        if (po && po->out_host) {
+            if (body > po->out_cap) return ambc_fail(AMBC_E_CAPACITY, "ambc_compress_host: out_cap too small");
+            CUDA_TRY(cudaMemcpyAsync(po->out_host, out_dev, body, cudaMemcpyDeviceToHost, stream));
+        }
         CUDA_TRY(cudaStreamSynchronize(stream));
         h_st.body_len = body;
         h_st.n_packages = 1;
