@@ -10,6 +10,21 @@
 #pragma once
 #include "common.cuh"
 
+// dev-only phase timeline (build with -DAMBC_PHASE_TIMING): thread 0 of every CTA adds the
+// clock64() delta since the previous mark to g_phase[id]
+#ifdef AMBC_PHASE_TIMING
+__device__ unsigned long long g_phase[32];
+__device__ __forceinline__ void phase_mark(long long &t, int id)
+{
+    if (threadIdx.x == 0) { long long now = clock64(); atomicAdd(&g_phase[id], (unsigned long long)(now - t)); t = now; }
+}
+#define PHASE_DECL long long ph_t = clock64();
+#define PHASE(id) phase_mark(ph_t, id)
+#else
+#define PHASE_DECL
+#define PHASE(id)
+#endif
+
 struct ChunkCtx {
     uint8_t *sd;       // chunk bytes, 16-byte aligned, followed by AMBC_PAD zero bytes
     int n;             // chunk length (<= AMBC_NMAX)

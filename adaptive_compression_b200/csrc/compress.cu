@@ -35,7 +35,9 @@ __device__ SelectOut select_chunk(ChunkCtx &c, uint32_t mask, int ovh)
 {
     const int n = c.n;
     ChunkFeatures f;
+    PHASE_DECL
     chunk_features(c, f);
+    PHASE(1);
     HuffScratch hs = huff_scratch(c.X);
 
     // gates (compression_methods.py:154-180, 315-343, 551-574)
@@ -64,7 +66,9 @@ __device__ SelectOut select_chunk(ChunkCtx &c, uint32_t mask, int ovh)
         // when it cannot win (strict '<' keeps the earlier method on ties, :575)
         int lb = lz_lower_bound(n);
         if (lb < best_len && lb + ovh < n) {
+            PHASE(10);
             int len = chunk_lz_encode(c);
+            PHASE(11);
             if (len < best_len && len + ovh < n) { best_type = 2; best_len = len; }
         }
     }
@@ -81,7 +85,9 @@ __device__ SelectOut select_chunk(ChunkCtx &c, uint32_t mask, int ovh)
             }
         }
     }
+    PHASE(12);
     if (best_type == 1) chunk_rle_encode(c);
+    PHASE(13);
     SelectOut o;
     o.type = best_type;
     o.len = best_type == 255 ? n : best_len;
@@ -547,6 +553,14 @@ int ambc_compress_dev_impl(const void *in_dev, uint64_t n, uint32_t chunk, uint3
     return AMBC_OK;
 }
 
+#ifdef AMBC_PHASE_TIMING
+extern "C" int ambc_phase_read(unsigned long long *out32, int reset)
+{
+    cudaMemcpyFromSymbol(out32, g_phase, sizeof(unsigned long long) * 32);
+    if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(g_phase, z, sizeof z); }
+    return 0;
+}
+#endif
 int ambc_lz_levels_compress(const int *levels, int n) { return lz_levels_upload(levels, n); }
 int ambc_lz_coop_compress(int t) { return lz_coop_upload(t); }
 int ambc_lz_force_buckets_compress(int on) { return lz_force_buckets_upload(on); }

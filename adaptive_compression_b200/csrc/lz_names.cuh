@@ -255,14 +255,17 @@ __device__ inline int lz2_refine_binary(ChunkCtx &c, const uint16_t *S, int k, i
     const int n = c.n, tid = threadIdx.x;
     volatile int *ovf = c.red + 31;
     if (tid == 0) *ovf = 0;
+    PHASE_DECL
     for (int pi = tid; pi < np; pi += AMBC_BLOCK) { mem[pi] = 1; mem2[pi] = 0; }
     __syncthreads();
+    PHASE(14);
     for (int step = k >> 1; step >= 1; step >>= 1) {
         // node t of this round: length k + (2t+1) * step inside the interval of half-width `step`
         int cntl = 0;
         for (int pi = tid; pi < np; pi += AMBC_BLOCK) cntl += __popc((uint32_t)mem[pi]);
         int E;
         const int base = block_excl_scan(cntl, c.red, &E);
+        PHASE(15);
         if (E >= LZ2_ISLOTS) return 1; // (strictly below the slot count: a probe always ends at a free slot)
         if (E == 0) return 0;
         int R = 1;
@@ -270,6 +273,7 @@ __device__ inline int lz2_refine_binary(ChunkCtx &c, const uint16_t *S, int k, i
         for (int r = 0; r < R; r++) {
             lz2_clear(c, LZ2_RSLOTS);
             __syncthreads();
+            PHASE(16);
             int overflow = 0, idx = base;
             for (int pi = tid; pi < np; pi += AMBC_BLOCK) {
                 const int p = plist[pi];
@@ -294,6 +298,7 @@ __device__ inline int lz2_refine_binary(ChunkCtx &c, const uint16_t *S, int k, i
             }
             if (overflow) *ovf = 1;
             __syncthreads();
+            PHASE(17);
             idx = base;
             for (int pi = tid; pi < np; pi += AMBC_BLOCK) {
                 const int p = plist[pi];
@@ -315,10 +320,12 @@ __device__ inline int lz2_refine_binary(ChunkCtx &c, const uint16_t *S, int k, i
                 mem2[pi] = (uint8_t)nm2;
             }
             __syncthreads();
+            PHASE(18);
             if (*ovf) return -1;
         }
         for (int pi = tid; pi < np; pi += AMBC_BLOCK) { mem[pi] = mem2[pi]; mem2[pi] = 0; }
         __syncthreads();
+        PHASE(19);
     }
     return 0;
 }
@@ -329,7 +336,9 @@ __device__ inline bool lz2_refine(ChunkCtx &c, const uint16_t *S, const uint16_t
     // list memory: plist 8 KiB | islot 16 KiB | mem 4 KiB | mem2 4 KiB
     uint16_t *plist = (uint16_t *)c.L;
     uint16_t *islot = (uint16_t *)(c.L + 8192);
+    PHASE_DECL
     const int np = lz2_participants(c, S, D, k, plist, LZ2_NMAX);
+    PHASE(20);
     if (np == 0) return true;
     if (k >= LZ2_BIN_MINK) {
         const int rc = lz2_refine_binary(c, S, k, np, plist, c.L + 24576, c.L + 28672, islot);
@@ -345,15 +354,25 @@ __device__ inline bool lz2_match_all(ChunkCtx &c)
 {
     uint16_t *A = c.nameA, *B = c.nameB;
     if (c.n < 3) return true;
+    PHASE_DECL // (dev-only phase timeline, see chunk_codec.cuh)
     const int any4 = lz2_level4(c, A);
+    PHASE(2);
     lz2_level3(c, A, B);
+    PHASE(3);
     if (!any4) return true;
     const int any8 = lz2_double(c, A, B, 4);
+    PHASE(4);
     if (!lz2_refine(c, A, B, 4)) return false;
+    PHASE(5);
     if (!any8) return true;
     const int any16 = lz2_double(c, B, A, 8);
+    PHASE(6);
     if (!lz2_refine(c, B, A, 8)) return false;
+    PHASE(7);
     if (!any16) return true;
     lz2_double(c, A, B, 16);
-    return lz2_refine(c, A, B, 16);
+    PHASE(8);
+    const bool ok = lz2_refine(c, A, B, 16);
+    PHASE(9);
+    return ok;
 }
