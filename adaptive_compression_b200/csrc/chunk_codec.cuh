@@ -20,9 +20,11 @@ __device__ __forceinline__ void phase_mark(long long &t, int id)
 }
 #define PHASE_DECL long long ph_t = clock64();
 #define PHASE(id) phase_mark(ph_t, id)
+#define PHASE_SYNC(id) do { __syncthreads(); phase_mark(ph_t, id); } while (0)
 #else
 #define PHASE_DECL
 #define PHASE(id)
+#define PHASE_SYNC(id)
 #endif
 
 struct ChunkCtx {
@@ -167,7 +169,7 @@ struct ChunkFeatures {
     int small;      // sampled |delta| < 32 count        (:658-662)
     int distinct3;  // distinct trigrams among the first min(n-3, 1000) positions (:333-336)
     int K;          // distinct byte values
-    int rle_pairs;  // (byte,count) pairs RLE would emit
+    int rle_pairs;  // (byte,count) pairs RLE would emit -- defined only when the RLE gate holds
     double H;       // entropy, parallel sum (order-insensitive to ~1e-13)
 };
 
@@ -190,6 +192,7 @@ __device__ inline void chunk_features(ChunkCtx &c, ChunkFeatures &f)
     for (int i = tid; i < 256; i += AMBC_BLOCK) c.hist[i] = 0;
     for (int i = tid; i < 2048 / 4; i += AMBC_BLOCK) ((uint4 *)tri)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
+    PHASE_DECL
 
     // histogram (run-aggregated shared atomics) + run-boundary bitmap
     for (int s = tid; s < nsl; s += AMBC_BLOCK) {
@@ -213,6 +216,7 @@ __device__ inline void chunk_features(ChunkCtx &c, ChunkFeatures &f)
         c.bmask[s] = mask;
     }
 
+    PHASE_SYNC(21);
     // sampled gates: RLE (:165-180) and Delta (:651-667) share the sample positions
     int rep = 0, small = 0;
     if (n >= 4) {
@@ -224,6 +228,7 @@ __device__ inline void chunk_features(ChunkCtx &c, ChunkFeatures &f)
             small += (abs(x - y) < 32);
         }
     }
+    PHASE_SYNC(22);
     // distinct trigrams (:326-343)
     int ins = 0;
     if (n >= 100) {
@@ -239,30 +244,47 @@ __device__ inline void chunk_features(ChunkCtx &c, ChunkFeatures &f)
             }
         }
     }
-    f.rep = block_sum(rep, c.red);
-    f.small = block_sum(small, c.red);
-    f.distinct3 = block_sum(ins, c.red); // also orders hist / bmask writes before the reads below
+    PHASE_SYNC(23);
+    // one block reduction for the three gate counters (also orders hist / bmask writes before the reads below)
+    int *redx = (int *)(c.X + 8192); // 4 x AMBC_WARPS ints behind the trigram set
+    {
+        const int lane = tid & 31, w = tid >> 5;
+        int a = warp_sum(rep), b = warp_sum(small), d = warp_sum(ins);
+        if (lane == 0) { redx[w] = a; redx[AMBC_WARPS + w] = b; redx[2 * AMBC_WARPS + w] = d; }
+        __syncthreads();
+        int ra = 0, rb = 0, rd = 0;
+#pragma unroll
+        for (int i = 0; i < AMBC_WARPS; i++) { ra += redx[i]; rb += redx[AMBC_WARPS + i]; rd += redx[2 * AMBC_WARPS + i]; }
+        f.rep = ra; f.small = rb; f.distinct3 = rd;
+        __syncthreads();
+    }
 
-    // RLE pair count: a run of R bytes -> ceil(R/255) pairs (:95-109)
+    PHASE(24);
+    // RLE pair count: a run of R bytes -> ceil(R/255) pairs (:95-109).  Only needed (and only
+    // defined) when the RLE gate holds (:177-180), which is rare outside run-heavy data.
     int pairs = 0;
-    for (int s = tid; s < nsl; s += AMBC_BLOCK) {
-        uint32_t w = c.bmask[s];
-        while (w) {
-            int bit = __ffs(w) - 1;
-            w &= w - 1;
-            int p = 32 * s + bit, q;
-            if (w) q = 32 * s + __ffs(w) - 1;
-            else {
-                q = n;
-                for (int s2 = s + 1; s2 < nsl; s2++) {
-                    uint32_t w2 = c.bmask[s2];
-                    if (w2) { q = 32 * s2 + __ffs(w2) - 1; break; }
+    const bool rle_gate = n >= 4 && __ddiv_rn((double)f.rep, (double)(min(1000, n) - 1)) > 0.3;
+    if (rle_gate) {
+        for (int s = tid; s < nsl; s += AMBC_BLOCK) {
+            uint32_t w = c.bmask[s];
+            while (w) {
+                int bit = __ffs(w) - 1;
+                w &= w - 1;
+                int p = 32 * s + bit, q;
+                if (w) q = 32 * s + __ffs(w) - 1;
+                else {
+                    q = n;
+                    for (int s2 = s + 1; s2 < nsl; s2++) {
+                        uint32_t w2 = c.bmask[s2];
+                        if (w2) { q = 32 * s2 + __ffs(w2) - 1; break; }
+                    }
                 }
+                const int R = q - p;
+                pairs += R <= 255 ? 1 : (R + 254) / 255;
             }
-            pairs += (q - p + 254) / 255;
         }
     }
-    f.rle_pairs = block_sum(pairs, c.red);
+    PHASE(25);
 
     // entropy (:566-574), tree sum; the caller resolves near-threshold cases in order
     double hsum = 0.0;
@@ -275,8 +297,22 @@ __device__ inline void chunk_features(ChunkCtx &c, ChunkFeatures &f)
             hsum -= p * log2(p);
         }
     }
-    f.K = block_sum(k, c.red);
-    f.H = block_sum_f64(hsum, (volatile double *)c.red);
+    {   // one block reduction for pairs, K and H
+        const int lane = tid & 31, w = tid >> 5;
+        int a = warp_sum(pairs), b = warp_sum(k);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) hsum += __shfl_xor_sync(FULL_MASK, hsum, d);
+        double *redd = (double *)(redx + 2 * AMBC_WARPS);
+        if (lane == 0) { redx[w] = a; redx[AMBC_WARPS + w] = b; redd[w] = hsum; }
+        __syncthreads();
+        int ra = 0, rb = 0;
+        double rh = 0.0;
+#pragma unroll
+        for (int i = 0; i < AMBC_WARPS; i++) { ra += redx[i]; rb += redx[AMBC_WARPS + i]; rh += redd[i]; }
+        f.rle_pairs = ra; f.K = rb; f.H = rh;
+        __syncthreads();
+    }
+    PHASE(26);
 }
 
 // first-occurrence order of the byte values (Counter insertion order, :368-370 / :566).
@@ -293,7 +329,9 @@ __device__ inline void chunk_first_order(ChunkCtx &c, uint32_t *firstpos, uint8_
             int bit = __ffs(w) - 1;
             w &= w - 1;
             int p = 32 * s + bit;
-            atomicMin(&firstpos[c.sd[p]], (uint32_t)p);
+            // values only decrease, so a stale plain read can only cause a redundant atomic
+            volatile uint32_t *fpv = firstpos + c.sd[p];
+            if (*fpv > (uint32_t)p) atomicMin(&firstpos[c.sd[p]], (uint32_t)p);
         }
     }
     __syncthreads();
@@ -707,6 +745,7 @@ __device__ inline int chunk_lz_encode(ChunkCtx &c)
     __syncthreads();
 
     // ---- token chain: pos -> pos + (len>2 ? len : 1) (:211-232), resolved per 32-block ---
+    PHASE_DECL
     const int nb = (n + 31) >> 5;
     uint8_t *fexit = c.X; // fexit[q * nb + b]: where a chain entering block b at offset q leaves it
     for (int b = tid; b < nb; b += AMBC_BLOCK) {
@@ -724,48 +763,80 @@ __device__ inline int chunk_lz_encode(ChunkCtx &c)
         }
     }
     __syncthreads();
-    if (tid == 0) {
-        int e = 0;
-        for (int b = 0; b < nb; b++) {
-            c.estart[b] = (uint8_t)e;
-            if (e != 255) e = fexit[e * nb + b];
+    PHASE(27);
+    {   // entry offset of every block on the chain from position 0: groups of 32 blocks are composed
+        // for all 32 entry offsets at once (one warp per group, lane = entry offset), then the few
+        // groups are chained and every group is walked from its true entry
+        uint8_t *gexit = c.X + 8192 + 2048; // [group][entry offset]
+        uint8_t *gentry = gexit + 256;      // entry offset of each group
+        const int ng = (nb + 31) >> 5, wid = tid >> 5, lane = tid & 31;
+        if (wid < ng) {
+            int e = lane;
+            const int bend = min(nb, 32 * wid + 32);
+            for (int b = 32 * wid; b < bend; b++)
+                if (e != 255) e = fexit[e * nb + b];
+            gexit[32 * wid + lane] = (uint8_t)e;
         }
-    }
-    __syncthreads();
-    const int bpt = (nb + AMBC_BLOCK - 1) / AMBC_BLOCK; // blocks per thread, contiguous
-    int tbytes = 0;
-    for (int b = tid * bpt; b < min(nb, (tid + 1) * bpt); b++) {
-        int q = c.estart[b];
-        uint32_t mask = 0;
-        while (q < 32 && 32 * b + q < n) {
-            mask |= 1u << q;
-            int L = c.mlen[32 * b + q];
-            if (L >= 3) { tbytes += 4; q += L; } else { tbytes += 2; q += 1; }
+        __syncthreads();
+        if (tid == 0) {
+            int e = 0;
+            for (int g = 0; g < ng; g++) {
+                gentry[g] = (uint8_t)e;
+                if (e != 255) e = gexit[32 * g + e];
+            }
         }
-        c.reach[b] = mask;
-    }
-    int total;
-    int off = block_excl_scan(tbytes, c.red, &total);
-    for (int b = tid * bpt; b < min(nb, (tid + 1) * bpt); b++) {
-        uint32_t w = c.reach[b];
-        while (w) {
-            int p = 32 * b + __ffs(w) - 1;
-            w &= w - 1;
-            int L = c.mlen[p];
-            if (L >= 3) {
-                if (off + 4 <= c.pcap) {
-                    int d = p - (int)c.mpos[p];
-                    c.pay[off] = 1; c.pay[off + 1] = (uint8_t)(d & 0xFF);
-                    c.pay[off + 2] = (uint8_t)(d >> 8); c.pay[off + 3] = (uint8_t)L;
-                }
-                off += 4;
-            } else {
-                if (off + 2 <= c.pcap) { c.pay[off] = 0; c.pay[off + 1] = c.sd[p]; }
-                off += 2;
+        __syncthreads();
+        if (tid < ng) {
+            int e = gentry[tid];
+            const int bend = min(nb, 32 * tid + 32);
+            for (int b = 32 * tid; b < bend; b++) {
+                c.estart[b] = (uint8_t)e;
+                if (e != 255) e = fexit[e * nb + b];
             }
         }
     }
     __syncthreads();
+    PHASE(28);
+    // per block: token-start mask, match mask, payload bytes; then every position emits its own token
+    uint32_t *mmask = (uint32_t *)(c.X + 8192);        // behind fexit (32 * nb <= 8 KiB)
+    uint32_t *boff = (uint32_t *)(c.X + 8192 + 1024);  // payload offset of the block's first token
+    const int bpt = (nb + AMBC_BLOCK - 1) / AMBC_BLOCK; // blocks per thread, contiguous
+    int tbytes = 0;
+    for (int b = tid * bpt; b < min(nb, (tid + 1) * bpt); b++) {
+        int q = c.estart[b];
+        uint32_t mask = 0, mm = 0;
+        boff[b] = (uint32_t)tbytes; // relative to this thread's first block until the scan below
+        while (q < 32 && 32 * b + q < n) {
+            mask |= 1u << q;
+            int L = c.mlen[32 * b + q];
+            if (L >= 3) { mm |= 1u << q; tbytes += 4; q += L; } else { tbytes += 2; q += 1; }
+        }
+        c.reach[b] = mask;
+        mmask[b] = mm;
+    }
+    int total;
+    const int off0 = block_excl_scan(tbytes, c.red, &total);
+    for (int b = tid * bpt; b < min(nb, (tid + 1) * bpt); b++) boff[b] += (uint32_t)off0;
+    __syncthreads();
+    PHASE(29);
+    uint16_t *pay16 = (uint16_t *)c.pay; // token offsets are even
+    for (int p = tid; p < n; p += AMBC_BLOCK) {
+        const int b = p >> 5;
+        const uint32_t bit = 1u << (p & 31), R = c.reach[b];
+        if (R & bit) {
+            const uint32_t below = R & (bit - 1), mm = mmask[b];
+            const int off = (int)boff[b] + 2 * __popc(below) + 2 * __popc(below & mm);
+            if (mm & bit) {
+                if (off + 4 <= c.pcap) {
+                    const int d = p - (int)c.mpos[p];
+                    pay16[off >> 1] = (uint16_t)(1u | ((uint32_t)(d & 0xFF) << 8));
+                    pay16[(off >> 1) + 1] = (uint16_t)((uint32_t)(d >> 8) | ((uint32_t)c.mlen[p] << 8));
+                }
+            } else if (off + 2 <= c.pcap) pay16[off >> 1] = (uint16_t)((uint32_t)c.sd[p] << 8);
+        }
+    }
+    __syncthreads();
+    PHASE(30);
     return total;
 }
 
@@ -828,23 +899,35 @@ __device__ inline int chunk_huff_build(ChunkCtx &c, HuffScratch &h, int K)
     }
     __syncthreads();
     if (tid == 0) {
+        // two-queue merge with both queue heads cached in registers: one (weight, leader) reload per pick
         int li = 0, mi = K, t = K;
+        uint32_t wl = h.nodeW[0], ll = h.lead[0];       // head of the leaf queue
+        uint32_t wm = 0xFFFFFFFFu, lm = 0xFFFFu;        // head of the merged queue (empty)
         for (int it = 0; it < K - 1; it++) {
             int pick[2];
+            uint32_t pw[2], pl0 = 0;
 #pragma unroll
             for (int z = 0; z < 2; z++) {
-                bool hasL = li < K, hasM = mi < t;
+                const bool hasL = li < K, hasM = mi < t;
                 bool takeL;
-                if (hasL && hasM) {
-                    uint32_t wl = h.nodeW[li], wm = h.nodeW[mi];
-                    takeL = (wl < wm) || (wl == wm && h.lead[li] < h.lead[mi]);
-                } else takeL = hasL;
-                pick[z] = takeL ? li++ : mi++;
+                if (hasL && hasM) takeL = (wl < wm) || (wl == wm && ll < lm);
+                else takeL = hasL;
+                if (takeL) {
+                    pick[z] = li; pw[z] = wl; if (z == 0) pl0 = ll;
+                    li++;
+                    if (li < K) { wl = h.nodeW[li]; ll = h.lead[li]; }
+                } else {
+                    pick[z] = mi; pw[z] = wm; if (z == 0) pl0 = lm;
+                    mi++;
+                    if (mi < t) { wm = h.nodeW[mi]; lm = h.lead[mi]; }
+                }
             }
-            h.nodeW[t] = h.nodeW[pick[0]] + h.nodeW[pick[1]];
-            h.lead[t] = h.lead[pick[0]];
+            const uint32_t nw = pw[0] + pw[1];
+            h.nodeW[t] = nw;
+            h.lead[t] = (uint16_t)pl0;
             h.parent[pick[0]] = (uint16_t)t; h.nbit[pick[0]] = 0;
             h.parent[pick[1]] = (uint16_t)t; h.nbit[pick[1]] = 1;
+            if (mi == t) { wm = nw; lm = pl0; } // the merged queue was empty: the new node is its head
             t++;
         }
     }

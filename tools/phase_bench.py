@@ -20,4 +20,6 @@ for k in (0, 1, 3, 4, 6):
     print(names[k], "cycles/chunk %.0f" % (tot / nch), " ".join("%s=%.0f" % (ph[i], v[i] / nch) for i in sorted(ph)),
           "chain+emit=%.0f" % ((v[11] - sum(v[2:10])) / nch),
           "| binary: init=%.0f count/scan=%.0f clear=%.0f insert=%.0f resolve=%.0f copy=%.0f participants=%.0f" %
-          tuple(v[i] / nch for i in (14, 15, 16, 17, 18, 19, 20)), flush=True)
+          tuple(v[i] / nch for i in (14, 15, 16, 17, 18, 19, 20)),
+          "| features: hist=%.0f samples=%.0f trigrams=%.0f 3sums=%.0f pairs=%.0f entropy=%.0f" % tuple(v[i] / nch for i in (21, 22, 23, 24, 25, 26)),
+          "| chain: exits=%.0f walk=%.0f count+scan=%.0f emit=%.0f" % tuple(v[i] / nch for i in (27, 28, 29, 30)), flush=True)
