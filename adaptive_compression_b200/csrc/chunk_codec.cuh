@@ -317,31 +317,47 @@ __device__ inline void chunk_features(ChunkCtx &c, ChunkFeatures &f)
 
 // first-occurrence order of the byte values (Counter insertion order, :368-370 / :566).
 // order[r] = r-th distinct byte value; firstpos scratch = 256 uint32.  Collective.
+// rank of key k among the 256 entries of keys[] (number of smaller entries), AMBC_BLOCK / 256
+// threads per key: thread tid serves key tid / RANK_TPK.  Warp-collective.
+#define RANK_TPK (AMBC_BLOCK / 256)
+static_assert(RANK_TPK == 1 || RANK_TPK == 2 || RANK_TPK == 4, "rank256 layout");
+template <class T>
+__device__ __forceinline__ int rank256(const T *keys, T k)
+{
+    const int part = threadIdx.x % RANK_TPK;
+    constexpr int SPAN = 256 / RANK_TPK;
+    int r = 0;
+#pragma unroll 8
+    for (int j = part * SPAN; j < (part + 1) * SPAN; j++) r += (keys[j] < k);
+#pragma unroll
+    for (int d = 1; d < RANK_TPK; d <<= 1) r += __shfl_xor_sync(FULL_MASK, r, d);
+    return r;
+}
+
 __device__ inline void chunk_first_order(ChunkCtx &c, uint32_t *firstpos, uint8_t *order)
 {
     const int n = c.n, tid = threadIdx.x;
     for (int i = tid; i < 256; i += AMBC_BLOCK) firstpos[i] = 0xFFFFFFFFu;
     __syncthreads();
-    const int nsl = (n + 31) >> 5;
-    for (int s = tid; s < nsl; s += AMBC_BLOCK) {
-        uint32_t w = c.bmask[s]; // run starts: only they can be first occurrences
-        while (w) {
-            int bit = __ffs(w) - 1;
-            w &= w - 1;
-            int p = 32 * s + bit;
+    volatile uint32_t *fpv = firstpos;
+    for (int s = tid; 8 * s < n; s += AMBC_BLOCK) { // 8 bytes per thread and step
+        const uint2 w = *(const uint2 *)(c.sd + 8 * s);
+        const int m = min(8, n - 8 * s);
+        uint32_t prev = 0x100u;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t v = ((j < 4 ? w.x : w.y) >> (8 * (j & 3))) & 0xFFu;
             // values only decrease, so a stale plain read can only cause a redundant atomic
-            volatile uint32_t *fpv = firstpos + c.sd[p];
-            if (*fpv > (uint32_t)p) atomicMin(&firstpos[c.sd[p]], (uint32_t)p);
+            if (j < m && v != prev && fpv[v] > (uint32_t)(8 * s + j)) atomicMin(&firstpos[v], (uint32_t)(8 * s + j));
+            prev = v;
         }
     }
     __syncthreads();
-    for (int b = tid; b < 256; b += AMBC_BLOCK) {
-        uint32_t fp = firstpos[b];
-        if (fp != 0xFFFFFFFFu) {
-            int r = 0;
-            for (int j = 0; j < 256; j++) r += (firstpos[j] < fp);
-            order[r] = (uint8_t)b;
-        }
+    {
+        const int b = tid / RANK_TPK;
+        const uint32_t fp = firstpos[b];
+        const int r = rank256(firstpos, fp);
+        if (fp != 0xFFFFFFFFu && tid % RANK_TPK == 0) order[r] = (uint8_t)b;
     }
     __syncthreads();
 }
@@ -880,6 +896,7 @@ __device__ inline HuffScratch huff_scratch(uint8_t *X)
 __device__ inline int chunk_huff_build(ChunkCtx &c, HuffScratch &h, int K)
 {
     const int tid = threadIdx.x;
+    PHASE_DECL
     for (int b = tid; b < 256; b += AMBC_BLOCK) {
         uint32_t cnt = c.hist[b];
         h.key[b] = cnt ? ((cnt << 8) | (uint32_t)b) : 0xFFFFFFFFu;
@@ -887,17 +904,18 @@ __device__ inline int chunk_huff_build(ChunkCtx &c, HuffScratch &h, int K)
         h.codeOf[b] = 0;
     }
     __syncthreads();
-    for (int b = tid; b < 256; b += AMBC_BLOCK) { // rank sort: keys are distinct
-        uint32_t k = h.key[b];
-        if (k != 0xFFFFFFFFu) {
-            int r = 0;
-            for (int j = 0; j < 256; j++) r += (h.key[j] < k);
+    {   // rank sort: keys are distinct
+        const int b = tid / RANK_TPK;
+        const uint32_t k = h.key[b];
+        const int r = rank256(h.key, k);
+        if (k != 0xFFFFFFFFu && tid % RANK_TPK == 0) {
             h.nodeW[r] = k >> 8;
             h.lead[r] = (uint16_t)b;
             h.leafsym[r] = (uint8_t)b;
         }
     }
     __syncthreads();
+    PHASE(31);
     if (tid == 0) {
         // two-queue merge with both queue heads cached in registers: one (weight, leader) reload per pick
         int li = 0, mi = K, t = K;
@@ -932,6 +950,7 @@ __device__ inline int chunk_huff_build(ChunkCtx &c, HuffScratch &h, int K)
         }
     }
     __syncthreads();
+    PHASE(0);
     const int root = 2 * K - 2;
     int bits = 0;
     for (int j = tid; j < K; j += AMBC_BLOCK) {
@@ -955,7 +974,9 @@ __device__ inline int chunk_huff_build(ChunkCtx &c, HuffScratch &h, int K)
 __device__ inline int chunk_huff_emit(ChunkCtx &c, HuffScratch &h, int K, int total_bits)
 {
     const int n = c.n, tid = threadIdx.x;
+    PHASE_DECL
     chunk_first_order(c, h.firstpos, h.order);
+    PHASE(14);
     const int hdr = 1 + 5 * K + 4;
     const int nbytes = (total_bits + 7) >> 3;
     if (tid == 0 && c.pcap >= 1) c.pay[0] = (uint8_t)K;
@@ -973,22 +994,29 @@ __device__ inline int chunk_huff_emit(ChunkCtx &c, HuffScratch &h, int K, int to
     const int nwords = (total_bits + 31) >> 5;
     const int wcap = min(nwords, (c.pcap >> 2) + 1);
     for (int i = tid; i < wcap; i += AMBC_BLOCK) bw[i] = 0;
-    const int nsl = (n + 31) >> 5;
+    const int nsl = (n + 7) >> 3; // 8-byte slices, contiguous per thread
     const int spt = (nsl + AMBC_BLOCK - 1) / AMBC_BLOCK;
     int mybits = 0;
     for (int s = tid * spt; s < min(nsl, (tid + 1) * spt); s++) {
-        const int m = min(32, n - 32 * s);
-        for (int j = 0; j < m; j++) mybits += h.lenOf[c.sd[32 * s + j]];
+        const uint2 w = *(const uint2 *)(c.sd + 8 * s);
+        const int m = min(8, n - 8 * s);
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (j < m) mybits += h.lenOf[((j < 4 ? w.x : w.y) >> (8 * (j & 3))) & 0xFFu];
     }
     int tot;
     int g = block_excl_scan(mybits, c.red, &tot); // includes the barrier after zeroing bw
+    PHASE(15);
     {
         int w = g >> 5, used = g & 31;
         uint32_t cur = 0;
         for (int s = tid * spt; s < min(nsl, (tid + 1) * spt); s++) {
-            const int m = min(32, n - 32 * s);
-            for (int j = 0; j < m; j++) {
-                int sym = c.sd[32 * s + j];
+            const uint2 w8 = *(const uint2 *)(c.sd + 8 * s);
+            const int m = min(8, n - 8 * s);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (j >= m) break;
+                const int sym = ((j < 4 ? w8.x : w8.y) >> (8 * (j & 3))) & 0xFFu;
                 uint32_t code = h.codeOf[sym];
                 int l = h.lenOf[sym];
                 int space = 32 - used;
@@ -1011,9 +1039,11 @@ __device__ inline int chunk_huff_emit(ChunkCtx &c, HuffScratch &h, int K, int to
         if (used && w < wcap) atomicOr(&bw[w], cur);
     }
     __syncthreads();
+    PHASE(16);
     for (int k = tid; k < nbytes; k += AMBC_BLOCK) {
         if (hdr + k < c.pcap) c.pay[hdr + k] = (uint8_t)(bw[k >> 2] >> (24 - 8 * (k & 3)));
     }
     __syncthreads();
+    PHASE(17);
     return hdr + nbytes;
 }
