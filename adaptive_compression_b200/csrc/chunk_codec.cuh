@@ -909,43 +909,41 @@ __device__ inline int chunk_huff_build(ChunkCtx &c, HuffScratch &h, int K)
         const uint32_t k = h.key[b];
         const int r = rank256(h.key, k);
         if (k != 0xFFFFFFFFu && tid % RANK_TPK == 0) {
-            h.nodeW[r] = k >> 8;
-            h.lead[r] = (uint16_t)b;
+            h.nodeW[r] = k; // (weight << 8 | leader): one word orders nodes by (weight, leader)
             h.leafsym[r] = (uint8_t)b;
         }
     }
     __syncthreads();
     PHASE(31);
     if (tid == 0) {
-        // two-queue merge with both queue heads cached in registers: one (weight, leader) reload per pick
+        // two-queue merge, both queue heads cached in registers: one reload per pick.  Weights stay
+        // below 2^24 (chunks of at most 8192 bytes), leaders are byte values.
         int li = 0, mi = K, t = K;
-        uint32_t wl = h.nodeW[0], ll = h.lead[0];       // head of the leaf queue
-        uint32_t wm = 0xFFFFFFFFu, lm = 0xFFFFu;        // head of the merged queue (empty)
+        uint32_t kl = h.nodeW[0];      // head of the leaf queue
+        uint32_t km = 0xFFFFFFFFu;     // head of the merged queue (empty)
         for (int it = 0; it < K - 1; it++) {
             int pick[2];
-            uint32_t pw[2], pl0 = 0;
+            uint32_t pk[2];
 #pragma unroll
             for (int z = 0; z < 2; z++) {
                 const bool hasL = li < K, hasM = mi < t;
-                bool takeL;
-                if (hasL && hasM) takeL = (wl < wm) || (wl == wm && ll < lm);
-                else takeL = hasL;
+                const bool takeL = (hasL && hasM) ? kl < km : hasL;
                 if (takeL) {
-                    pick[z] = li; pw[z] = wl; if (z == 0) pl0 = ll;
+                    pick[z] = li; pk[z] = kl;
                     li++;
-                    if (li < K) { wl = h.nodeW[li]; ll = h.lead[li]; }
+                    if (li < K) kl = h.nodeW[li];
                 } else {
-                    pick[z] = mi; pw[z] = wm; if (z == 0) pl0 = lm;
+                    pick[z] = mi; pk[z] = km;
                     mi++;
-                    if (mi < t) { wm = h.nodeW[mi]; lm = h.lead[mi]; }
+                    if (mi < t) km = h.nodeW[mi];
                 }
             }
-            const uint32_t nw = pw[0] + pw[1];
-            h.nodeW[t] = nw;
-            h.lead[t] = (uint16_t)pl0;
+            // merged weight = sum, leader = leader of the lower node (:482-494)
+            const uint32_t nk = (((pk[0] >> 8) + (pk[1] >> 8)) << 8) | (pk[0] & 0xFFu);
+            h.nodeW[t] = nk;
             h.parent[pick[0]] = (uint16_t)t; h.nbit[pick[0]] = 0;
             h.parent[pick[1]] = (uint16_t)t; h.nbit[pick[1]] = 1;
-            if (mi == t) { wm = nw; lm = pl0; } // the merged queue was empty: the new node is its head
+            if (mi == t) km = nk; // the merged queue was empty: the new node is its head
             t++;
         }
     }

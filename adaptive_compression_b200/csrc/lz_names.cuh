@@ -48,9 +48,10 @@ __device__ __forceinline__ uint32_t lz2_slot_pos(uint32_t v) { return (v >> 1) &
 __device__ __forceinline__ uint32_t lz2_slot_name(uint32_t v) { return ((v >> 1) & 0xFFFu) | ((v & 1u) ? 0u : LZ2_NS); }
 
 // first occurrence of the raw key `w` (bytes of sd + p under kmask): insert p, return the slot
-__device__ __forceinline__ uint32_t lz2_insert_raw(ChunkCtx &c, uint32_t w, uint32_t kmask, int p)
+__device__ __forceinline__ uint32_t lz2_insert_raw(ChunkCtx &c, uint32_t w, uint32_t kmask, int p, int tbits = 13)
 {
-    uint32_t s = (w * LZ2_GOLD) >> (32 - 13);
+    const uint32_t tmask = (1u << tbits) - 1u;
+    uint32_t s = (w * LZ2_GOLD) >> (32 - tbits);
     const uint32_t val = ((uint32_t)p << 1) | 1u;
     for (;;) {
         const uint32_t q = atomicCAS(&c.T[s], LZ2_EMPTY, val);
@@ -60,7 +61,7 @@ __device__ __forceinline__ uint32_t lz2_insert_raw(ChunkCtx &c, uint32_t w, uint
             else if (q & 1u) atomicAnd(&c.T[s], ~1u);
             return s;
         }
-        s = (s + 1) & (LZ2_TSLOTS - 1);
+        s = (s + 1) & tmask;
     }
 }
 
@@ -93,6 +94,7 @@ __device__ inline int lz2_level4(ChunkCtx &c, uint16_t *D)
 {
     const int n = c.n, tid = threadIdx.x;
     lz2_clear(c, LZ2_TSLOTS);
+    if (tid == 0) c.red[30] = 0; // length of the level-3 candidate list
     __syncthreads();
     const int P = n - 3;
     for (int p = tid; p < n; p += AMBC_BLOCK) {
@@ -101,46 +103,67 @@ __device__ inline int lz2_level4(ChunkCtx &c, uint16_t *D)
         D[p] = (uint16_t)slot;
     }
     __syncthreads();
+    // resolve; the heads (no 4-byte match) are listed for the 3-byte level
+    uint16_t *list3 = (uint16_t *)c.L;
+    volatile int *cnt = c.red + 30;
+    const int lane = tid & 31;
     int nonhead = 0;
-    for (int p = tid; p < n; p += AMBC_BLOCK) {
-        const uint32_t slot = D[p];
-        uint32_t nm = (uint32_t)p;
-        if (slot != 0xFFFFu) nm = lz2_slot_name(c.T[slot]);
-        D[p] = (uint16_t)nm;
-        if ((nm & 0xFFFu) < (uint32_t)p) { c.mlen[p] = 4; c.mpos[p] = (uint16_t)(nm & 0xFFFu); nonhead = 1; }
+    for (int pb = 0; pb < n; pb += AMBC_BLOCK) {
+        const int p = pb + tid;
+        bool head3 = false;
+        if (p < n) {
+            const uint32_t slot = D[p];
+            uint32_t nm = (uint32_t)p;
+            if (slot != 0xFFFFu) nm = lz2_slot_name(c.T[slot]);
+            D[p] = (uint16_t)nm;
+            if ((nm & 0xFFFu) < (uint32_t)p) { c.mlen[p] = 4; c.mpos[p] = (uint16_t)(nm & 0xFFFu); nonhead = 1; }
+            else head3 = p + 3 <= n; // (positions past n - 4 are their own name)
+        }
+        const uint32_t m = __ballot_sync(FULL_MASK, head3);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd((int *)cnt, __popc(m));
+            base = __shfl_sync(FULL_MASK, base, 0);
+            if (head3) list3[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)p;
+        }
     }
     return __syncthreads_or(nonhead);
 }
 
-// matches of length exactly 3: only heads of name_4 can have one.  tmp: scratch names buffer.
-__device__ inline void lz2_level3(ChunkCtx &c, const uint16_t *N4, uint16_t *tmp)
+// matches of length exactly 3: only heads of name_4 can have one (listed by lz2_level4 in c.L).
+// tmp: scratch buffer for the slots.
+__device__ inline void lz2_level3(ChunkCtx &c, uint16_t *tmp)
 {
-    const int n = c.n, tid = threadIdx.x;
-    lz2_clear(c, LZ2_TSLOTS);
+    const int tid = threadIdx.x;
+    const uint16_t *list3 = (const uint16_t *)c.L;
+    const int cnt = c.red[30];
+    int tbits = 10; // table sized to the list (load factor <= 1/2)
+    while ((1 << tbits) < 2 * cnt && tbits < 13) tbits++;
+    lz2_clear(c, 1 << tbits);
     __syncthreads();
-    for (int p = tid; p < n; p += AMBC_BLOCK) {
-        uint32_t slot = 0xFFFFu;
-        if (p + 3 <= n && (N4[p] & 0xFFFu) == p) // (positions past n - 4 are their own name)
-            slot = lz2_insert_raw(c, lds_u32u(c.sd + p) & 0xFFFFFFu, 0xFFFFFFu, p);
-        tmp[p] = (uint16_t)slot;
+    for (int i = tid; i < cnt; i += AMBC_BLOCK) {
+        const int p = list3[i];
+        tmp[i] = (uint16_t)lz2_insert_raw(c, lds_u32u(c.sd + p) & 0xFFFFFFu, 0xFFFFFFu, p, tbits);
     }
     __syncthreads();
-    for (int p = tid; p < n; p += AMBC_BLOCK) {
-        const uint32_t slot = tmp[p];
-        if (slot != 0xFFFFu) {
-            const uint32_t nm = lz2_slot_pos(c.T[slot]);
-            if (nm < (uint32_t)p) { c.mlen[p] = 3; c.mpos[p] = (uint16_t)nm; }
-        }
+    for (int i = tid; i < cnt; i += AMBC_BLOCK) {
+        const int p = list3[i];
+        const uint32_t nm = lz2_slot_pos(c.T[tmp[i]]);
+        if (nm < (uint32_t)p) { c.mlen[p] = 3; c.mpos[p] = (uint16_t)nm; }
     }
     __syncthreads();
 }
 
 // name_2k (D) from name_k (S).  Positions whose k-gram at p or at p + k occurs nowhere else are
-// heads by construction and do not enter the table.  Returns "any match of 2k bytes".
+// heads by construction and do not enter the table.  Also lists the participants of the bracket
+// (k, 2k) in c.L: heads of their 2k-gram whose k-gram occurs elsewhere, with room for k+1 bytes
+// (count in c.red[30]).  Returns "any match of 2k bytes".
 __device__ inline int lz2_double(ChunkCtx &c, const uint16_t *S, uint16_t *D, int k)
 {
-    const int n = c.n, tid = threadIdx.x;
+    const int n = c.n, tid = threadIdx.x, lane = tid & 31;
     lz2_clear(c, LZ2_TSLOTS);
+    volatile int *cnt = c.red + 30;
+    if (tid == 0) *cnt = 0;
     __syncthreads();
     const int P = n - 2 * k + 1;
     int dummy = 0;
@@ -156,45 +179,34 @@ __device__ inline int lz2_double(ChunkCtx &c, const uint16_t *S, uint16_t *D, in
         D[p] = (uint16_t)slot;
     }
     __syncthreads();
+    uint16_t *plist = (uint16_t *)c.L;
+    const int Pmax = n - k - 1;
     int nonhead = 0;
-    for (int p = tid; p < n; p += AMBC_BLOCK) {
-        const uint32_t slot = D[p];
-        uint32_t nm = (uint32_t)p;
-        if (slot != 0xFFFFu) nm = lz2_slot_name(c.T[slot]);
-        D[p] = (uint16_t)nm;
-        if ((nm & 0xFFFu) < (uint32_t)p) {
-            c.mlen[p] = (uint8_t)(2 * k); c.mpos[p] = (uint16_t)(nm & 0xFFFu);
-            nonhead = 1;
+    for (int pb = 0; pb < n; pb += AMBC_BLOCK) {
+        const int p = pb + tid;
+        bool part = false;
+        if (p < n) {
+            const uint32_t slot = D[p];
+            uint32_t nm = (uint32_t)p;
+            if (slot != 0xFFFFu) nm = lz2_slot_name(c.T[slot]);
+            D[p] = (uint16_t)nm;
+            if ((nm & 0xFFFu) < (uint32_t)p) {
+                c.mlen[p] = (uint8_t)(2 * k); c.mpos[p] = (uint16_t)(nm & 0xFFFu);
+                nonhead = 1;
+            } else part = p <= Pmax && (S[p] & LZ2_NS);
+        }
+        const uint32_t m = __ballot_sync(FULL_MASK, part);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd((int *)cnt, __popc(m));
+            base = __shfl_sync(FULL_MASK, base, 0);
+            if (part) plist[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)p;
         }
     }
     return __syncthreads_or(nonhead);
 }
 
 // ---- lengths k+1 .. 2k-1 --------------------------------------------------------------------
-// participant list: heads of their 2k-gram whose k-gram occurs elsewhere, with room for k+1 bytes
-__device__ inline int lz2_participants(ChunkCtx &c, const uint16_t *S, const uint16_t *D, int k, uint16_t *plist, int cap)
-{
-    const int n = c.n, tid = threadIdx.x, lane = tid & 31;
-    volatile int *cnt = c.red + 30;
-    if (tid == 0) *cnt = 0;
-    __syncthreads();
-    const int Pmax = n - k - 1;
-    for (int p0 = 0; p0 <= Pmax; p0 += AMBC_BLOCK) {
-        const int p = p0 + tid;
-        const bool pred = p <= Pmax && (D[p] & 0xFFFu) == p && (S[p] & LZ2_NS);
-        const uint32_t m = __ballot_sync(FULL_MASK, pred);
-        if (m) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd((int *)cnt, __popc(m));
-            base = __shfl_sync(FULL_MASK, base, 0);
-            const int at = base + __popc(m & ((1u << lane) - 1));
-            if (pred && at < cap) plist[at] = (uint16_t)p;
-        }
-    }
-    __syncthreads();
-    return *cnt;
-}
-
 // every participant enters every length (np > LZ2_BIN_MAXP, and the fallback of the binary order)
 __device__ inline bool lz2_refine_flat(ChunkCtx &c, const uint16_t *S, int k, int np, const uint16_t *plist, uint16_t *islot)
 {
@@ -256,13 +268,12 @@ __device__ inline int lz2_refine_binary(ChunkCtx &c, const uint16_t *S, int k, i
     volatile int *ovf = c.red + 31;
     if (tid == 0) *ovf = 0;
     PHASE_DECL
-    for (int pi = tid; pi < np; pi += AMBC_BLOCK) { mem[pi] = 1; mem2[pi] = 0; }
+    int cntl = 0; // items of this thread in the coming round
+    for (int pi = tid; pi < np; pi += AMBC_BLOCK) { mem[pi] = 1; cntl++; }
     __syncthreads();
     PHASE(14);
     for (int step = k >> 1; step >= 1; step >>= 1) {
         // node t of this round: length k + (2t+1) * step inside the interval of half-width `step`
-        int cntl = 0;
-        for (int pi = tid; pi < np; pi += AMBC_BLOCK) cntl += __popc((uint32_t)mem[pi]);
         int E;
         const int base = block_excl_scan(cntl, c.red, &E);
         PHASE(15);
@@ -270,14 +281,21 @@ __device__ inline int lz2_refine_binary(ChunkCtx &c, const uint16_t *S, int k, i
         if (E == 0) return 0;
         int R = 1;
         while (R * LZ2_PART_TARGET < E) R <<= 1;
+        // table of this round: the smallest power of two with load factor <= 1/2 (fewer slots to clear)
+        int tbits = 10;
+        while ((1 << tbits) < 2 * E && tbits < 13) tbits++;
+        const uint32_t tmask = (1u << tbits) - 1u;
+        const int tshift = 32 - tbits;
+        cntl = 0;
         for (int r = 0; r < R; r++) {
-            lz2_clear(c, LZ2_RSLOTS);
+            lz2_clear(c, 1 << tbits);
             __syncthreads();
             PHASE(16);
             int overflow = 0, idx = base;
             for (int pi = tid; pi < np; pi += AMBC_BLOCK) {
-                const int p = plist[pi];
                 uint32_t m = mem[pi];
+                if (!m) continue;
+                const int p = plist[pi];
                 const uint32_t a = S[p];
                 while (m) {
                     const int t = __ffs(m) - 1;
@@ -290,7 +308,7 @@ __device__ inline int lz2_refine_binary(ChunkCtx &c, const uint16_t *S, int k, i
                             const uint32_t h = ((a | (b << 16)) + (uint32_t)t * 0x9E3779B9u) * LZ2_GOLD;
                             slot = 0xFFFFu;  // 0xFFFF: belongs to another partition pass
                             if (((h >> 16) & (uint32_t)(R - 1)) == (uint32_t)r)
-                                slot = lz2_insert_pair(c, LZ2_RSLOTS - 1, h >> LZ2_RSHIFT, S, a, b, p, j, (uint32_t)t, &overflow);
+                                slot = lz2_insert_pair(c, tmask, h >> tshift, S, a, b, p, j, (uint32_t)t, &overflow);
                         }
                     }
                     islot[idx++] = (uint16_t)slot;
@@ -301,8 +319,10 @@ __device__ inline int lz2_refine_binary(ChunkCtx &c, const uint16_t *S, int k, i
             PHASE(17);
             idx = base;
             for (int pi = tid; pi < np; pi += AMBC_BLOCK) {
+                uint32_t m = mem[pi];
+                if (!m) { if (r == 0) mem2[pi] = 0; continue; }
                 const int p = plist[pi];
-                uint32_t m = mem[pi], nm2 = mem2[pi];
+                uint32_t nm2 = r == 0 ? 0u : mem2[pi];
                 while (m) {
                     const int t = __ffs(m) - 1;
                     m &= m - 1;
@@ -318,27 +338,24 @@ __device__ inline int lz2_refine_binary(ChunkCtx &c, const uint16_t *S, int k, i
                     if (!(v & 1u)) nm2 |= 1u << (2 * t + 1);  // occurs elsewhere: lengths above m remain
                 }
                 mem2[pi] = (uint8_t)nm2;
+                if (r == R - 1) cntl += __popc(nm2 & 0xFFu);
             }
             __syncthreads();
             PHASE(18);
             if (*ovf) return -1;
         }
-        for (int pi = tid; pi < np; pi += AMBC_BLOCK) { mem[pi] = mem2[pi]; mem2[pi] = 0; }
-        __syncthreads();
-        PHASE(19);
+        uint8_t *tmp = mem; mem = mem2; mem2 = tmp; // the children masks are the next round's membership
     }
     return 0;
 }
 
 // S = name_k, D = name_2k.  Returns false on table overflow.
-__device__ inline bool lz2_refine(ChunkCtx &c, const uint16_t *S, const uint16_t *D, int k)
+__device__ inline bool lz2_refine(ChunkCtx &c, const uint16_t *S, int k)
 {
     // list memory: plist 8 KiB | islot 16 KiB | mem 4 KiB | mem2 4 KiB
     uint16_t *plist = (uint16_t *)c.L;
     uint16_t *islot = (uint16_t *)(c.L + 8192);
-    PHASE_DECL
-    const int np = lz2_participants(c, S, D, k, plist, LZ2_NMAX);
-    PHASE(20);
+    const int np = c.red[30]; // listed by lz2_double
     if (np == 0) return true;
     if (k >= LZ2_BIN_MINK) {
         const int rc = lz2_refine_binary(c, S, k, np, plist, c.L + 24576, c.L + 28672, islot);
@@ -357,22 +374,22 @@ __device__ inline bool lz2_match_all(ChunkCtx &c)
     PHASE_DECL // (dev-only phase timeline, see chunk_codec.cuh)
     const int any4 = lz2_level4(c, A);
     PHASE(2);
-    lz2_level3(c, A, B);
+    lz2_level3(c, B);
     PHASE(3);
     if (!any4) return true;
     const int any8 = lz2_double(c, A, B, 4);
     PHASE(4);
-    if (!lz2_refine(c, A, B, 4)) return false;
+    if (!lz2_refine(c, A, 4)) return false;
     PHASE(5);
     if (!any8) return true;
     const int any16 = lz2_double(c, B, A, 8);
     PHASE(6);
-    if (!lz2_refine(c, B, A, 8)) return false;
+    if (!lz2_refine(c, B, 8)) return false;
     PHASE(7);
     if (!any16) return true;
     lz2_double(c, A, B, 16);
     PHASE(8);
-    const bool ok = lz2_refine(c, A, B, 16);
+    const bool ok = lz2_refine(c, A, 16);
     PHASE(9);
     return ok;
 }
