@@ -252,10 +252,9 @@ __device__ inline void chunk_features(ChunkCtx &c, ChunkFeatures &f)
         int a = warp_sum(rep), b = warp_sum(small), d = warp_sum(ins);
         if (lane == 0) { redx[w] = a; redx[AMBC_WARPS + w] = b; redx[2 * AMBC_WARPS + w] = d; }
         __syncthreads();
-        int ra = 0, rb = 0, rd = 0;
-#pragma unroll
-        for (int i = 0; i < AMBC_WARPS; i++) { ra += redx[i]; rb += redx[AMBC_WARPS + i]; rd += redx[2 * AMBC_WARPS + i]; }
-        f.rep = ra; f.small = rb; f.distinct3 = rd;
+        f.rep = warp_sum(lane < AMBC_WARPS ? redx[lane] : 0);
+        f.small = warp_sum(lane < AMBC_WARPS ? redx[AMBC_WARPS + lane] : 0);
+        f.distinct3 = warp_sum(lane < AMBC_WARPS ? redx[2 * AMBC_WARPS + lane] : 0);
         __syncthreads();
     }
 
@@ -305,11 +304,12 @@ __device__ inline void chunk_features(ChunkCtx &c, ChunkFeatures &f)
         double *redd = (double *)(redx + 2 * AMBC_WARPS);
         if (lane == 0) { redx[w] = a; redx[AMBC_WARPS + w] = b; redd[w] = hsum; }
         __syncthreads();
-        int ra = 0, rb = 0;
         double rh = 0.0;
 #pragma unroll
-        for (int i = 0; i < AMBC_WARPS; i++) { ra += redx[i]; rb += redx[AMBC_WARPS + i]; rh += redd[i]; }
-        f.rle_pairs = ra; f.K = rb; f.H = rh;
+        for (int i = 0; i < AMBC_WARPS; i++) rh += redd[i]; // fixed order: the same sum in every thread
+        f.rle_pairs = warp_sum(lane < AMBC_WARPS ? redx[lane] : 0);
+        f.K = warp_sum(lane < AMBC_WARPS ? redx[AMBC_WARPS + lane] : 0);
+        f.H = rh;
         __syncthreads();
     }
     PHASE(26);

@@ -42,6 +42,10 @@ __device__ __forceinline__ int warp_sum(int v)
     return v;
 }
 
+// The per-warp partials of a block reduction are combined by every warp with a shuffle scan over
+// lanes 0 .. AMBC_WARPS-1 (a loop over the partials costs AMBC_WARPS loads per thread).
+static_assert(AMBC_WARPS <= 32, "one lane per warp partial");
+
 // block-wide exclusive scan (AMBC_BLOCK threads).  red: >= AMBC_WARPS ints of shared memory.
 // Contains two __syncthreads(); every thread of the block must call it.
 __device__ __forceinline__ int block_excl_scan(int v, volatile int *red, int *total)
@@ -51,14 +55,10 @@ __device__ __forceinline__ int block_excl_scan(int v, volatile int *red, int *to
     __syncthreads();
     if (lane == 31) red[w] = inc;
     __syncthreads();
-    int base = 0, tot = 0;
-#pragma unroll
-    for (int i = 0; i < AMBC_WARPS; i++) {
-        int x = red[i];
-        if (i < w) base += x;
-        tot += x;
-    }
-    *total = tot;
+    int x = lane < AMBC_WARPS ? red[lane] : 0;
+    int xs = warp_incl_scan(x);                          // inclusive prefix of the warp totals
+    *total = __shfl_sync(FULL_MASK, xs, AMBC_WARPS - 1);
+    int base = __shfl_sync(FULL_MASK, xs - x, w);        // sum of the warps before this one
     return base + inc - v;
 }
 
@@ -70,10 +70,7 @@ __device__ __forceinline__ int block_sum(int v, volatile int *red)
     __syncthreads();
     if (lane == 0) red[w] = v;
     __syncthreads();
-    int tot = 0;
-#pragma unroll
-    for (int i = 0; i < AMBC_WARPS; i++) tot += red[i];
-    return tot;
+    return warp_sum(lane < AMBC_WARPS ? red[lane] : 0);
 }
 
 __device__ __forceinline__ double block_sum_f64(double v, volatile double *red)
@@ -86,7 +83,7 @@ __device__ __forceinline__ double block_sum_f64(double v, volatile double *red)
     __syncthreads();
     double tot = 0.0;
 #pragma unroll
-    for (int i = 0; i < AMBC_WARPS; i++) tot += red[i];
+    for (int i = 0; i < AMBC_WARPS; i++) tot += red[i]; // fixed order: the same sum in every thread
     return tot;
 }
 
