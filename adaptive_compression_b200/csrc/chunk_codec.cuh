@@ -317,21 +317,36 @@ __device__ inline void chunk_features(ChunkCtx &c, ChunkFeatures &f)
 
 // first-occurrence order of the byte values (Counter insertion order, :368-370 / :566).
 // order[r] = r-th distinct byte value; firstpos scratch = 256 uint32.  Collective.
-// rank of key k among the 256 entries of keys[] (number of smaller entries), AMBC_BLOCK / 256
-// threads per key: thread tid serves key tid / RANK_TPK.  Warp-collective.
-#define RANK_TPK (AMBC_BLOCK / 256)
-static_assert(RANK_TPK == 1 || RANK_TPK == 2 || RANK_TPK == 4, "rank256 layout");
-template <class T>
-__device__ __forceinline__ int rank256(const T *keys, T k)
+// Ranks of the present entries of keys[256] (absent = 0xFFFFFFFF, present keys distinct): the
+// present keys are compacted first, so the all-pairs compare costs K^2 instead of 256^2.
+// emit(rank, symbol, key) runs once per present entry.  Scratch (see huff_scratch): ck[256],
+// cs[256], cw[8].  Block-collective, three __syncthreads().  Returns K.
+template <class F>
+__device__ __forceinline__ int rank_present(const uint32_t *keys, uint32_t *ck, uint8_t *cs, int *cw, F emit)
 {
-    const int part = threadIdx.x % RANK_TPK;
-    constexpr int SPAN = 256 / RANK_TPK;
-    int r = 0;
-#pragma unroll 8
-    for (int j = part * SPAN; j < (part + 1) * SPAN; j++) r += (keys[j] < k);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    uint32_t key = 0xFFFFFFFFu;
+    if (tid < 256) key = keys[tid];
+    const uint32_t m = __ballot_sync(FULL_MASK, key != 0xFFFFFFFFu);
+    if (tid < 256 && lane == 0) cw[w] = __popc(m);
+    __syncthreads();
+    int base = 0, K = 0;
 #pragma unroll
-    for (int d = 1; d < RANK_TPK; d <<= 1) r += __shfl_xor_sync(FULL_MASK, r, d);
-    return r;
+    for (int i = 0; i < 8; i++) { const int x = cw[i]; if (i < w) base += x; K += x; }
+    if (key != 0xFFFFFFFFu) {
+        const int at = base + __popc(m & ((1u << lane) - 1));
+        ck[at] = key;
+        cs[at] = (uint8_t)tid;
+    }
+    __syncthreads();
+    if (tid < K) {
+        const uint32_t k = ck[tid];
+        int r = 0;
+        for (int j = 0; j < K; j++) r += (ck[j] < k);
+        emit(r, (int)cs[tid], k);
+    }
+    __syncthreads();
+    return K;
 }
 
 __device__ inline void chunk_first_order(ChunkCtx &c, uint32_t *firstpos, uint8_t *order)
@@ -353,13 +368,8 @@ __device__ inline void chunk_first_order(ChunkCtx &c, uint32_t *firstpos, uint8_
         }
     }
     __syncthreads();
-    {
-        const int b = tid / RANK_TPK;
-        const uint32_t fp = firstpos[b];
-        const int r = rank256(firstpos, fp);
-        if (fp != 0xFFFFFFFFu && tid % RANK_TPK == 0) order[r] = (uint8_t)b;
-    }
-    __syncthreads();
+    rank_present(firstpos, (uint32_t *)(c.X + 3072), c.X + 8448, (int *)(c.X + 8704),
+                 [&](int r, int sym, uint32_t) { order[r] = (uint8_t)sym; });
 }
 
 // exact Python-order entropy: e -= p*log2(p) over the Counter's insertion order, no FMA
@@ -904,15 +914,9 @@ __device__ inline int chunk_huff_build(ChunkCtx &c, HuffScratch &h, int K)
         h.codeOf[b] = 0;
     }
     __syncthreads();
-    {   // rank sort: keys are distinct
-        const int b = tid / RANK_TPK;
-        const uint32_t k = h.key[b];
-        const int r = rank256(h.key, k);
-        if (k != 0xFFFFFFFFu && tid % RANK_TPK == 0) {
-            h.nodeW[r] = k; // (weight << 8 | leader): one word orders nodes by (weight, leader)
-            h.leafsym[r] = (uint8_t)b;
-        }
-    }
+    // rank sort: keys are distinct; one word (weight << 8 | leader) orders nodes by (weight, leader)
+    rank_present(h.key, (uint32_t *)(c.X + 3072), c.X + 8448, (int *)(c.X + 8704),
+                 [&](int r, int sym, uint32_t k) { h.nodeW[r] = k; h.leafsym[r] = (uint8_t)sym; });
     __syncthreads();
     PHASE(31);
     if (tid == 0) {
