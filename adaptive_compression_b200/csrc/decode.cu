@@ -266,14 +266,30 @@ int ambc_decode_launch(const void *body_dev, const ambc_pkg *table_dev, uint64_t
         CUDA_TRY(cudaFuncSetAttribute(k_decode_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
         attr_done = true;
     }
+    // the two decoders touch disjoint packages: k_decode_lz runs on a side stream, forked from and
+    // joined back into the caller's stream
+    static cudaStream_t side[16] = {};
+    static cudaEvent_t ev_fork[16] = {}, ev_join[16] = {};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) return ambc_fail(AMBC_E_ARG, "device index out of range");
+    if (!side[dev]) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventRecord(ev_fork[dev], stream));
+    CUDA_TRY(cudaStreamWaitEvent(side[dev], ev_fork[dev], 0));
+    unsigned lgrid = (unsigned)min<uint64_t>((n_entries + DLZ_WARPS - 1) / DLZ_WARPS, 148ull * 24);
+    k_decode_lz<<<lgrid, DLZ_WARPS * 32, lsmem, side[dev]>>>((const uint8_t *)body_dev, table_dev, n_entries,
+                                                            (uint8_t *)out_dev, status_dev);
+    ambc_count_launch();
+    CUDA_TRY(cudaEventRecord(ev_join[dev], side[dev]));
     unsigned grid = (unsigned)min<uint64_t>(n_entries, 0x7fffffffull);
     k_decode<<<grid, AMBC_BLOCK, smem, stream>>>((const uint8_t *)body_dev, table_dev, n_entries, (uint8_t *)out_dev,
                                                  in_cap, status_dev);
     ambc_count_launch();
-    unsigned lgrid = (unsigned)min<uint64_t>((n_entries + DLZ_WARPS - 1) / DLZ_WARPS, 148ull * 24);
-    k_decode_lz<<<lgrid, DLZ_WARPS * 32, lsmem, stream>>>((const uint8_t *)body_dev, table_dev, n_entries,
-                                                         (uint8_t *)out_dev, status_dev);
-    ambc_count_launch();
+    CUDA_TRY(cudaStreamWaitEvent(stream, ev_join[dev], 0));
     CUDA_TRY(cudaGetLastError());
     return AMBC_OK;
 }
