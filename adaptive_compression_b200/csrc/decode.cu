@@ -182,7 +182,10 @@ __device__ int decode_package(DecCtx &d, uint32_t type, const uint8_t *__restric
     return r;
 }
 
-__global__ void __launch_bounds__(AMBC_BLOCK)
+#ifndef KDEC_MINB
+#define KDEC_MINB 6
+#endif
+__global__ void __launch_bounds__(AMBC_BLOCK, KDEC_MINB)
 k_decode(const uint8_t *__restrict__ body, const ambc_pkg *__restrict__ table, uint64_t n_entries,
          uint8_t *__restrict__ out, int in_cap, uint32_t *status)
 {

@@ -14,6 +14,9 @@
 #define DEC_OUT_CAP 8192      // largest orig_len decoded in shared memory
 #define DEC_OUT_SLACK 512     // LZ may overrun orig_len by one match (<= 255 bytes) before truncation
 #define DEC_LUT_BITS 10
+#ifndef DEC_SHORT_CODE_BITS
+#define DEC_SHORT_CODE_BITS 6   // alphabets whose codes all fit: near-fixed-length codes, decoded for all entry offsets
+#endif
 
 struct DecCtx {
     uint8_t *in;   // staged payload, 16-byte aligned, in_cap + 16 bytes
@@ -301,6 +304,7 @@ struct HuffDec {
     uint32_t *start;           // [AMBC_BLOCK + 4] subsequence start bits (overlays key)
     uint32_t *cnt;             // [AMBC_BLOCK] symbols per subsequence (overlays firstidx)
     int K, root;
+    int short_codes; // no code is longer than DEC_SHORT_CODE_BITS
 };
 __device__ inline HuffDec huffdec_scratch(uint8_t *X) // needs 12288 bytes
 {
@@ -316,7 +320,7 @@ __device__ inline HuffDec huffdec_scratch(uint8_t *X) // needs 12288 bytes
     h.start = (uint32_t *)(X + 4096);
     h.cnt = (uint32_t *)(X + 11264); // firstidx is dead once the tree is built
     static_assert(4 * (AMBC_BLOCK + 4) <= 2048 && 4 * AMBC_BLOCK <= 1024, "Huffman decode scratch layout");
-    h.K = 0; h.root = 0;
+    h.K = 0; h.root = 0; h.short_codes = 0;
     return h;
 }
 
@@ -380,13 +384,29 @@ __device__ inline int huffdec_build(DecCtx &d, HuffDec &h, const uint8_t *in, in
     const int K = block_sum(present, d.red);
     h.K = K;
     if (K <= 1) return -1; // heappop on an empty heap / code[-1] of an empty code (:497, :527)
-    for (int b = tid; b < 256; b += AMBC_BLOCK) {
-        unsigned long long k = h.key[b];
-        if (k != ~0ull) {
-            int r = 0;
-            for (int j = 0; j < 256; j++) r += (h.key[j] < k);
-            h.nodeW[r] = k >> 8;
-            h.lead[r] = (uint16_t)b;
+    {   // rank sort over the K present keys only (compacted into nodeW[256..512), dead until the merge)
+        unsigned long long *ck = h.nodeW + 256;
+        volatile int *cw = d.red + 16;
+        const int lane = tid & 31, w = tid >> 5;
+        unsigned long long key = ~0ull;
+        if (tid < 256) key = h.key[tid];
+        const uint32_t m = __ballot_sync(FULL_MASK, key != ~0ull);
+        if (tid < 256 && lane == 0) cw[w] = __popc(m);
+        __syncthreads();
+        int base = 0;
+        for (int i = 0; i < w && i < 8; i++) base += cw[i];
+        if (key != ~0ull) ck[base + __popc(m & ((1u << lane) - 1))] = key;
+        __syncthreads();
+        unsigned long long mine = ~0ull;
+        int r = 0;
+        if (tid < K) {
+            mine = ck[tid];
+            for (int j = 0; j < K; j++) r += (ck[j] < mine);
+        }
+        __syncthreads(); // ck aliases nodeW[256..): all ranks are computed before anything is written
+        if (tid < K) {
+            h.nodeW[r] = mine >> 8;
+            h.lead[r] = (uint16_t)(mine & 0xFF);
         }
     }
     __syncthreads();
@@ -413,6 +433,7 @@ __device__ inline int huffdec_build(DecCtx &d, HuffDec &h, const uint8_t *in, in
     }
     __syncthreads();
     h.root = 2 * K - 2;
+    int longc = 0;
     for (int idx = tid; idx < (1 << DEC_LUT_BITS); idx += AMBC_BLOCK) {
         int node = h.root, l = 0;
         while (node >= K && l < DEC_LUT_BITS) {
@@ -421,7 +442,9 @@ __device__ inline int huffdec_build(DecCtx &d, HuffDec &h, const uint8_t *in, in
             l++;
         }
         h.lut[idx] = node < K ? (uint16_t)(0x8000u | (l << 8) | h.lead[node]) : (uint16_t)node;
+        if (node >= K || l > DEC_SHORT_CODE_BITS) longc = 1;
     }
+    h.short_codes = !__syncthreads_or(longc);
     int off = 1 + 5 * ne;
     uint32_t nb = 0;
     for (int t = 0; t < 4; t++) if (off + t < len) nb |= (uint32_t)in[off + t] << (8 * t);
@@ -431,6 +454,81 @@ __device__ inline int huffdec_build(DecCtx &d, HuffDec &h, const uint8_t *in, in
     *nbits = nb < avail ? nb : avail;
     __syncthreads();
     return 0;
+}
+
+// Codes of at most E <= 8 bits (small alphabets): near-fixed-length codes never re-synchronise, so
+// instead of iterating, every thread decodes its bit segment for EVERY entry offset 0..E-1 (entries
+// whose first code stays below E chain into an entry already computed), the true entry offsets are
+// composed across segments, and a last pass decodes from them.  Returns symbols produced.  Collective.
+__device__ inline int dec_huff_short_codes(DecCtx &d, HuffDec &h, const uint8_t *bits, uint32_t nbits, int orig, int E)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint8_t *xo = (uint8_t *)h.nodeW;           // [AMBC_BLOCK][8] exit offset into the next segment, 0xFF = stream ended
+    uint8_t *cn = xo + AMBC_BLOCK * 8;          // [AMBC_BLOCK][8] symbols decoded
+    uint8_t *ent = cn + AMBC_BLOCK * 8;         // [AMBC_BLOCK] true entry offset of each segment (0xFF: none)
+    uint8_t *gx = ent + AMBC_BLOCK;             // [AMBC_WARPS][8] exits of groups of 32 segments
+    uint8_t *ge = gx + AMBC_WARPS * 8;          // [AMBC_WARPS] entry offset of each group
+    static_assert(AMBC_BLOCK * 17 + AMBC_WARPS * 9 <= 4096 + 2048, "short-code tables overlay nodeW + key");
+    const uint32_t S = max(32u, (nbits + AMBC_BLOCK - 1) / AMBC_BLOCK);
+    const uint32_t seg0 = (uint32_t)tid * S;
+    const uint32_t lim = min(nbits, seg0 + S);
+    for (int e = E - 1; e >= 0; e--) {
+        uint32_t pos = seg0 + (uint32_t)e;
+        uint32_t x = 0xFFu, c = 0;
+        if (pos < lim) {
+            int l;
+            huff_next(h, bits, pos, nbits, &l);
+            if (l == 0) x = 0xFFu;                                   // incomplete tail code: nothing more decodes
+            else if (e + l < E && pos + (uint32_t)l < lim) { x = xo[tid * 8 + e + l]; c = (uint32_t)cn[tid * 8 + e + l] + 1u; }
+            else {
+                pos += (uint32_t)l; c = 1;
+                while (pos < lim) {
+                    huff_next(h, bits, pos, nbits, &l);
+                    if (l == 0) { pos = nbits; break; }
+                    pos += (uint32_t)l; c++;
+                }
+                x = pos >= nbits ? 0xFFu : pos - lim;
+            }
+        } else if (seg0 + (uint32_t)e < nbits) x = 0xFFu; // (cannot happen: S >= E)
+        xo[tid * 8 + e] = (uint8_t)x;
+        cn[tid * 8 + e] = (uint8_t)c;
+    }
+    __syncthreads();
+    // true entry offsets: groups of 32 segments composed for all entry offsets, groups chained, groups walked
+    if (lane < E) {
+        uint32_t x = (uint32_t)lane;
+        for (int sgm = 32 * wid; sgm < 32 * wid + 32; sgm++)
+            if (x != 0xFFu) x = xo[sgm * 8 + x];
+        gx[wid * 8 + lane] = (uint8_t)x;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t x = 0;
+        for (int g = 0; g < AMBC_WARPS; g++) { ge[g] = (uint8_t)x; if (x != 0xFFu) x = gx[g * 8 + x]; }
+    }
+    __syncthreads();
+    if (tid < AMBC_WARPS) {
+        uint32_t x = ge[tid];
+        for (int sgm = 32 * tid; sgm < 32 * tid + 32; sgm++) { ent[sgm] = (uint8_t)x; if (x != 0xFFu) x = xo[sgm * 8 + x]; }
+    }
+    __syncthreads();
+    const uint32_t en = ent[tid];
+    const int mine = en == 0xFFu ? 0 : (int)cn[tid * 8 + en];
+    int total;
+    int o = block_excl_scan(mine, d.red, &total);
+    const int limit = max(orig, 1); // stops after the append that reaches orig_len (:464-468)
+    if (en != 0xFFu) {
+        uint32_t pos = seg0 + en;
+        while (pos < lim && o < limit) {
+            int l;
+            const int sym = huff_next(h, bits, pos, nbits, &l);
+            if (l == 0) break;
+            if (o < DEC_OUT_CAP + DEC_OUT_SLACK) d.out[o] = (uint8_t)sym;
+            pos += (uint32_t)l; o++;
+        }
+    }
+    __syncthreads();
+    return min(total, limit);
 }
 
 // Fast path: payload in d.in[0..len) (zero padded 16 bytes), output to d.out.  Self-synchronising
@@ -446,6 +544,9 @@ __device__ inline int dec_huff(DecCtx &d, int len, int orig)
     if (huffdec_build(d, h, d.in, len, &boff, &nbits) < 0) return -1;
     const uint8_t *bits = d.in + boff;
     uint32_t *start = h.start, *cnt = h.cnt;
+    // every code fits DEC_SHORT_CODE_BITS (small alphabet): all-entry-offsets decode
+    // (segments of at most 255 bits keep the per-entry symbol counts within a byte)
+    if (h.short_codes && nbits > 0 && nbits <= 255u * AMBC_BLOCK) return dec_huff_short_codes(d, h, bits, nbits, orig, DEC_SHORT_CODE_BITS);
     const uint32_t S = max(32u, (nbits + AMBC_BLOCK - 1) / AMBC_BLOCK);
     if (tid == 0) start[0] = 0;
     start[tid + 1] = min(nbits, (uint32_t)(tid + 1) * S); // provisional
