@@ -349,21 +349,123 @@ __device__ inline int lz2_refine_binary(ChunkCtx &c, const uint16_t *S, int k, i
     return 0;
 }
 
-// S = name_k, D = name_2k.  Returns false on table overflow.
-__device__ inline bool lz2_refine(ChunkCtx &c, const uint16_t *S, int k)
+// Binary-search order with dense item lists.  An item = (node t << 12 | position): participant at
+// node t of the current round.  Round 1's list is the participant list itself (t = 0); the resolve
+// pass of a round appends the children items of the next round (left child 2t: the participant is a
+// head at this length; right child 2t+1: the gram occurs elsewhere), so every pass runs over a dense
+// list with one item per lane.  A participant matches at most once per round (a head at the common
+// ancestor length cannot match above it), so mlen / mpos are written without atomics.
+// Returns 0 = done, 1 = a list would overflow (caller rebuilds the participant list and runs the flat
+// method).  Lists: three arrays of LZ2_LISTCAP items in c.L.
+#define LZ2_LISTCAP 5461
+__device__ inline int lz2_refine_binary_dense(ChunkCtx &c, const uint16_t *S, int k, int np)
 {
-    // list memory: plist 8 KiB | islot 16 KiB | mem 4 KiB | mem2 4 KiB
-    uint16_t *plist = (uint16_t *)c.L;
-    uint16_t *islot = (uint16_t *)(c.L + 8192);
+    const int n = c.n, tid = threadIdx.x, lane = tid & 31;
+    uint16_t *A = (uint16_t *)c.L, *B = A + LZ2_LISTCAP, *islot = B + LZ2_LISTCAP;
+    volatile int *cntB = c.red + 29;
+    int E = np, dummy = 0;
+    PHASE_DECL
+    for (int step = k >> 1; step >= 1; step >>= 1) {
+        if (E == 0) return 0;
+        // table of this round: the smallest power of two with load factor <= 1/2 (E < slot count always)
+        int tbits = 10;
+        while ((1 << tbits) < 2 * E && tbits < 13) tbits++;
+        const uint32_t tmask = (1u << tbits) - 1u;
+        const int tshift = 32 - tbits;
+        lz2_clear(c, 1 << tbits);
+        if (tid == 0) *cntB = 0;
+        __syncthreads();
+        PHASE(16);
+        for (int i = tid; i < E; i += AMBC_BLOCK) {
+            const uint32_t item = A[i];
+            const int p = item & 0xFFFu, t = item >> 12;
+            const int j = (2 * t + 1) * step;
+            uint32_t slot = 0xFFFEu; // 0xFFFE: unique by construction (head, no follower)
+            if (p + k + j <= n) {
+                const uint32_t a = S[p], b = S[p + j];
+                if (b & LZ2_NS) {
+                    const uint32_t h = ((a | (b << 16)) + (uint32_t)t * 0x9E3779B9u) * LZ2_GOLD;
+                    slot = lz2_insert_pair(c, tmask, h >> tshift, S, a, b, p, j, (uint32_t)t, &dummy);
+                }
+            }
+            islot[i] = (uint16_t)slot;
+        }
+        __syncthreads();
+        PHASE(17);
+        bool overflow = false;
+        for (int ib = 0; ib < E; ib += AMBC_BLOCK) {
+            const int i = ib + tid;
+            bool left = false, right = false;
+            uint32_t p = 0, t = 0;
+            if (i < E) {
+                const uint32_t item = A[i];
+                p = item & 0xFFFu; t = item >> 12;
+                const uint32_t slot = islot[i];
+                if (slot == 0xFFFEu) left = true;
+                else {
+                    const uint32_t v = c.T[slot];
+                    const uint32_t nm = lz2_slot_pos(v);
+                    if (nm < p) {
+                        const int L = k + (2 * (int)t + 1) * step;
+                        if (L > (int)c.mlen[p]) { c.mlen[p] = (uint8_t)L; c.mpos[p] = (uint16_t)nm; }
+                    } else left = true;      // head at this length: the lengths below remain
+                    right = !(v & 1u);       // occurs elsewhere: the lengths above remain
+                }
+            }
+            if (step > 1) {
+                const uint32_t ml = __ballot_sync(FULL_MASK, left), mr = __ballot_sync(FULL_MASK, right);
+                const int nl = __popc(ml), nr = __popc(mr);
+                if (nl + nr) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd((int *)cntB, nl + nr);
+                    base = __shfl_sync(FULL_MASK, base, 0);
+                    const uint32_t below = (1u << lane) - 1u;
+                    if (base + nl + nr <= LZ2_LISTCAP) {
+                        if (left) B[base + __popc(ml & below)] = (uint16_t)(((2u * t) << 12) | p);
+                        if (right) B[base + nl + __popc(mr & below)] = (uint16_t)(((2u * t + 1u) << 12) | p);
+                    } else overflow = true;
+                }
+            }
+        }
+        const int ov = __syncthreads_or(overflow);
+        PHASE(18);
+        if (ov) return 1;
+        E = *cntB;
+        __syncthreads(); // everybody has read the count before it is reset
+        uint16_t *tmp = A; A = B; B = tmp;
+    }
+    return 0;
+}
+
+// S = name_k, D = name_2k.  Returns false on table overflow.
+__device__ inline bool lz2_refine(ChunkCtx &c, const uint16_t *S, const uint16_t *D, int k)
+{
     const int np = c.red[30]; // listed by lz2_double
     if (np == 0) return true;
-    if (k >= LZ2_BIN_MINK) {
-        const int rc = lz2_refine_binary(c, S, k, np, plist, c.L + 24576, c.L + 28672, islot);
-        if (rc == 0) return true;
-        if (rc < 0) return false;
+    uint16_t *plist = (uint16_t *)c.L;
+    if (k >= LZ2_BIN_MINK && np <= LZ2_LISTCAP) {
+        if (lz2_refine_binary_dense(c, S, k, np) == 0) return true;
+        // (rare) the item lists outgrew their memory: list the participants again, every length below
+        const int n = c.n, tid = threadIdx.x, lane = tid & 31;
+        volatile int *cnt = c.red + 30;
+        __syncthreads();
+        if (tid == 0) *cnt = 0;
+        __syncthreads();
+        for (int pb = 0; pb < n; pb += AMBC_BLOCK) {
+            const int p = pb + tid;
+            const bool part = p <= n - k - 1 && (D[p] & 0xFFFu) == (uint32_t)p && (S[p] & LZ2_NS);
+            const uint32_t m = __ballot_sync(FULL_MASK, part);
+            if (m) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd((int *)cnt, __popc(m));
+                base = __shfl_sync(FULL_MASK, base, 0);
+                if (part) plist[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)p;
+            }
+        }
         __syncthreads();
     }
-    return lz2_refine_flat(c, S, k, np, plist, islot);
+    // flat method: plist 8 KiB | islot 16 KiB
+    return lz2_refine_flat(c, S, k, c.red[30], plist, (uint16_t *)(c.L + 8192));
 }
 
 // mlen / mpos for every position of the chunk (c.mlen zeroed by the caller).  n <= LZ2_NMAX.
@@ -379,17 +481,17 @@ __device__ inline bool lz2_match_all(ChunkCtx &c)
     if (!any4) return true;
     const int any8 = lz2_double(c, A, B, 4);
     PHASE(4);
-    if (!lz2_refine(c, A, 4)) return false;
+    if (!lz2_refine(c, A, B, 4)) return false;
     PHASE(5);
     if (!any8) return true;
     const int any16 = lz2_double(c, B, A, 8);
     PHASE(6);
-    if (!lz2_refine(c, B, 8)) return false;
+    if (!lz2_refine(c, B, A, 8)) return false;
     PHASE(7);
     if (!any16) return true;
     lz2_double(c, A, B, 16);
     PHASE(8);
-    const bool ok = lz2_refine(c, A, 16);
+    const bool ok = lz2_refine(c, A, B, 16);
     PHASE(9);
     return ok;
 }
