@@ -33,7 +33,7 @@
 #define LZ2_PART_TARGET 4096     // entries per refinement pass (load factor 1/2; measured best of 2048..4096)
 #endif
 #ifndef LZ2_BIN_MINK
-#define LZ2_BIN_MINK 8           // smallest bracket refined in binary-search order
+#define LZ2_BIN_MINK 4           // smallest bracket refined in binary-search order (8: the (4,8) bracket uses the flat method)
 #endif
 #define LZ2_ISLOTS 8192          // slot memo entries
 
