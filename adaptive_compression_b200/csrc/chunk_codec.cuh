@@ -46,15 +46,13 @@ struct ChunkCtx {
     uint32_t *T;       // LZ2_TSLOTS hash slots (32 KiB)
     uint16_t *nameA;   // LZ2_NMAX first-occurrence names (two buffers, alternating levels)
     uint16_t *nameB;
-    uint8_t *L;        // LZ2_LBYTES of list memory: participant list | slot memo | node-membership masks
-    uint32_t *wq;      // per-warp staging queues, 64 entries x 2 words each
+    uint8_t *L;        // LZ2_LBYTES of list memory: participant / item lists and the slot memo
 };
 
 #define LZ2_NMAX 4096
 #define LZ2_TSLOTS 8192
 #define LZ2_LBYTES 32768
-#define LZ2_QBYTES (AMBC_WARPS * 512)
-#define LZ2_BYTES (LZ2_TSLOTS * 4 + 2 * LZ2_NMAX * 2 + LZ2_LBYTES + LZ2_QBYTES)
+#define LZ2_BYTES (LZ2_TSLOTS * 4 + 2 * LZ2_NMAX * 2 + LZ2_LBYTES)
 
 // scratch region X: LZ per-warp bucket counters, or 16 KiB for the other users
 #define AMBC_XBYTES ((AMBC_WARPS * AMBC_NBUCKET * 2) > 16384 ? (AMBC_WARPS * AMBC_NBUCKET * 2) : 16384)
@@ -103,8 +101,7 @@ __device__ inline void chunkctx_carve(ChunkCtx &c, uint8_t *base, int N, int pca
     c.T = (uint32_t *)p; p += LZ2_TSLOTS * 4;
     c.nameA = (uint16_t *)p; p += LZ2_NMAX * 2;
     c.nameB = (uint16_t *)p; p += LZ2_NMAX * 2;
-    c.L = p; p += LZ2_LBYTES;
-    c.wq = (uint32_t *)p;
+    c.L = p;
     c.pcap = pcap;
     c.n = 0;
 }
@@ -116,7 +113,7 @@ __device__ inline void chunkctx_carve(ChunkCtx &c, uint8_t *base, int N, int pca
 __host__ __device__ inline size_t chunkctx_fast_smem_bytes(int N)
 {
     size_t nb = (size_t)(N + 31) / 32;
-    return r16((size_t)N) + AMBC_PAD + LZ2_TSLOTS * 4 + 2 * LZ2_NMAX * 2 + LZ2_LBYTES + LZ2_QBYTES
+    return r16((size_t)N) + AMBC_PAD + LZ2_TSLOTS * 4 + 2 * LZ2_NMAX * 2 + LZ2_LBYTES
            + r16((size_t)N) + r16(2 * (size_t)N) + 1024 + r16(nb * 4) * 2 + r16(nb) + 128;
 }
 __device__ inline void chunkctx_carve_fast(ChunkCtx &c, uint8_t *base, int N)
@@ -136,7 +133,6 @@ __device__ inline void chunkctx_carve_fast(ChunkCtx &c, uint8_t *base, int N)
     c.nameA = (uint16_t *)p; p += LZ2_NMAX * 2;
     c.nameB = (uint16_t *)p; p += LZ2_NMAX * 2;
     c.L = p; p += LZ2_LBYTES;
-    c.wq = (uint32_t *)p; p += LZ2_QBYTES;
     c.mlen = p; p += r16((size_t)N);
     c.mpos = (uint16_t *)p; p += r16(2 * (size_t)N);
     c.hist = (uint32_t *)p; p += 1024;

@@ -16,7 +16,8 @@
 //               >= 2k bytes or no k-byte match at all).  The lengths of a bracket are visited in
 //               binary-search order; a participant enters length m of the interval (lo, hi) only
 //               if it is a head at hi and its lo-gram occurs elsewhere -- the first occurrence of
-//               any m-gram that somebody matches always satisfies both.
+//               any m-gram that somebody matches always satisfies both.  Every round runs over a
+//               dense item list that the previous round's resolve pass appended.
 // Every "first occurrence of a key" is one open-addressing insert with atomicMin on the position;
 // a later arrival at a key clears the slot's `single` bit ("this gram occurs more than once").
 // Keys are verified through the name arrays, so the result is exact for any hash function.
@@ -258,95 +259,6 @@ __device__ inline bool lz2_refine_flat(ChunkCtx &c, const uint16_t *S, int k, in
         }
     }
     return true;
-}
-
-// binary-search order over the lengths of the bracket; returns 0 = done, 1 = use the flat method, -1 = overflow
-__device__ inline int lz2_refine_binary(ChunkCtx &c, const uint16_t *S, int k, int np, const uint16_t *plist,
-                                        uint8_t *mem, uint8_t *mem2, uint16_t *islot)
-{
-    const int n = c.n, tid = threadIdx.x;
-    volatile int *ovf = c.red + 31;
-    if (tid == 0) *ovf = 0;
-    PHASE_DECL
-    int cntl = 0; // items of this thread in the coming round
-    for (int pi = tid; pi < np; pi += AMBC_BLOCK) { mem[pi] = 1; cntl++; }
-    __syncthreads();
-    PHASE(14);
-    for (int step = k >> 1; step >= 1; step >>= 1) {
-        // node t of this round: length k + (2t+1) * step inside the interval of half-width `step`
-        int E;
-        const int base = block_excl_scan(cntl, c.red, &E);
-        PHASE(15);
-        if (E >= LZ2_ISLOTS) return 1; // (strictly below the slot count: a probe always ends at a free slot)
-        if (E == 0) return 0;
-        int R = 1;
-        while (R * LZ2_PART_TARGET < E) R <<= 1;
-        // table of this round: the smallest power of two with load factor <= 1/2 (fewer slots to clear)
-        int tbits = 10;
-        while ((1 << tbits) < 2 * E && tbits < 13) tbits++;
-        const uint32_t tmask = (1u << tbits) - 1u;
-        const int tshift = 32 - tbits;
-        cntl = 0;
-        for (int r = 0; r < R; r++) {
-            lz2_clear(c, 1 << tbits);
-            __syncthreads();
-            PHASE(16);
-            int overflow = 0, idx = base;
-            for (int pi = tid; pi < np; pi += AMBC_BLOCK) {
-                uint32_t m = mem[pi];
-                if (!m) continue;
-                const int p = plist[pi];
-                const uint32_t a = S[p];
-                while (m) {
-                    const int t = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int j = (2 * t + 1) * step;
-                    uint32_t slot = 0xFFFEu; // 0xFFFE: unique by construction (head, no follower)
-                    if (p + k + j <= n) {
-                        const uint32_t b = S[p + j];
-                        if (b & LZ2_NS) {
-                            const uint32_t h = ((a | (b << 16)) + (uint32_t)t * 0x9E3779B9u) * LZ2_GOLD;
-                            slot = 0xFFFFu;  // 0xFFFF: belongs to another partition pass
-                            if (((h >> 16) & (uint32_t)(R - 1)) == (uint32_t)r)
-                                slot = lz2_insert_pair(c, tmask, h >> tshift, S, a, b, p, j, (uint32_t)t, &overflow);
-                        }
-                    }
-                    islot[idx++] = (uint16_t)slot;
-                }
-            }
-            if (overflow) *ovf = 1;
-            __syncthreads();
-            PHASE(17);
-            idx = base;
-            for (int pi = tid; pi < np; pi += AMBC_BLOCK) {
-                uint32_t m = mem[pi];
-                if (!m) { if (r == 0) mem2[pi] = 0; continue; }
-                const int p = plist[pi];
-                uint32_t nm2 = r == 0 ? 0u : mem2[pi];
-                while (m) {
-                    const int t = __ffs(m) - 1;
-                    m &= m - 1;
-                    const uint32_t slot = islot[idx++];
-                    if (slot == 0xFFFFu) continue;
-                    if (slot == 0xFFFEu) { if (r == 0) nm2 |= 1u << (2 * t); continue; }
-                    const uint32_t v = c.T[slot];
-                    const uint32_t nm = lz2_slot_pos(v);
-                    if (nm < (uint32_t)p) {
-                        const int L = k + (2 * t + 1) * step;
-                        if (L > (int)c.mlen[p]) { c.mlen[p] = (uint8_t)L; c.mpos[p] = (uint16_t)nm; }
-                    } else nm2 |= 1u << (2 * t);               // head at m: lengths below m remain
-                    if (!(v & 1u)) nm2 |= 1u << (2 * t + 1);  // occurs elsewhere: lengths above m remain
-                }
-                mem2[pi] = (uint8_t)nm2;
-                if (r == R - 1) cntl += __popc(nm2 & 0xFFu);
-            }
-            __syncthreads();
-            PHASE(18);
-            if (*ovf) return -1;
-        }
-        uint8_t *tmp = mem; mem = mem2; mem2 = tmp; // the children masks are the next round's membership
-    }
-    return 0;
 }
 
 // Binary-search order with dense item lists.  An item = (node t << 12 | position): participant at
