@@ -205,6 +205,9 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL prints its version banner to stdout at VERSION level; stdout carries the one JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = engine.require_cuda()
     n = args.size_mib << 20
@@ -368,7 +371,7 @@ def run_b200(args):
                                     "sample": "first %d MiB of the same corpus, one pass; C restatement of the reference "
                                               "(oracle/), %d threads; the Python reference itself runs at ~7 KB/s on one "
                                               "core (BASELINE.md §2)" % (args.cpu_sample_mib, threads)}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
