@@ -26,6 +26,11 @@ class CompressResult(C.Structure):
                 ("payload_bytes", C.c_uint64), ("usage", C.c_uint64 * 5)]
 
 
+class ChunkInfo(C.Structure):
+    _fields_ = [("pos", C.c_uint64), ("orig_len", C.c_uint32), ("comp_len", C.c_uint32), ("type", C.c_uint32),
+                ("pad", C.c_uint32)]
+
+
 class Pkg(C.Structure):
     _fields_ = [("src_off", C.c_uint64), ("dst_off", C.c_uint64), ("comp_len", C.c_uint32),
                 ("orig_len", C.c_uint32), ("type", C.c_uint32), ("out_len", C.c_uint32)]
@@ -46,6 +51,10 @@ _SIGS = {
     "ambc_compress_host": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p,
                                      C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
                                      C.POINTER(CompressResult)]),
+    "ambc_compress_dynamic_workspace_bytes": (C.c_uint64, [C.c_uint64, C.c_void_p, C.c_uint32]),
+    "ambc_compress_dynamic_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                            C.c_char_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+                                            C.POINTER(CompressResult), C.c_void_p, C.c_uint64, C.c_void_p]),
     "ambc_index_host": (C.c_int, [C.c_void_p, C.c_uint64, C.c_char_p, C.c_uint32, C.c_uint64, C.c_uint32,
                                   C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ambc_decompress_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,

@@ -7,8 +7,10 @@ END package (:595-607), "rest of the file is one raw package" when a chunk has n
 (:586-590), verbatim copy when header+body is larger than the input (:241-247).
 
 What differs, on purpose:
-  * CHUNK_SIZE_CANDIDATES holds ONE size (default 4096, the documented --chunk-size default,
-    README.md:79).  The reference's dynamic multi-size search (:548-584) is not built yet.
+  * CHUNK_SIZE_CANDIDATES defaults to ONE size (4096, the documented --chunk-size default,
+    README.md:79) -- the benchmarked fixed-grid path.  Several candidates (chunk_size=[...] or
+    chunk_size="dynamic" for the reference's own list 131072..1024, :61-62) run the reference's
+    dynamic multi-size search (:548-584): every size is tried at every position on the GPU.
   * only the repo-native methods 1-4 (+255) are loaded; third-party codecs 5-11 are out of scope.
   * per_chunk_raw=True and use_marker_search=True are labelled extensions (files stay readable by
     the reference decoder)."""
@@ -34,6 +36,9 @@ METHOD_CHUNK_PREFS = {1: (32, 4096), 2: (128, 8192), 3: (32, 8192), 4: (32, 4096
                       10: (1024, 262144), 11: (1024, 262144), 255: (1, 999999999)}
 
 
+REFERENCE_CANDIDATES = (131072, 65536, 32768, 16384, 8192, 4096, 2048, 1024)  # adaptive_compressor.py:61-62
+
+
 class AdaptiveCompressor:
     MAGIC_NUMBER = b"AMBC"
     FORMAT_VERSION = 2
@@ -54,7 +59,14 @@ class AdaptiveCompressor:
         self.per_chunk_raw = bool(per_chunk_raw)
         self.use_marker_search = bool(use_marker_search)
         if chunk_size is not None:
-            self.CHUNK_SIZE_CANDIDATES = [int(chunk_size)]
+            if isinstance(chunk_size, str):
+                if chunk_size.lower() not in ("dynamic", "auto", "default"):
+                    raise ValueError("chunk_size: an int, a list of candidate sizes, or 'dynamic'")
+                chunk_size = REFERENCE_CANDIDATES
+            if isinstance(chunk_size, (list, tuple)):
+                self.CHUNK_SIZE_CANDIDATES = sorted({int(c) for c in chunk_size}, reverse=True)
+            else:
+                self.CHUNK_SIZE_CANDIDATES = [int(chunk_size)]
         self.compression_methods = [RLECompression(), DictionaryCompression(), HuffmanCompression(),
                                     DeltaCompression(), NoCompression()]
         if methods is not None:
@@ -124,12 +136,12 @@ class AdaptiveCompressor:
 
     # ---- configuration checks ----
     def _fixed_chunk(self):
+        """the single candidate size, or None when several candidates are set (dynamic mode)"""
         c = list(self.CHUNK_SIZE_CANDIDATES)
-        if len(c) != 1:
-            raise NotImplementedError("the B200 path runs one chunk size (CHUNK_SIZE_CANDIDATES=[N]); the reference's "
-                                      "dynamic multi-size search is not built yet")
-        if c[0] <= 0:
+        if not c or min(c) <= 0:
             raise ValueError("chunk size must be positive")
+        if len(c) != 1:
+            return None
         return int(c[0])
 
     def _method_mask(self):
@@ -156,10 +168,14 @@ class AdaptiveCompressor:
         self._init_marker(marker_bytes, marker_len)
         t_in = torch.from_numpy(file_data).to("cuda") if n else torch.empty(0, dtype=torch.uint8, device="cuda")
         flags = L.F_PER_CHUNK_RAW if self.per_chunk_raw else 0
-        out = engine.compress_device(t_in, chunk, mask, flags, self.marker_bytes_aligned)
-        if out.first_raw >= 0 and not self.per_chunk_raw and n - out.first_raw * chunk > 0xFFFFFFFF:
-            raise struct.error("'I' format requires 0 <= number <= 4294967295")  # as struct.pack at :617-619
-        self._fill_chunk_stats(out, n, chunk)
+        if chunk is None:  # several candidate sizes: the reference's dynamic mode (:548-584)
+            out = engine.compress_dynamic_device(t_in, self.CHUNK_SIZE_CANDIDATES, mask, flags, self.marker_bytes_aligned)
+            self._fill_chunk_stats_packages(out.packages, n)
+        else:
+            out = engine.compress_device(t_in, chunk, mask, flags, self.marker_bytes_aligned)
+            if out.first_raw >= 0 and not self.per_chunk_raw and n - out.first_raw * chunk > 0xFFFFFFFF:
+                raise struct.error("'I' format requires 0 <= number <= 4294967295")  # as struct.pack at :617-619
+            self._fill_chunk_stats(out, n, chunk)
         t_gpu = time.time()
         th.join()
         header = self._build_header(marker_bytes[:self.marker_byte_length], marker_len, md5["d"], n, out.body_len)
@@ -205,6 +221,24 @@ class AdaptiveCompressor:
             "original_size": n,
             "compressed_size_without_overhead": int(comps[:limit][comp_mask].sum()),
             "overhead_bytes": ovh * n_comp + self.marker_byte_length + 12,
+        }
+
+    def _fill_chunk_stats_packages(self, packages, n):
+        """_init_stats/_update_stats (:457-480) from a package list [(type, orig, comp)]"""
+        ovh = self.marker_byte_length + 14
+        usage = {m.type_id: 0 for m in self.compression_methods}
+        n_comp = saved = payload = 0
+        for t, orig, comp in packages:
+            if t != 255:
+                n_comp += 1
+                saved += orig - comp - ovh
+                payload += comp
+                if t in usage:
+                    usage[t] += 1
+        self.chunk_stats = {
+            "total_chunks": len(packages), "compressed_chunks": n_comp, "raw_chunks": len(packages) - n_comp,
+            "method_usage": usage, "bytes_saved": saved, "original_size": n,
+            "compressed_size_without_overhead": payload, "overhead_bytes": ovh * n_comp + self.marker_byte_length + 12,
         }
 
     def _build_stats_raw(self, original_size, elapsed):

@@ -12,6 +12,7 @@
 //   k_pack     one CTA per chunk: 18-byte package header + payload to the final offset.
 #define AMBC_BLOCK 512 // encoder CTAs: 16 warps per chunk, 2 CTAs per SM (100 KB of shared memory each)
 #include "ambc_internal.h"
+#include <vector>
 #include "chunk_codec.cuh"
 
 
@@ -214,13 +215,15 @@ k_scan_tiles(unsigned long long *tile_sum, uint64_t tile_begin, uint64_t n_tiles
             npk = fr + 1;
         }
         st->n_packages = npk;
-        body += mb + 12; // END package (:595-607)
-        st->body_len = body;
-        if (body <= out_cap) {
-            uint8_t *e = out + body - (mb + 12);
-            for (uint32_t k = 0; k < mb; k++) e[k] = (uint8_t)(marker_word >> (8 * k));
-            for (uint32_t k = 0; k < 12; k++) e[mb + k] = 0;
+        if (!(flags & 2u)) { // (bit 1: the caller appends a raw tail package and END itself -- span mode)
+            body += mb + 12; // END package (:595-607)
+            if (body <= out_cap) {
+                uint8_t *e = out + body - (mb + 12);
+                for (uint32_t k = 0; k < mb; k++) e[k] = (uint8_t)(marker_word >> (8 * k));
+                for (uint32_t k = 0; k < 12; k++) e[mb + k] = 0;
+            }
         }
+        st->body_len = body;
     }
 }
 
@@ -333,6 +336,75 @@ k_pack(const uint8_t *__restrict__ in, uint64_t total, uint32_t N, const uint8_t
             __syncthreads();
             copy_s2g<PACK_BLOCK>(out + offs[i], buf + 32 - ovh, len + ovh);
         }
+        __syncthreads();
+    }
+}
+
+// ---- span mode: chunks given by (position, size) instead of the fixed grid ---------------------
+// Used by the multi-candidate ("dynamic chunk size") path, adaptive_compressor.py:537-590: first as a
+// trial at every stride-aligned position for one candidate size (sizes only), then on the chosen
+// chunk chain (payloads).  Separate kernels so that the fixed-grid hot path stays untouched.
+struct ChunkSpan { unsigned long long pos; uint32_t size; uint32_t pad; };
+
+__global__ void __launch_bounds__(AMBC_BLOCK, 1)
+k_select_span(const uint8_t *__restrict__ in, uint64_t total, uint32_t N, uint32_t mask, uint32_t ovh,
+              uint32_t stride, const ChunkSpan *__restrict__ list, uint8_t *__restrict__ slots,
+              uint8_t *__restrict__ type, uint32_t *__restrict__ comp, uint64_t n_items)
+{
+    // list == nullptr: item i = [i * stride, i * stride + min(N, total - i * stride)), no payload kept;
+    // else item i = list[i] and its payload goes to slots + list[i].pos (payloads are shorter than
+    // their chunks, so the chunk's own offset is a collision-free slot)
+    extern __shared__ uint4 smem4[];
+    ChunkCtx c;
+    if (N <= LZ2_NMAX) chunkctx_carve_fast(c, (uint8_t *)smem4, (int)N);
+    else chunkctx_carve(c, (uint8_t *)smem4, (int)N, (int)N);
+    for (uint64_t i = blockIdx.x; i < n_items; i += gridDim.x) {
+        uint64_t off;
+        int n;
+        if (list) { off = list[i].pos; n = (int)list[i].size; }
+        else { off = i * (uint64_t)stride; n = (int)min((uint64_t)N, total - off); }
+        chunk_load(c, in + off, n);
+        SelectOut o = select_chunk(c, mask, (int)ovh);
+        __syncthreads();
+        if (slots && o.type != 255) {
+            uint8_t *dst = slots + off;
+            if ((((uintptr_t)dst) & 15) == 0) {
+                int nv = (o.len + 15) >> 4;
+                for (int k = threadIdx.x; k < nv; k += AMBC_BLOCK) ((uint4 *)dst)[k] = ((const uint4 *)c.pay)[k];
+            } else {
+                for (int k = threadIdx.x; k < o.len; k += AMBC_BLOCK) dst[k] = c.pay[k];
+            }
+        }
+        if (threadIdx.x == 0) {
+            type[i] = (uint8_t)o.type;
+            comp[i] = (uint32_t)o.len;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(PACK_BLOCK)
+k_pack_span(const uint8_t *__restrict__ in, const ChunkSpan *__restrict__ list, const uint8_t *__restrict__ slots,
+            const uint8_t *__restrict__ type, const uint32_t *__restrict__ comp,
+            const unsigned long long *__restrict__ offs, uint32_t marker_word, uint32_t mb,
+            uint8_t *__restrict__ out, uint64_t n_items)
+{
+    extern __shared__ uint4 smem4[];
+    uint8_t *buf = (uint8_t *)smem4; // [32 header area][payload]
+    const uint32_t ovh = mb + 14;
+    for (uint64_t i = blockIdx.x; i < n_items; i += gridDim.x) {
+        const uint64_t coff = list[i].pos;
+        const int n = (int)list[i].size;
+        const int t = type[i];
+        const int len = (int)comp[i];
+        if (t == 255) {
+            for (int k = threadIdx.x; k < n; k += PACK_BLOCK) buf[32 + k] = in[coff + k];
+        } else {
+            for (int k = threadIdx.x; k < len; k += PACK_BLOCK) buf[32 + k] = slots[coff + k];
+        }
+        if (threadIdx.x == 0) write_pkg_header(buf + 32 - ovh, marker_word, mb, t, (uint32_t)n, (uint32_t)len);
+        __syncthreads();
+        copy_s2g<PACK_BLOCK>(out + offs[i], buf + 32 - ovh, len + ovh);
         __syncthreads();
     }
 }
@@ -561,6 +633,231 @@ extern "C" int ambc_phase_read(unsigned long long *out32, int reset)
     return 0;
 }
 #endif
+// ---- multi-candidate ("dynamic chunk size") mode ------------------------------------------------
+// adaptive_compressor.py:537-590 with several CHUNK_SIZE_CANDIDATES: at every position each candidate
+// size (clamped to the remaining bytes) is tried, the smallest ratio (len + overhead) / size wins,
+// larger candidates win ties; no winner -> the rest of the file is one raw package.
+// Every reachable position is a multiple of g = gcd(candidates), so each distinct size min(cand, 8192)
+// is tried at every multiple of g on the GPU (sizes only), the chain is resolved on the host (it is a
+// serial walk over <= n / g table entries), and the chosen chunks are encoded and framed in span mode.
+static uint64_t gcd64(uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; }
+
+struct DynLayout {
+    uint64_t slots, spans, type, comp, offs, tiles, state, trial_type, trial_len, total;
+    uint64_t n_pos, n_tiles, n_pass, g;
+    uint32_t pass_size[16];
+    int cand_pass[32];
+};
+static int dyn_layout(uint64_t n, const uint32_t *cands, uint32_t n_cands, DynLayout &L)
+{
+    if (!cands || n_cands < 1 || n_cands > 32) return ambc_fail(AMBC_E_ARG, "need 1..32 candidate sizes");
+    uint64_t g = 0;
+    for (uint32_t i = 0; i < n_cands; i++) {
+        if (cands[i] == 0) return ambc_fail(AMBC_E_ARG, "candidate size 0");
+        if (i && cands[i] >= cands[i - 1]) return ambc_fail(AMBC_E_ARG, "candidate sizes must be strictly descending");
+        g = gcd64(g, cands[i]);
+    }
+    if (g < 256 || g % 16) return ambc_fail(AMBC_E_ARG, "candidate sizes need a common divisor that is a multiple of 16 and >= 256");
+    L.g = g;
+    L.n_pos = (n + g - 1) / g;
+    L.n_pass = 0;
+    for (uint32_t i = 0; i < n_cands; i++) {
+        uint32_t sz = cands[i] < AMBC_NMAX ? cands[i] : AMBC_NMAX;
+        int found = -1;
+        for (uint64_t j = 0; j < L.n_pass; j++) if (L.pass_size[j] == sz) found = (int)j;
+        if (found < 0) { if (L.n_pass >= 16) return ambc_fail(AMBC_E_ARG, "too many distinct candidate sizes"); found = (int)L.n_pass; L.pass_size[L.n_pass++] = sz; }
+        L.cand_pass[i] = found;
+    }
+    L.n_tiles = (L.n_pos + SCAN_TILE - 1) / SCAN_TILE;
+    uint64_t o = 0;
+    auto take = [&](uint64_t bytes) { uint64_t r = o; o += (bytes + 255) & ~255ull; return r; };
+    L.slots = take(n + 64);
+    L.spans = take(L.n_pos * sizeof(ChunkSpan) + 16);
+    L.type = take(L.n_pos + 16);
+    L.comp = take(L.n_pos * 4 + 16);
+    L.offs = take(L.n_pos * 8 + 16);
+    L.tiles = take(L.n_tiles * 8 + 16);
+    L.state = take(sizeof(ScanState));
+    L.trial_type = take(L.n_pass * (L.n_pos + 16));
+    L.trial_len = take(L.n_pass * (L.n_pos * 4 + 16));
+    L.total = o;
+    return AMBC_OK;
+}
+
+extern "C" uint64_t ambc_compress_dynamic_workspace_bytes(uint64_t n, const uint32_t *cands, uint32_t n_cands)
+{
+    DynLayout L;
+    if (dyn_layout(n, cands, n_cands, L)) return 0;
+    return L.total;
+}
+
+extern "C" int ambc_compress_dynamic_dev(const void *in_dev, uint64_t n, const uint32_t *cands, uint32_t n_cands,
+                                         uint32_t method_mask, uint32_t flags, const uint8_t *marker,
+                                         uint32_t marker_bytes, void *out_dev, uint64_t out_cap, void *work_dev,
+                                         uint64_t work_bytes, ambc_compress_result *res, ambc_chunk_info *map_out,
+                                         uint64_t map_cap, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!res || !marker || marker_bytes < 1 || marker_bytes > 4) return ambc_fail(AMBC_E_ARG, "ambc_compress_dynamic_dev: bad argument");
+    if ((n && (!in_dev || !work_dev)) || !out_dev) return ambc_fail(AMBC_E_ARG, "ambc_compress_dynamic_dev: null buffer");
+    DynLayout L;
+    int rc = dyn_layout(n, cands, n_cands, L);
+    if (rc) return rc;
+    if (work_bytes < L.total) return ambc_fail(AMBC_E_CAPACITY, "ambc_compress_dynamic_dev: workspace too small");
+    const uint32_t ovh = marker_bytes + 14;
+    uint32_t marker_word = 0;
+    for (uint32_t k = 0; k < marker_bytes; k++) marker_word |= (uint32_t)marker[k] << (8 * k);
+    memset(res, 0, sizeof(*res));
+    res->first_raw = -1;
+    uint8_t endp[16], hdr[18];
+    memcpy(endp, marker, marker_bytes);
+    memset(endp + marker_bytes, 0, 12);
+    uint8_t *W = (uint8_t *)work_dev;
+    const bool pcr = flags & AMBC_F_PER_CHUNK_RAW;
+
+    // ---- trial passes: sizes only, every multiple of g, one pass per distinct size ----------------
+    std::vector<uint8_t> h_type(L.n_pass * L.n_pos);
+    std::vector<uint32_t> h_len(L.n_pass * L.n_pos);
+    const bool native = (method_mask & AMBC_NATIVE_MASK) != 0;
+    if (n && native) {
+        for (uint64_t j = 0; j < L.n_pass; j++) {
+            const uint32_t S = L.pass_size[j];
+            size_t smem = S <= LZ2_NMAX ? chunkctx_fast_smem_bytes((int)S) : chunkctx_smem_bytes((int)S, (int)S);
+            CUDA_TRY(cudaFuncSetAttribute(k_select_span, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            uint8_t *tt = W + L.trial_type + j * (L.n_pos + 16);
+            uint32_t *tl = (uint32_t *)(W + L.trial_len + j * (L.n_pos * 4 + 16));
+            unsigned grid = (unsigned)min<uint64_t>(L.n_pos, 0x7fffffffull);
+            k_select_span<<<grid, AMBC_BLOCK, smem, stream>>>((const uint8_t *)in_dev, n, S, method_mask, ovh, (uint32_t)L.g,
+                                                             nullptr, nullptr, tt, tl, L.n_pos);
+            ambc_count_launch();
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(h_type.data() + j * L.n_pos, tt, L.n_pos, cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaMemcpyAsync(h_len.data() + j * L.n_pos, tl, L.n_pos * 4, cudaMemcpyDeviceToHost, stream));
+        }
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+
+    // ---- the chain (adaptive_compressor.py:363-394 + 537-590) -------------------------------------
+    std::vector<ChunkSpan> spans;
+    std::vector<uint8_t> s_type;
+    std::vector<uint32_t> s_len;
+    uint64_t pos = 0, raw_from = n; // raw_from < n: one raw package [raw_from, n)
+    while (pos < n) {
+        const uint64_t remain = n - pos, i = pos / L.g;
+        double best_ratio = 1.0;
+        uint64_t best_c = remain;
+        int best_t = 255;
+        uint32_t best_len = 0;
+        for (uint32_t ci = 0; ci < n_cands && native; ci++) {
+            const uint64_t c = cands[ci] < remain ? cands[ci] : remain;
+            if (c > AMBC_NMAX) continue; // no native method is eligible (:114-127)
+            const uint64_t j = (uint64_t)L.cand_pass[ci];
+            const int t = h_type[j * L.n_pos + i];
+            if (t == 255) continue;
+            const uint32_t len = h_len[j * L.n_pos + i];
+            const double ratio = (double)((uint64_t)len + ovh) / (double)c; // (:573-574)
+            if (ratio < best_ratio) { best_ratio = ratio; best_c = c; best_t = t; best_len = len; }
+        }
+        if (best_t == 255) {
+            if (!pcr) { raw_from = pos; break; }                       // rest of the file raw (:586-590)
+            best_c = cands[n_cands - 1] < remain ? cands[n_cands - 1] : remain; // labelled extension
+            best_len = (uint32_t)best_c;
+        }
+        ChunkSpan sp; sp.pos = pos; sp.size = (uint32_t)best_c; sp.pad = 0;
+        spans.push_back(sp); s_type.push_back((uint8_t)best_t); s_len.push_back(best_len);
+        pos += best_c;
+    }
+    const uint64_t n_list = spans.size();
+    if (n_list > L.n_pos) return ambc_fail(AMBC_E_ARG, "internal: chain longer than the position table");
+    uint64_t body = 0;
+    for (uint64_t k = 0; k < n_list; k++) body += ovh + s_len[k];
+    const uint64_t raw_len = raw_from < n ? n - raw_from : 0;
+    if (raw_len > 0xFFFFFFFFull) return ambc_fail(AMBC_E_ARG, "raw package over 4 GiB cannot be framed (u32 fields)");
+    const uint64_t total_body = body + (raw_len ? ovh + raw_len : 0) + marker_bytes + 12;
+    if (total_body > out_cap) return ambc_fail(AMBC_E_CAPACITY, "ambc_compress_dynamic_dev: out_cap too small");
+
+    // ---- encode + frame the chosen chunks ---------------------------------------------------------
+    if (n_list) {
+        ChunkSpan *d_spans = (ChunkSpan *)(W + L.spans);
+        uint8_t *type = W + L.type;
+        uint32_t *comp = (uint32_t *)(W + L.comp);
+        unsigned long long *offs = (unsigned long long *)(W + L.offs);
+        unsigned long long *tiles = (unsigned long long *)(W + L.tiles);
+        ScanState *st = (ScanState *)(W + L.state);
+        ScanState h_st;
+        memset(&h_st, 0, sizeof h_st);
+        h_st.first_raw = ~0ull;
+        CUDA_TRY(cudaMemcpyAsync(st, &h_st, sizeof h_st, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(d_spans, spans.data(), n_list * sizeof(ChunkSpan), cudaMemcpyHostToDevice, stream));
+        uint32_t maxsz = 0;
+        for (uint64_t k = 0; k < n_list; k++) maxsz = max(maxsz, spans[k].size);
+        if (maxsz > AMBC_NMAX) { // only per-chunk-raw pieces can be this large
+            return ambc_fail(AMBC_E_ARG, "per-chunk-raw pieces larger than 8192 bytes are not supported");
+        }
+        size_t smem = maxsz <= LZ2_NMAX ? chunkctx_fast_smem_bytes((int)maxsz) : chunkctx_smem_bytes((int)maxsz, (int)maxsz);
+        CUDA_TRY(cudaFuncSetAttribute(k_select_span, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        unsigned grid = (unsigned)min<uint64_t>(n_list, 0x7fffffffull);
+        k_select_span<<<grid, AMBC_BLOCK, smem, stream>>>((const uint8_t *)in_dev, n, maxsz, method_mask, ovh, 0, d_spans,
+                                                         W + L.slots, type, comp, n_list);
+        ambc_count_launch();
+        const unsigned gt = (unsigned)((n_list + SCAN_TILE - 1) / SCAN_TILE);
+        const uint32_t sflags = 1u | 2u; // every entry is a package; no END (appended below)
+        k_sizes<<<gt, 256, 0, stream>>>(type, comp, 0, n_list, maxsz, n, ovh, sflags, st, tiles);
+        ambc_count_launch();
+        k_scan_tiles<<<1, 1024, 0, stream>>>(tiles, 0, gt, 1, type, comp, n_list, maxsz, n, ovh, sflags, st, (uint8_t *)out_dev,
+                                             out_cap, marker_word, marker_bytes);
+        ambc_count_launch();
+        k_offsets<<<gt, 256, 0, stream>>>(type, comp, 0, n_list, maxsz, n, ovh, sflags, st, tiles, offs);
+        ambc_count_launch();
+        size_t psmem = 32 + (((size_t)maxsz + 15) & ~(size_t)15) + 32;
+        CUDA_TRY(cudaFuncSetAttribute(k_pack_span, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+        k_pack_span<<<grid, PACK_BLOCK, psmem, stream>>>((const uint8_t *)in_dev, d_spans, W + L.slots, type, comp, offs,
+                                                        marker_word, marker_bytes, (uint8_t *)out_dev, n_list);
+        ambc_count_launch();
+        CUDA_TRY(cudaGetLastError());
+        // the second evaluation must agree with the trial the chain was built from
+        std::vector<uint8_t> chk_t(n_list);
+        std::vector<uint32_t> chk_l(n_list);
+        CUDA_TRY(cudaMemcpyAsync(chk_t.data(), type, n_list, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(chk_l.data(), comp, n_list * 4, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(&h_st, st, sizeof h_st, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        for (uint64_t k = 0; k < n_list; k++)
+            if (chk_t[k] != s_type[k] || chk_l[k] != s_len[k])
+                return ambc_fail(AMBC_E_CUDA, "internal: span encode disagrees with its trial at chunk %llu", (unsigned long long)k);
+        if (h_st.body_len != body) return ambc_fail(AMBC_E_CUDA, "internal: span body length mismatch");
+    }
+    // ---- raw tail package (if any) and END ---------------------------------------------------------
+    uint8_t *o = (uint8_t *)out_dev + body;
+    if (raw_len) {
+        memcpy(hdr, marker, marker_bytes);
+        hdr[marker_bytes] = 255; hdr[marker_bytes + 1] = 0;
+        const uint32_t r32 = (uint32_t)raw_len;
+        for (int r = 0; r < 3; r++) memcpy(hdr + marker_bytes + 2 + 4 * r, &r32, 4);
+        CUDA_TRY(cudaMemcpyAsync(o, hdr, ovh, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(o + ovh, (const uint8_t *)in_dev + raw_from, raw_len, cudaMemcpyDeviceToDevice, stream));
+        o += ovh + raw_len;
+    }
+    CUDA_TRY(cudaMemcpyAsync(o, endp, marker_bytes + 12, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+
+    res->body_len = total_body;
+    res->n_chunks = n_list + (raw_len ? 1 : 0);
+    res->n_packages = res->n_chunks;
+    res->first_raw = raw_len ? (int64_t)n_list : -1;
+    for (uint64_t k = 0; k < n_list; k++) {
+        const int t = s_type[k];
+        if (t >= 1 && t <= 4) { res->usage[t]++; res->payload_bytes += s_len[k]; }
+        else res->usage[0]++;
+        if (map_out && k < map_cap) { map_out[k].pos = spans[k].pos; map_out[k].orig_len = spans[k].size; map_out[k].comp_len = s_len[k]; map_out[k].type = (uint32_t)t; }
+    }
+    if (raw_len) {
+        res->usage[0]++;
+        if (map_out && n_list < map_cap) { map_out[n_list].pos = raw_from; map_out[n_list].orig_len = (uint32_t)raw_len; map_out[n_list].comp_len = (uint32_t)raw_len; map_out[n_list].type = 255; }
+    }
+    return AMBC_OK;
+}
+
 int ambc_lz_levels_compress(const int *levels, int n) { return lz_levels_upload(levels, n); }
 int ambc_lz_coop_compress(int t) { return lz_coop_upload(t); }
 int ambc_lz_force_buckets_compress(int on) { return lz_force_buckets_upload(on); }

@@ -57,7 +57,7 @@ def method_mask(ids):
 
 class CompressOutput:
     __slots__ = ("body", "body_len", "n_chunks", "first_raw", "n_packages", "types", "comp_lens", "payload_bytes",
-                 "usage", "_keep")
+                 "usage", "packages", "_keep")
 
 
 def compress_device(t_in, chunk=4096, mask=L.NATIVE_MASK, flags=0, marker=FIXED_MARKER, out=None, work=None):
@@ -85,6 +85,42 @@ def compress_device(t_in, chunk=4096, mask=L.NATIVE_MASK, flags=0, marker=FIXED_
     nc = res.n_chunks
     o.types = work[res.map_type_off:res.map_type_off + nc]
     o.comp_lens = work[res.map_comp_off:res.map_comp_off + 4 * nc].view(torch.int32)
+    o._keep = (out, work)
+    return o
+
+
+def compress_dynamic_device(t_in, candidates, mask=L.NATIVE_MASK, flags=0, marker=FIXED_MARKER):
+    """multi-candidate mode (adaptive_compressor.py:548-584): device tensor -> CompressOutput whose
+    `packages` is the reference's package walk [(type, orig, comp)]"""
+    lib = require_cuda()
+    n = t_in.numel()
+    cands = sorted({int(c) for c in candidates}, reverse=True)
+    arr = (C.c_uint32 * len(cands))(*cands)
+    wbytes = lib.ambc_compress_dynamic_workspace_bytes(n, arr, len(cands))
+    if wbytes == 0:
+        raise L.AmbcError(L.E_ARG, lib.ambc_last_error().decode("utf-8", "replace"))
+    g = 0
+    for c in cands:
+        g = c if g == 0 else __import__("math").gcd(g, c)
+    bound = n + (n // g + 3) * (len(marker) + 14) + len(marker) + 12 + 64
+    out = torch.empty(bound, dtype=torch.uint8, device="cuda")
+    work = torch.empty(max(wbytes, 1), dtype=torch.uint8, device="cuda")
+    cap = n // g + 3
+    info = (L.ChunkInfo * cap)()
+    res = L.CompressResult()
+    L.check(lib.ambc_compress_dynamic_dev(C.c_void_p(t_in.data_ptr() if n else 0), n, arr, len(cands), mask, flags, marker,
+                                          len(marker), C.c_void_p(out.data_ptr()), out.numel(), C.c_void_p(work.data_ptr()),
+                                          work.numel(), C.byref(res), info, cap, _stream_ptr()))
+    o = CompressOutput()
+    o.body = out[:res.body_len]
+    o.body_len = res.body_len
+    o.n_chunks = res.n_chunks
+    o.first_raw = res.first_raw
+    o.n_packages = res.n_packages
+    o.payload_bytes = res.payload_bytes
+    o.usage = list(res.usage)
+    o.types = o.comp_lens = None
+    o.packages = [(int(info[k].type), int(info[k].orig_len), int(info[k].comp_len)) for k in range(int(res.n_packages))]
     o._keep = (out, work)
     return o
 

@@ -107,6 +107,28 @@ int ambc_compress_host(const void *in_host, uint64_t n, uint32_t chunk, uint32_t
                        const uint8_t *marker, uint32_t marker_bytes, void *out_host, uint64_t out_cap,
                        uint8_t *map_type, uint32_t *map_comp, ambc_compress_result *res);
 
+/*
+ * Multi-candidate ("dynamic chunk size") mode: the reference's default
+ * CHUNK_SIZE_CANDIDATES = [131072 .. 1024] (adaptive_compressor.py:61-62) or any
+ * strictly descending list whose gcd is a multiple of 16 and >= 256.  At every
+ * position each candidate (clamped to the remaining bytes) is tried, the smallest
+ * ratio (len + overhead) / size wins, larger candidates win ties
+ * (adaptive_compressor.py:548-584); no winner -> the rest is one raw package.
+ * map_out (optional, map_cap entries): the package list in file order.
+ */
+typedef struct {
+    uint64_t pos;       /* offset of the chunk in the input */
+    uint32_t orig_len;  /* chunk size                        */
+    uint32_t comp_len;  /* payload bytes                     */
+    uint32_t type;      /* package type                      */
+    uint32_t pad;
+} ambc_chunk_info;
+uint64_t ambc_compress_dynamic_workspace_bytes(uint64_t n, const uint32_t *cands, uint32_t n_cands);
+int ambc_compress_dynamic_dev(const void *in_dev, uint64_t n, const uint32_t *cands, uint32_t n_cands,
+                              uint32_t method_mask, uint32_t flags, const uint8_t *marker, uint32_t marker_bytes,
+                              void *out_dev, uint64_t out_cap, void *work_dev, uint64_t work_bytes,
+                              ambc_compress_result *res, ambc_chunk_info *map_out, uint64_t map_cap, void *stream);
+
 /* ------------------------------------------------------------------ */
 /* decompress: AdaptiveCompressor._adaptive_decompress                  */
 /*   adaptive_compressor.py:396-454                                     */

@@ -105,13 +105,26 @@ def decompress_file(args):
         sys.exit(1)
 
 
+def parse_chunk_size(text):
+    """--chunk-size N | dynamic | N1,N2,..."""
+    t = text.strip().lower()
+    if t in ("dynamic", "auto", "default"):
+        from adaptive_compression_b200.adaptive_compressor import REFERENCE_CANDIDATES
+        return list(REFERENCE_CANDIDATES)
+    if "," in t:
+        return [int(x) for x in t.split(",") if x.strip()]
+    return int(t)
+
+
 def main(argv=None):
     p = argparse.ArgumentParser(description="Adaptive Marker-Based Compression (B200 chunk path)")
     sub = p.add_subparsers(dest="command", help="Command to execute")
     c = sub.add_parser("compress", help="Compress a file")
     c.add_argument("input")
     c.add_argument("output")
-    c.add_argument("--chunk-size", type=int, default=4096, help="Size of data chunks in bytes (default: 4096)")
+    c.add_argument("--chunk-size", type=parse_chunk_size, default=4096,
+                   help="Size of data chunks in bytes (default: 4096); 'dynamic' = the reference's candidate list "
+                        "131072..1024 (adaptive_compressor.py:61-62), or a comma-separated candidate list")
     c.add_argument("--methods", default=None, help="Comma-separated list of compression methods to use")
     c.add_argument("--disable-methods", default=None, help="Comma-separated list of compression methods to disable")
     c.add_argument("--show-progress", action="store_true", help="accepted for compatibility; the GPU path has no per-chunk progress")

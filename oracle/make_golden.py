@@ -115,6 +115,31 @@ def gen_container():
     dump("container_kat.json", rows)
 
 
+def gen_container_dyn():
+    """multi-candidate (dynamic chunk size) containers -> container_dyn_kat.json"""
+    rows = []
+    with tempfile.TemporaryDirectory() as td:
+        for name, data, cfg in inputs.dynamic_cases():
+            t0 = time.time()
+            out, stats, pm = R.compress_bytes(data, td, **cfg)
+            row = {"name": name, "n": len(data), "sha256": sha(data), "cfg": {k: (list(v) if isinstance(v, tuple) else v) for k, v in cfg.items()},
+                   "ambc_len": len(out), "ambc_sha256": sha(out), "stored_verbatim": pm is None and out == data,
+                   "packages": pm}
+            if pm is not None:
+                back = R.decompress_bytes(out, td)
+                row["ref_roundtrip"] = back == data
+            cs = stats["chunk_stats"]
+            row["stats"] = {"original_size": stats["original_size"], "compressed_size": stats["compressed_size"],
+                            "ratio": stats["ratio"], "percent_reduction": stats["percent_reduction"],
+                            "overhead_bytes": stats["overhead_bytes"],
+                            "compression_efficiency": stats["compression_efficiency"],
+                            "chunk_stats": {k: ({str(a): b for a, b in v.items()} if isinstance(v, dict) else v)
+                                            for k, v in cs.items()}}
+            rows.append(row)
+            print("container_dyn", name, len(data), "->", len(out), "%.1fs" % (time.time() - t0), flush=True)
+    dump("container_dyn_kat.json", rows)
+
+
 def gen_marker():
     rows = []
     for name, data, max_len, sample in inputs.marker_cases():

@@ -197,6 +197,24 @@ def container_cases():
     return out
 
 
+REF_DEFAULT_CANDIDATES = (131072, 65536, 32768, 16384, 8192, 4096, 2048, 1024)  # adaptive_compressor.py:61-62
+
+
+def dynamic_cases():
+    """(name, data, cfg) for the reference's multi-candidate mode (adaptive_compressor.py:548-584):
+    every candidate size is tried at every position, the best ratio wins, larger sizes win ties"""
+    out = []
+    out.append(("dyn_default_mixed", mixed_file(9, 4096, 71, ("text", "csv", "log", "runs", "lowcard")) + text(700, 72),
+                dict(chunk_size=REF_DEFAULT_CANDIDATES)))
+    out.append(("dyn_default_tailraw", text(4096, 73) + runs(3000, 74) + csv(5000, 75) + rand(3000, 76) + text(500, 77),
+                dict(chunk_size=REF_DEFAULT_CANDIDATES)))
+    out.append(("dyn_small", mixed_file(10, 1024, 78) + lowcard(300, 79), dict(chunk_size=(2048, 1024, 512))))
+    out.append(("dyn_no8192", mixed_file(5, 4096, 80, ("text", "log", "csv")) + log(2500, 81),
+                dict(chunk_size=(16384, 4096, 1024))))
+    out.append(("dyn_rle_huff", mixed_file(6, 2048, 82, ("runs", "lowcard", "skewed")), dict(chunk_size=(4096, 2048, 1024), method_ids=(1, 3))))
+    return out
+
+
 def marker_cases():
     """(name, data, max_len, sample_size)"""
     return [

@@ -173,3 +173,43 @@ def test_config5_interleaved_segments(eng, pcr):
         assert o.first_raw == 8 and wpm[-1][0] == 255 and wpm[-1][1] == len(data) - 8 * 4096
     out, status = eng.decompress_device(o.body, len(data))
     assert status == [0, 0] and out.cpu().numpy().tobytes() == data
+
+
+def test_dynamic_candidates_golden_and_oracle(eng, golden):
+    """the reference's multi-candidate mode (adaptive_compressor.py:548-584): body and package list ==
+    the files the unmodified reference wrote (golden) and the oracle; round trip through the decoder"""
+    from adaptive_compression_b200.adaptive_compressor import AdaptiveCompressor
+    cases = {n: (d, c) for n, d, c in inputs.dynamic_cases()}
+    for row in golden["container_dyn_kat"]:
+        data, cfg = cases[row["name"]]
+        mids = tuple(cfg.get("method_ids", (1, 2, 3, 4)))
+        o = eng.compress_dynamic_device(eng.to_device(data), cfg["chunk_size"], mask=eng.method_mask(mids))
+        body = o.body.cpu().numpy().tobytes()
+        wbody, wpm = O.compress_body(data, tuple(cfg["chunk_size"]), mids)
+        assert body == wbody, row["name"]
+        assert [list(p) for p in o.packages] == [list(p) for p in wpm] == row["packages"], row["name"]
+        # whole file == the reference's own file
+        f, raw, _ = O.compress_file(data, tuple(cfg["chunk_size"]), mids)
+        assert sha(f) == row["ambc_sha256"]
+        hs = int.from_bytes(f[5:9], "little")
+        assert f[hs:] == body
+        out, status = eng.decompress_device(o.body, len(data))
+        assert status == [0, 0] and out.cpu().numpy().tobytes() == data, row["name"]
+
+
+@pytest.mark.parametrize("cands", [(131072, 65536, 32768, 16384, 8192, 4096, 2048, 1024), (4096, 1024), (8192, 2048, 512)])
+def test_dynamic_candidates_fuzz_vs_oracle(eng, cands):
+    r = np.random.RandomState(sum(cands) % 1000)
+    for i in range(6):
+        kinds = ("text", "csv", "log", "runs", "lowcard", "binrec", "periodic", "rand")
+        parts = [inputs.make(kinds[r.randint(len(kinds) - (0 if i % 3 == 2 else 1))], int(r.choice([700, 1024, 2048, 3000, 4096, 9000])), 6000 + 100 * i + j)
+                 for j in range(int(r.randint(3, 9)))]
+        data = b"".join(parts)
+        for pcr in (False, True):
+            from adaptive_compression_b200 import _lib as L
+            o = eng.compress_dynamic_device(eng.to_device(data), cands, flags=L.F_PER_CHUNK_RAW if pcr else 0)
+            wbody, wpm = O.compress_body(data, cands, per_chunk_raw=pcr)
+            assert o.body.cpu().numpy().tobytes() == wbody, (cands, i, pcr)
+            assert [list(p) for p in o.packages] == [list(p) for p in wpm]
+            out, status = eng.decompress_device(o.body, len(data))
+            assert status == [0, 0] and out.cpu().numpy().tobytes() == data

@@ -77,8 +77,14 @@ def test_error_conventions(tmp_path):
     with pytest.raises(ValueError, match="Checksum mismatch"):
         c.decompress(str(dst), str(back))
     assert back.exists()
-    with pytest.raises(NotImplementedError):
-        c2 = AdaptiveCompressor(); c2.CHUNK_SIZE_CANDIDATES = [8192, 4096]; c2.compress(str(src), str(dst))
+    # candidate lists the GPU search cannot grid (common divisor below 256 bytes) are refused loudly
+    from adaptive_compression_b200._lib import AmbcError
+    with pytest.raises(AmbcError):
+        c2 = AdaptiveCompressor(); c2.CHUNK_SIZE_CANDIDATES = [4096, 1000]; c2.compress(str(src), str(dst))
+    # the harness-style configuration of the reference selects the dynamic mode
+    c3 = AdaptiveCompressor(); c3.CHUNK_SIZE_CANDIDATES = [8192, 4096]; c3.compress(str(src), str(dst))
+    want, _, _ = O.compress_file(src.read_bytes(), (8192, 4096))
+    assert dst.read_bytes() == want
 
 
 def test_plugin_objects():
@@ -182,3 +188,45 @@ def test_host_buffer_abi_pipelined(kind_mask):
     L.check(lib.ambc_decompress_host(C.c_void_p(body.ctypes.data), res.body_len, b"\xff\xff\x00\x00", 4, L.NATIVE_MASK,
                                      C.c_void_p(back.ctypes.data), n + 100, st))
     assert np.array_equal(back[:n], data) and not back[n:].any() and list(st) == [0, 0]
+
+
+def test_dynamic_mode_files_equal_reference_files(golden, tmp_path):
+    """several CHUNK_SIZE_CANDIDATES (the reference's default list and custom ones): the facade's file ==
+    the file the unmodified reference wrote; stats equal; both decoders read it"""
+    cases = {c[0]: c for c in inputs.dynamic_cases()}
+    for row in golden["container_dyn_kat"]:
+        name, data, _ = cases[row["name"]]
+        src, dst, back = tmp_path / "in.bin", tmp_path / "out.ambc", tmp_path / "back.bin"
+        src.write_bytes(data)
+        c = _compressor(row["cfg"])
+        stats = c.compress(str(src), str(dst))
+        out = dst.read_bytes()
+        assert len(out) == row["ambc_len"] and sha(out) == row["ambc_sha256"], name
+        if "stats" in row:
+            g = row["stats"]
+            for k in ("original_size", "compressed_size", "ratio", "percent_reduction", "overhead_bytes",
+                      "compression_efficiency"):
+                assert stats[k] == pytest.approx(g[k], rel=1e-12, abs=1e-12), (name, k, stats[k], g[k])
+            gcs = g["chunk_stats"]
+            for k in ("total_chunks", "compressed_chunks", "raw_chunks", "bytes_saved", "original_size",
+                      "compressed_size_without_overhead", "overhead_bytes"):
+                assert stats["chunk_stats"][k] == gcs[k], (name, k, stats["chunk_stats"][k], gcs[k])
+            assert {str(k): v for k, v in stats["chunk_stats"]["method_usage"].items()} == gcs["method_usage"], name
+        c.decompress(str(dst), str(back))
+        assert back.read_bytes() == data, name
+        assert O.decompress_file(out) == data
+
+
+def test_cli_dynamic_chunk_size(tmp_path):
+    data = inputs.mixed_file(5, 4096, 91, ("text", "log", "runs")) + inputs.csv(900, 92)
+    src, dst, back = tmp_path / "a.bin", tmp_path / "a.ambc", tmp_path / "a.out"
+    src.write_bytes(data)
+    env = dict(os.environ)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "main.py"), "compress", str(src), str(dst), "--chunk-size",
+                        "dynamic", "--no-history"], capture_output=True, text=True, env=env, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout + r.stderr
+    want, raw, _ = O.compress_file(data, inputs.REF_DEFAULT_CANDIDATES)
+    assert dst.read_bytes() == want
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "main.py"), "decompress", str(dst), str(back)],
+                       capture_output=True, text=True, env=env, cwd=str(tmp_path))
+    assert r.returncode == 0 and back.read_bytes() == data

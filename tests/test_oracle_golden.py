@@ -103,3 +103,16 @@ def test_fast_lz_equals_naive_fuzz():
         n = int(r.choice([1, 2, 3, 7, 64, 500, 2048, 4096, 4097, 6000, 8192]))
         d = inputs.make(k, n, 7000 + i)
         assert O.compress(2, d, lz_fast=True) == O.compress(2, d), (k, n, i)
+
+
+def test_container_dynamic_kat(golden):
+    """multi-candidate (dynamic chunk size) files written by the unmodified reference
+    (adaptive_compressor.py:548-584, default and custom candidate lists) == oracle, byte for byte"""
+    cases = {n: (d, c) for n, d, c in inputs.dynamic_cases()}
+    for row in golden["container_dyn_kat"]:
+        data, cfg = cases[row["name"]]
+        assert sha(data) == row["sha256"]
+        f, raw, pm = O.compress_file(data, tuple(cfg["chunk_size"]), tuple(cfg.get("method_ids", (1, 2, 3, 4))))
+        assert len(f) == row["ambc_len"] and sha(f) == row["ambc_sha256"], row["name"]
+        assert [list(p) for p in pm] == row["packages"], row["name"]
+        assert O.decompress_file(f) == data
