@@ -57,6 +57,8 @@ _SIGS = {
                                             C.POINTER(CompressResult), C.c_void_p, C.c_uint64, C.c_void_p]),
     "ambc_index_host": (C.c_int, [C.c_void_p, C.c_uint64, C.c_char_p, C.c_uint32, C.c_uint64, C.c_uint32,
                                   C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "ambc_index_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.c_char_p, C.c_uint32, C.c_uint64, C.c_uint32,
+                                 C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p]),
     "ambc_decompress_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
                                       C.c_void_p, C.c_void_p]),
     "ambc_decompress_host": (C.c_int, [C.c_void_p, C.c_uint64, C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p,

@@ -156,17 +156,40 @@ def index_host(body, orig_size, marker=FIXED_MARKER, known_mask=L.NATIVE_MASK):
     return table[:ne.value], cov.value
 
 
-def decompress_device(t_body, orig_size, marker=FIXED_MARKER, known_mask=L.NATIVE_MASK, body_host=None, out=None):
-    """device body -> (device output tensor, status [codec errors, length mismatches])"""
+def index_device(t_body, orig_size, marker=FIXED_MARKER, known_mask=L.NATIVE_MASK):
+    """package table built on the GPU -> (uint8 device tensor of 32-byte entries, n entries, covered bytes)"""
     lib = require_cuda()
-    if body_host is None:
-        body_host = t_body.cpu().numpy()
-    table, _ = index_host(body_host, orig_size, marker, known_mask)
+    ne, cov = C.c_uint64(0), C.c_uint64(0)
+    ptr = C.c_void_p(t_body.data_ptr() if t_body.numel() else 0)
+    L.check(lib.ambc_index_dev(ptr, t_body.numel(), marker, len(marker), orig_size, known_mask, None, 0,
+                               C.byref(ne), C.byref(cov), _stream_ptr()))
+    t_table = torch.empty(max(ne.value, 1) * 32, dtype=torch.uint8, device="cuda")
+    if ne.value:
+        L.check(lib.ambc_index_dev(ptr, t_body.numel(), marker, len(marker), orig_size, known_mask,
+                                   C.c_void_p(t_table.data_ptr()), ne.value, C.byref(ne), C.byref(cov), _stream_ptr()))
+    return t_table, ne.value, cov.value
+
+
+def decompress_device(t_body, orig_size, marker=FIXED_MARKER, known_mask=L.NATIVE_MASK, body_host=None, out=None,
+                      gpu_index=None):
+    """device body -> (device output tensor, status [codec errors, length mismatches]).
+    The package table comes from the GPU index (default when no host copy of the body is given)
+    or from the host walk."""
+    lib = require_cuda()
+    if gpu_index is None:
+        gpu_index = body_host is None
     if out is None or out.numel() < orig_size:
         out = torch.empty(max(orig_size, 1), dtype=torch.uint8, device="cuda")
     status = torch.zeros(2, dtype=torch.int32, device="cuda")
-    t_table = torch.from_numpy(table.view(np.uint8).reshape(-1).copy()).to("cuda") if len(table) else \
-        torch.empty(0, dtype=torch.uint8, device="cuda")
+    if gpu_index:
+        t_table, n_table, _ = index_device(t_body, orig_size, marker, known_mask)
+        table = range(n_table)
+    else:
+        if body_host is None:
+            body_host = t_body.cpu().numpy()
+        table, _ = index_host(body_host, orig_size, marker, known_mask)
+        t_table = torch.from_numpy(table.view(np.uint8).reshape(-1).copy()).to("cuda") if len(table) else \
+            torch.empty(0, dtype=torch.uint8, device="cuda")
     L.check(lib.ambc_decompress_dev(C.c_void_p(t_body.data_ptr() if t_body.numel() else 0), t_body.numel(),
                                     C.c_void_p(t_table.data_ptr() if len(table) else 0), len(table),
                                     C.c_void_p(out.data_ptr()), orig_size, C.c_void_p(status.data_ptr()),

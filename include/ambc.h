@@ -155,6 +155,17 @@ int ambc_index_host(const uint8_t *body, uint64_t body_len, const uint8_t *marke
                     uint64_t *n_entries, uint64_t *out_bytes);
 
 /*
+ * The same table built on the GPU from a device-resident body (no host copy of the body needed):
+ * marker scan, header parse, successor links, pointer jumping from position 0, placement scans.
+ * Only positions reachable from position 0 become packages, exactly as in the serial walk; a marker
+ * mismatch the walk would hit returns AMBC_E_MARKER.  table_dev may be NULL to obtain *n_entries
+ * first.  Synchronises `stream`.
+ */
+int ambc_index_dev(const void *body_dev, uint64_t body_len, const uint8_t *marker, uint32_t marker_bytes,
+                   uint64_t orig_size, uint32_t known_mask, ambc_pkg *table_dev, uint64_t table_cap,
+                   uint64_t *n_entries, uint64_t *out_bytes, void *stream);
+
+/*
  * Decode every table entry into out_dev (orig_size bytes; zero padded / truncated
  * as adaptive_compressor.py:447-452).  status_dev (optional, uint32[2]):
  * [0] = entries whose codec raised (output zero-filled, :440-442),
