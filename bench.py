@@ -81,12 +81,24 @@ def cpu_port_run(sample_bytes, steps, warmup, threads):
     return {"compress_s": tc / steps, "decompress_s": td / steps, "bytes": sample_bytes}
 
 
+def cpu_sample_bytes(args, threads, budget_s=10.0):
+    """bytes per CPU pass: --cpu-sample-mib when given, else calibrated on 8 MiB so that one pass takes
+    about `budget_s` seconds on this box's host cores (16 MiB .. 512 MiB, whole 16 MiB units)"""
+    if args.cpu_sample_mib:
+        return args.cpu_sample_mib << 20
+    r = cpu_port_run(8 << 20, 1, 0, threads)
+    rate = (8 << 20) / (r["compress_s"] + r["decompress_s"])
+    mib = int(rate * budget_s) >> 20
+    return max(16, min(512, mib // 16 * 16)) << 20
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = args.cpu_sample_mib << 20
+    sample = cpu_sample_bytes(args, threads)
+    args.cpu_sample_mib = sample >> 20
     r = cpu_port_run(sample, max(1, args.steps), min(args.warmup, 1), threads)
     t = r["compress_s"] + r["decompress_s"]
     value = sample / t / 1e9
@@ -373,6 +385,7 @@ def run_b200(args):
         }
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
+            args.cpu_sample_mib = cpu_sample_bytes(args, threads) >> 20
             r = cpu_port_run(args.cpu_sample_mib << 20, 1, 0, threads)
             v = (args.cpu_sample_mib << 20) / (r["compress_s"] + r["decompress_s"]) / 1e9
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
@@ -393,7 +406,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size-mib", type=int, default=1024)
-    ap.add_argument("--cpu-sample-mib", type=int, default=16)
+    ap.add_argument("--cpu-sample-mib", type=int, default=0,
+                    help="MiB of the corpus the CPU legs process per pass (0 = calibrate to ~10 s per pass)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--traffic", type=float, default=None,
                     help="dram bytes per k_select launch from the committed ncu capture (profiles/)")
