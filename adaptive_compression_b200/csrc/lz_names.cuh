@@ -139,7 +139,7 @@ __device__ inline void lz2_level3(ChunkCtx &c, uint16_t *tmp)
     const uint16_t *list3 = (const uint16_t *)c.L;
     const int cnt = c.red[30];
     int tbits = 10; // table sized to the list (load factor <= 1/2)
-    while ((1 << tbits) < 2 * cnt && tbits < 13) tbits++;
+    while ((1 << tbits) < 4 * cnt && tbits < 13) tbits++;
     lz2_clear(c, 1 << tbits);
     __syncthreads();
     for (int i = tid; i < cnt; i += AMBC_BLOCK) {
@@ -269,6 +269,9 @@ __device__ inline bool lz2_refine_flat(ChunkCtx &c, const uint16_t *S, int k, in
 // ancestor length cannot match above it), so mlen / mpos are written without atomics.
 // Returns 0 = done, 1 = a list would overflow (caller rebuilds the participant list and runs the flat
 // method).  Lists: three arrays of LZ2_LISTCAP items in c.L.
+#ifndef LZ2_LOADINV
+#define LZ2_LOADINV 4  // table slots per entry in the refinement rounds (1/4 load: measured best of 2..4)
+#endif
 #define LZ2_LISTCAP 5461
 __device__ inline int lz2_refine_binary_dense(ChunkCtx &c, const uint16_t *S, int k, int np)
 {
@@ -281,7 +284,7 @@ __device__ inline int lz2_refine_binary_dense(ChunkCtx &c, const uint16_t *S, in
         if (E == 0) return 0;
         // table of this round: the smallest power of two with load factor <= 1/2 (E < slot count always)
         int tbits = 10;
-        while ((1 << tbits) < 2 * E && tbits < 13) tbits++;
+        while ((1 << tbits) < LZ2_LOADINV * E && tbits < 13) tbits++;
         const uint32_t tmask = (1u << tbits) - 1u;
         const int tshift = 32 - tbits;
         lz2_clear(c, 1 << tbits);
