@@ -159,8 +159,8 @@ def test_host_buffer_abi(tmp_path):
     assert (back == data).all() and list(st) == [0, 0]
 
 
-@pytest.mark.parametrize("kind_mask", [0b1011111, 0b1111111])
-def test_host_buffer_abi_pipelined(kind_mask):
+@pytest.mark.parametrize("kind_mask,chunk", [(0b1011111, 4096), (0b1111111, 4096), (0b1011111, 1024), (0b1111111, 3000)])
+def test_host_buffer_abi_pipelined(kind_mask, chunk):
     """multi-piece pipelines of the host-buffer calls (64 MiB upload pieces overlapping k_select,
     16384-package decode pieces overlapping the host walk): same body as the device-resident path,
     bit-exact round trip; kind_mask with the random kind exercises the rest-of-file-raw rule"""
@@ -172,13 +172,13 @@ def test_host_buffer_abi_pipelined(kind_mask):
     lib = engine.require_cuda()
     n = (150 << 20) + 12345
     t = engine.synth(n, 0, kind_mask=kind_mask)
-    dev = engine.compress_device(t, 4096)
+    dev = engine.compress_device(t, chunk)
     want = dev.body.cpu().numpy()
     data = t.cpu().numpy()
-    bound = lib.ambc_compress_bound(n, 4096, 4)
+    bound = lib.ambc_compress_bound(n, chunk, 4)
     body = np.empty(bound, dtype=np.uint8)
     res = L.CompressResult()
-    L.check(lib.ambc_compress_host(C.c_void_p(data.ctypes.data), n, 4096, L.NATIVE_MASK, 0, b"\xff\xff\x00\x00", 4,
+    L.check(lib.ambc_compress_host(C.c_void_p(data.ctypes.data), n, chunk, L.NATIVE_MASK, 0, b"\xff\xff\x00\x00", 4,
                                    C.c_void_p(body.ctypes.data), bound, None, None, C.byref(res)))
     assert res.body_len == dev.body_len and res.first_raw == dev.first_raw
     assert np.array_equal(body[:res.body_len], want)
