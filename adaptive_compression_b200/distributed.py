@@ -107,3 +107,67 @@ def merge_marker_flags(flags):
     """in-place byte-wise MAX all-reduce of a 2^L-byte presence-flag tensor"""
     dist.all_reduce(flags, op=dist.ReduceOp.MAX)
     return flags
+
+
+def carry_windows(lens, tails):
+    """lens[r] = bytes in shard r, tails[r] = its last min(4, lens[r]) bytes.  -> for every rank the
+    (up to) 4 bytes that precede its shard in the global stream and how many exist, plus the same for
+    the end of the whole stream.  Shards may be shorter than 4 bytes (or empty)."""
+    out, window, before = [], b"", 0
+    for n, t in zip(lens, tails):
+        out.append((window, before))
+        window = (window + bytes(t))[-4:]
+        before += int(n)
+    return out, (window, before)
+
+
+def _bits_of(window, before_bytes, want_bits):
+    """the last min(want_bits, 8 * before_bytes) bits of the stream ending with `window`, as (value, count)"""
+    have = min(want_bits, 8 * min(before_bytes, len(window)))
+    v = int.from_bytes(window, "big") if window else 0
+    return (v & ((1 << have) - 1)) if have else 0, have
+
+
+def find_marker_sharded(t_shard, max_len=32, levels=(16, 24)):
+    """MarkerFinder.find_marker (marker_finder.py:22-123) over a stream sharded across the ranks in rank
+    order: every rank flags the L-bit windows that start in its shard (with the <= L-1 bits that precede
+    it as carry), one byte-wise MAX all-reduce merges the flags (NCCL has no bitwise OR), every rank
+    picks the same (marker bytes, length).  Raises ValueError when no marker of at most
+    min(max_len, levels[-1]) bits exists."""
+    import ctypes as C
+    from . import _lib as L
+    from . import engine
+    lib = engine.require_cuda()
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n_local = t_shard.numel()
+    dev = t_shard.device
+    meta = torch.zeros(5, dtype=torch.int64, device=dev)
+    meta[0] = n_local
+    k = min(4, n_local)
+    if k:
+        meta[1:1 + k] = t_shard[n_local - k:].to(torch.int64)
+    allm = torch.empty(5 * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allm, meta)
+    rows = allm.view(world, 5).cpu().tolist()
+    lens = [int(r[0]) for r in rows]
+    tails = [bytes(int(x) for x in r[1:1 + min(4, int(r[0]))]) for r in rows]
+    per_rank, (end_window, total_bytes) = carry_windows(lens, tails)
+    window, before = per_rank[rank]
+    total_bits = 8 * total_bytes
+    tail, tail_bits = _bits_of(end_window, total_bytes, 31)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for lv in levels:
+        Lb = min(lv, max_len)
+        flags = torch.zeros(1 << Lb, dtype=torch.uint8, device=dev)
+        carry, cb = _bits_of(window, before, Lb - 1)
+        L.check(lib.ambc_marker_flags_dev(C.c_void_p(t_shard.data_ptr() if n_local else 0), n_local, Lb, carry, cb,
+                                          C.c_void_p(flags.data_ptr()), stream))
+        merge_marker_flags(flags)
+        ln, val = C.c_uint32(0), C.c_uint64(0)
+        rc = lib.ambc_marker_pick_dev(C.c_void_p(flags.data_ptr()), Lb, max_len, total_bits, tail, tail_bits,
+                                      C.byref(ln), C.byref(val), stream)
+        if rc == L.OK:
+            return engine.marker_bytes(val.value, ln.value), ln.value
+        if rc != L.E_NO_MARKER or Lb == max_len:
+            L.check(rc)
+    raise ValueError("Could not find a marker of length <= %d bits" % min(max_len, levels[-1]))

@@ -216,10 +216,12 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    # stdout carries exactly one JSON line: anything libraries print meanwhile (the NCCL version banner
+    # at the first collective, for one) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # NCCL prints its version banner to stdout at VERSION level; stdout carries the one JSON line
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = engine.require_cuda()
     n = args.size_mib << 20
@@ -342,6 +344,23 @@ def run_b200(args):
         dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
     te = te_t.item()
 
+    # sharded marker search (MarkerFinder.find_marker over the whole N-shard stream): per-shard flags,
+    # one NCCL MAX all-reduce, same pick on every rank.  Not part of `value` (a separate API).
+    marker_info = None
+    if world > 1:
+        try:
+            mev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            D.find_marker_sharded(t_in, 32)
+            barrier()
+            mev[0].record()
+            mk, mk_bits = D.find_marker_sharded(t_in, 32)
+            mev[1].record()
+            torch.cuda.synchronize()
+            marker_info = {"marker_hex": mk.hex(), "bits": mk_bits, "ms": mev[0].elapsed_time(mev[1]),
+                           "collective": "1 x all_gather(40 B/rank) + 1 x all_reduce(MAX, 2^16 B flags) over NCCL"}
+        except Exception as e:  # noqa: BLE001
+            marker_info = {"error": str(e)[:200]}
+
     if rank == 0:
         peaks = {}
         pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -383,6 +402,8 @@ def run_b200(args):
                             "~0.6 GB/s/core, identical in both arms) is outside the chunk path"},
             "gpu_launches": int(launches), "clocks": clocks.summary(),
         }
+        if marker_info is not None:
+            line["marker_search"] = marker_info
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
             args.cpu_sample_mib = cpu_sample_bytes(args, threads) >> 20
@@ -394,7 +415,10 @@ def run_b200(args):
                                     "sample": "first %d MiB of the same corpus, one pass; C restatement of the reference "
                                               "(oracle/), %d threads; the Python reference itself runs at ~7 KB/s on one "
                                               "core (BASELINE.md §2)" % (args.cpu_sample_mib, threads)}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 

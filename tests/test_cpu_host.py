@@ -113,3 +113,24 @@ def test_synth_numpy_twin_is_seekable():
     assert (a[123457:124457] == b).all()
     kinds = {synth_ref.seg_kind(synth_ref.DEFAULT_SEED, s, synth_ref.DEFAULT_KINDS) for s in range(200)}
     assert kinds == {0, 1, 2, 3, 4, 6}
+
+
+def test_marker_carry_windows():
+    """bits that precede each shard (and end the stream) from per-shard lengths and 4-byte tails == slicing
+    the concatenated stream, also for shards shorter than 4 bytes and empty shards"""
+    from adaptive_compression_b200 import distributed as D
+    r = np.random.RandomState(3)
+    for _ in range(200):
+        shards = [bytes(r.randint(0, 256, size=int(r.choice([0, 1, 2, 3, 4, 5, 9, 40]))).astype(np.uint8)) for _ in range(int(r.randint(1, 6)))]
+        whole = b"".join(shards)
+        bits = "".join(format(b, "08b") for b in whole)
+        per, end = D.carry_windows([len(s) for s in shards], [s[-4:] for s in shards])
+        pos = 0
+        for s, (w, before) in zip(shards, per):
+            assert before == pos and w == whole[:pos][-4:]
+            for want in (1, 7, 15, 23, 31):
+                v, have = D._bits_of(w, before, want)
+                assert have == min(want, 8 * pos) and (have == 0 or v == int(bits[8 * pos - have:8 * pos], 2))
+            pos += len(s)
+        v, have = D._bits_of(end[0], end[1], 31)
+        assert end[1] == len(whole) and have == min(31, 8 * len(whole)) and (have == 0 or v == int(bits[-have:], 2))
