@@ -9,7 +9,7 @@
 // Dictionary packages decoded one warp per package by k_decode_lz (see below)
 __device__ __forceinline__ bool dlz_eligible(const ambc_pkg &e)
 {
-    return e.type == 2 && e.comp_len <= DLZ_MAX_COMP && e.orig_len <= 4096;
+    return e.type == 2 && e.comp_len <= DLZ_MAX_COMP && e.orig_len <= 8192;
 }
 
 
@@ -214,18 +214,19 @@ k_decode(const uint8_t *__restrict__ body, const ambc_pkg *__restrict__ table, u
     }
 }
 
+template <int OUTCAP> // DLZ_OUT: packages of at most 4096 bytes; DLZ_OUT_BIG: 4097 .. 8192
 __global__ void __launch_bounds__(DLZ_WARPS * 32)
 k_decode_lz(const uint8_t *__restrict__ body, const ambc_pkg *__restrict__ table, uint64_t n_entries,
             uint8_t *__restrict__ out, uint32_t *status)
 {
     extern __shared__ uint4 smem4[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t *buf = (uint8_t *)smem4 + (size_t)w * DLZ_OUT;
+    uint8_t *buf = (uint8_t *)smem4 + (size_t)w * OUTCAP;
     for (uint64_t i = (uint64_t)blockIdx.x * DLZ_WARPS + w; i < n_entries; i += (uint64_t)gridDim.x * DLZ_WARPS) {
         const ambc_pkg e = table[i];
-        if (!dlz_eligible(e)) continue;
+        if (!dlz_eligible(e) || (e.orig_len <= 4096) != (OUTCAP == DLZ_OUT)) continue;
         uint8_t *dst = out + e.dst_off;
-        const int produced = dec_lz_warp(body + e.src_off, (int)e.comp_len, (int)e.orig_len, buf);
+        const int produced = dec_lz_warp(body + e.src_off, (int)e.comp_len, (int)e.orig_len, buf, OUTCAP);
         const uint32_t nominal = e.comp_len == 0 ? 0 : e.orig_len;
         uint32_t good = produced < 0 ? 0u : min((uint32_t)produced, e.out_len);
         // smem -> global, 16-byte stores when the destination allows
@@ -263,10 +264,11 @@ int ambc_decode_launch(const void *body_dev, const ambc_pkg *table_dev, uint64_t
     const int in_cap = DEC_OUT_CAP; // payloads the reference's encoder emits are < orig_len <= 8192
     size_t smem = decctx_smem_bytes(in_cap);
     static bool attr_done = false;
-    size_t lsmem = (size_t)DLZ_WARPS * DLZ_OUT;
+    size_t lsmem = (size_t)DLZ_WARPS * DLZ_OUT, lsmem_big = (size_t)DLZ_WARPS * DLZ_OUT_BIG;
     if (!attr_done) {
         CUDA_TRY(cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(k_decode_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
+        CUDA_TRY(cudaFuncSetAttribute(k_decode_lz<DLZ_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
+        CUDA_TRY(cudaFuncSetAttribute(k_decode_lz<DLZ_OUT_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem_big));
         attr_done = true;
     }
     // the two decoders touch disjoint packages: k_decode_lz runs on a side stream, forked from and
@@ -284,8 +286,11 @@ int ambc_decode_launch(const void *body_dev, const ambc_pkg *table_dev, uint64_t
     CUDA_TRY(cudaEventRecord(ev_fork[dev], stream));
     CUDA_TRY(cudaStreamWaitEvent(side[dev], ev_fork[dev], 0));
     unsigned lgrid = (unsigned)min<uint64_t>((n_entries + DLZ_WARPS - 1) / DLZ_WARPS, 148ull * 24);
-    k_decode_lz<<<lgrid, DLZ_WARPS * 32, lsmem, side[dev]>>>((const uint8_t *)body_dev, table_dev, n_entries,
-                                                            (uint8_t *)out_dev, status_dev);
+    k_decode_lz<DLZ_OUT><<<lgrid, DLZ_WARPS * 32, lsmem, side[dev]>>>((const uint8_t *)body_dev, table_dev, n_entries,
+                                                                     (uint8_t *)out_dev, status_dev);
+    k_decode_lz<DLZ_OUT_BIG><<<lgrid, DLZ_WARPS * 32, lsmem_big, side[dev]>>>((const uint8_t *)body_dev, table_dev, n_entries,
+                                                                             (uint8_t *)out_dev, status_dev);
+    ambc_count_launch();
     ambc_count_launch();
     CUDA_TRY(cudaEventRecord(ev_join[dev], side[dev]));
     unsigned grid = (unsigned)min<uint64_t>(n_entries, 0x7fffffffull);

@@ -147,7 +147,8 @@ __device__ inline int lz_walk(const uint8_t *in, long len, long orig, uint8_t *o
 }
 
 #define DLZ_WARPS 8
-#define DLZ_OUT (4096 + 512)
+#define DLZ_OUT (4096 + 512)        // per-warp output buffer, packages of at most 4096 bytes
+#define DLZ_OUT_BIG (8192 + 512)    // packages of 4097 .. 8192 bytes
 #define DLZ_MAX_COMP 8192
 
 // ---- warp-per-package Dictionary decode ----------------------------------------------------
@@ -172,7 +173,7 @@ __device__ __forceinline__ uint32_t dlz_skipped(uint32_t M, uint32_t &carry)
 }
 
 // returns bytes produced (before truncation to `cap` by the caller) or -1; out = this warp's buffer
-__device__ int dec_lz_warp(const uint8_t *__restrict__ in, int len, int orig, uint8_t *out)
+__device__ int dec_lz_warp(const uint8_t *__restrict__ in, int len, int orig, uint8_t *out, int out_cap = DLZ_OUT)
 {
     if (len <= 0) return 0;
     const int lane = threadIdx.x & 31;
@@ -244,7 +245,7 @@ __device__ int dec_lz_warp(const uint8_t *__restrict__ in, int len, int orig, ui
     int result;
     if (irregular) {
         int r = 0;
-        if (lane == 0) r = lz_walk(in, len, orig, out, DLZ_OUT);
+        if (lane == 0) r = lz_walk(in, len, orig, out, out_cap);
         result = __shfl_sync(FULL_MASK, r, 0);
     } else {
         if (!stop) { // the last <= 3 bytes: incomplete tokens, serial rules
@@ -255,7 +256,7 @@ __device__ int dec_lz_warp(const uint8_t *__restrict__ in, int len, int orig, ui
                 while (pos < len && oo < orig) {
                     uint8_t flag = in[pos++];
                     if (flag == 0) {
-                        if (pos < len) { uint8_t vb = in[pos++]; if (oo < DLZ_OUT) out[oo] = vb; oo++; }
+                        if (pos < len) { uint8_t vb = in[pos++]; if (oo < out_cap) out[oo] = vb; oo++; }
                     } else if (pos + 2 < len) {
                         r = -2; break; // cannot happen: a complete match token lies in the full region
                     }
@@ -265,7 +266,7 @@ __device__ int dec_lz_warp(const uint8_t *__restrict__ in, int len, int orig, ui
             o = __shfl_sync(FULL_MASK, r, 0);
             if (o == -2) {
                 int r2 = 0;
-                if (lane == 0) r2 = lz_walk(in, len, orig, out, DLZ_OUT);
+                if (lane == 0) r2 = lz_walk(in, len, orig, out, out_cap);
                 o = __shfl_sync(FULL_MASK, r2, 0);
                 __syncwarp();
                 return o;
@@ -280,9 +281,9 @@ __device__ int dec_lz_warp(const uint8_t *__restrict__ in, int len, int orig, ui
 __device__ inline int dec_lz(DecCtx &d, int len, int orig)
 {
     volatile int *res = d.red;
-    if (orig <= 4096) { // warp 0 decodes, same code as k_decode_lz
+    if (orig <= DEC_OUT_CAP) { // warp 0 decodes, same code as k_decode_lz
         if (threadIdx.x < 32) {
-            int r = dec_lz_warp(d.in, len, orig, d.out);
+            int r = dec_lz_warp(d.in, len, orig, d.out, DEC_OUT_CAP + DEC_OUT_SLACK);
             if (threadIdx.x == 0) res[24] = r;
         }
     } else if (threadIdx.x == 0) res[24] = lz_walk(d.in, len, orig, d.out, DEC_OUT_CAP + DEC_OUT_SLACK);
