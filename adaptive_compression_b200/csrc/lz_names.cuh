@@ -138,8 +138,7 @@ __device__ inline void lz2_level3(ChunkCtx &c, uint16_t *tmp)
     const int tid = threadIdx.x;
     const uint16_t *list3 = (const uint16_t *)c.L;
     const int cnt = c.red[30];
-    int tbits = 10; // table sized to the list (load factor <= 1/2)
-    while ((1 << tbits) < 4 * cnt && tbits < 13) tbits++;
+    const int tbits = min(13, max(10, 32 - __clz(max(4 * cnt, 2) - 1))); // table sized to the list (load <= 1/4)
     lz2_clear(c, 1 << tbits);
     __syncthreads();
     for (int i = tid; i < cnt; i += AMBC_BLOCK) {
@@ -283,8 +282,7 @@ __device__ inline int lz2_refine_binary_dense(ChunkCtx &c, const uint16_t *S, in
     for (int step = k >> 1; step >= 1; step >>= 1) {
         if (E == 0) return 0;
         // table of this round: the smallest power of two with load factor <= 1/2 (E < slot count always)
-        int tbits = 10;
-        while ((1 << tbits) < LZ2_LOADINV * E && tbits < 13) tbits++;
+        const int tbits = min(13, max(10, 32 - __clz(LZ2_LOADINV * E - 1))); // smallest power of two >= LOADINV * E
         const uint32_t tmask = (1u << tbits) - 1u;
         const int tshift = 32 - tbits;
         lz2_clear(c, 1 << tbits);
