@@ -280,8 +280,9 @@ class AdaptiveCompressor:
         body = cdata[hdr["header_size"]:]
         known = engine.method_mask([m.type_id for m in self.compression_methods if m.type_id != 255])
         t_body = torch.from_numpy(body).to("cuda") if body.size else torch.empty(0, dtype=torch.uint8, device="cuda")
+        # package index on the GPU (ambc_index_dev); the host walk (engine.index_host) gives the same table
         out, status = engine.decompress_device(t_body, hdr["original_size"], self.marker_bytes_aligned, known,
-                                               body_host=body)
+                                               gpu_index=True)
         decompressed = out.cpu().numpy()
         decompressed.tofile(output_file)
         self.last_status = status
