@@ -112,7 +112,7 @@ struct HostCtx {
     cudaEvent_t done_ev[AMBC_MAX_PIECES] = {};
     void *states = nullptr; // pinned scan states, one per piece
     bool ring_used[4] = {false, false, false, false};
-    std::vector<ambc_pkg> host_table;
+    void *table_host = nullptr; // pinned ring of table pieces (ambc_decompress_host)
 };
 int ambc_index_vector(const uint8_t *body, uint64_t body_len, const uint8_t *marker, uint32_t mb, uint64_t orig_size,
                       uint32_t known_mask, std::vector<ambc_pkg> &v, uint64_t *n_entries, uint64_t *out_bytes);
@@ -210,27 +210,52 @@ int ambc_decode_launch(const void *body_dev, const ambc_pkg *table_dev, uint64_t
 // state of the piece-wise decode that runs while the host walks the package chain
 struct DecPipe {
     HostCtx *c;
+    const uint8_t *body_host;
     uint8_t *out_host;
-    uint64_t piece_entries, filled = 0, flushed_entries = 0;
+    uint64_t body_len, uploaded = 0; // body bytes whose upload has been queued on the copy stream
+    uint64_t filled = 0, flushed_entries = 0;
     int rc = AMBC_OK;
-    int ev = 0, ring = 0;
+    int ev = 0, ring = 0, up = 0;
 };
 #define DEC_PIECE_ENTRIES 16384
-#define DEC_RING 4 // device table pieces in flight
+#define DEC_RING 4                     // table pieces in flight (pinned host + device copies)
+#define DEC_BODY_PIECE (16ull << 20)   // body upload granule
+#define DEC_BODY_AHEAD (32ull << 20)   // body bytes queued ahead of the walk
+
+// queue body uploads until at least `upto` bytes (capped at the body) are on their way
+static void decpipe_upload(DecPipe &d, uint64_t upto)
+{
+    HostCtx *c = d.c;
+    if (upto > d.body_len) upto = d.body_len;
+    while (d.uploaded < upto && !d.rc) {
+        uint64_t nb = min<uint64_t>(DEC_BODY_PIECE, d.body_len - d.uploaded);
+        cudaError_t e = cudaMemcpyAsync((uint8_t *)c->in.p + d.uploaded, d.body_host + d.uploaded, nb,
+                                        cudaMemcpyHostToDevice, c->copy);
+        if (e != cudaSuccess) { d.rc = ambc_fail(AMBC_E_CUDA, "body upload: %s", cudaGetErrorString(e)); return; }
+        d.uploaded += nb;
+    }
+}
 
 static void decpipe_flush(DecPipe &d)
 {
     if (d.rc || d.filled == 0) return;
     HostCtx *c = d.c;
-    // ring of device table pieces: slot r is free again once the kernels of its previous piece ran
+    // ring slot r (pinned host piece + its device copy) is free again once the kernels of its previous piece ran
+    const ambc_pkg *src = (const ambc_pkg *)c->table_host + (uint64_t)d.ring * DEC_PIECE_ENTRIES;
     ambc_pkg *tab_dev = (ambc_pkg *)c->table.p + (uint64_t)d.ring * DEC_PIECE_ENTRIES;
-    if (c->ring_used[d.ring]) cudaEventSynchronize(c->ring_ev[d.ring]);
-    const ambc_pkg *src = c->host_table.data();
-    cudaError_t e = cudaMemcpyAsync(tab_dev, src, d.filled * sizeof(ambc_pkg), cudaMemcpyHostToDevice, c->stream);
+    // copy stream, in order: the body bytes these packages read (plus some ahead), then their table piece
+    const uint64_t need = src[d.filled - 1].src_off + src[d.filled - 1].comp_len;
+    decpipe_upload(d, need + DEC_BODY_AHEAD);
+    if (d.rc) return;
+    cudaError_t e = cudaMemcpyAsync(tab_dev, src, d.filled * sizeof(ambc_pkg), cudaMemcpyHostToDevice, c->copy);
     if (e != cudaSuccess) { d.rc = ambc_fail(AMBC_E_CUDA, "table upload: %s", cudaGetErrorString(e)); return; }
+    cudaEvent_t up = c->done_ev[d.up];
+    d.up = (d.up + 1) % AMBC_MAX_PIECES;
+    cudaEventRecord(up, c->copy);
+    cudaStreamWaitEvent(c->stream, up, 0);
     d.rc = ambc_decode_launch(c->in.p, tab_dev, d.filled, c->out.p, (uint32_t *)c->status.p, c->stream);
     if (d.rc) return;
-    // results of this piece go home on the copy stream while the walk and the next kernels continue
+    // results of this piece go home on the download stream while the walk and the next kernels continue
     const uint64_t d0 = src[0].dst_off, d1 = src[d.filled - 1].dst_off + src[d.filled - 1].out_len;
     cudaEvent_t ev = c->piece_ev[d.ev];
     d.ev = (d.ev + 1) % AMBC_MAX_PIECES;
@@ -243,14 +268,16 @@ static void decpipe_flush(DecPipe &d)
     if (e != cudaSuccess) { d.rc = ambc_fail(AMBC_E_CUDA, "result download: %s", cudaGetErrorString(e)); return; }
     d.flushed_entries += d.filled;
     d.filled = 0;
+    // the next piece is written into the next ring slot: wait until the GPU is done with it
+    if (c->ring_used[d.ring]) cudaEventSynchronize(c->ring_ev[d.ring]);
 }
 
 static void decpipe_sink(void *user, const ambc_pkg &e)
 {
     DecPipe &d = *(DecPipe *)user;
     if (d.rc) return;
-    d.c->host_table[d.filled++] = e;
-    if (d.filled == d.piece_entries) decpipe_flush(d);
+    ((ambc_pkg *)d.c->table_host)[(uint64_t)d.ring * DEC_PIECE_ENTRIES + d.filled++] = e;
+    if (d.filled == DEC_PIECE_ENTRIES) decpipe_flush(d);
 }
 
 
@@ -264,27 +291,32 @@ extern "C" int ambc_decompress_host(const void *body_host, uint64_t body_len, co
     if (rc) return rc;
     if (!marker || marker_bytes < 1 || marker_bytes > 4) return ambc_fail(AMBC_E_ARG, "ambc_decompress_host: bad marker");
     uint64_t ne = 0, covered = 0;
-    // the body upload, the host walk of the package chain, the decode kernels and the download of
-    // finished pieces all overlap: the walk hands DEC_PIECE_ENTRIES packages at a time to the GPU
+    // the body upload (in DEC_BODY_PIECE granules, a little ahead of the walk), the host walk of the package
+    // chain, the decode kernels and the download of finished pieces all overlap: the walk hands
+    // DEC_PIECE_ENTRIES packages at a time to the GPU, which needs only the body bytes up to their end
     if ((rc = c->in.ensure(body_len + 64))) return rc;
     if ((rc = c->out.ensure(orig_size + 64))) return rc;
     if ((rc = c->status.ensure(64))) return rc;
     if ((rc = c->table.ensure((uint64_t)DEC_RING * DEC_PIECE_ENTRIES * sizeof(ambc_pkg) + 64))) return rc;
     for (int i = 0; i < DEC_RING; i++) c->ring_used[i] = false;
-    if (c->host_table.size() < DEC_PIECE_ENTRIES) c->host_table.resize(DEC_PIECE_ENTRIES);
-    if (body_len) CUDA_TRY(cudaMemcpyAsync(c->in.p, body_host, body_len, cudaMemcpyHostToDevice, c->stream));
+    if (!c->table_host &&
+        cudaMallocHost(&c->table_host, (uint64_t)DEC_RING * DEC_PIECE_ENTRIES * sizeof(ambc_pkg)) != cudaSuccess)
+        return ambc_fail(AMBC_E_CUDA, "cudaMallocHost failed");
     CUDA_TRY(cudaMemsetAsync(c->status.p, 0, 8, c->stream));
     DecPipe d;
-    d.c = c; d.out_host = (uint8_t *)out_host; d.piece_entries = DEC_PIECE_ENTRIES;
+    d.c = c; d.body_host = (const uint8_t *)body_host; d.out_host = (uint8_t *)out_host; d.body_len = body_len;
+    decpipe_upload(d, DEC_BODY_AHEAD);
+    if (d.rc) return d.rc;
     rc = ambc_index_stream((const uint8_t *)body_host, body_len, marker, marker_bytes, orig_size, known_mask,
                            decpipe_sink, &d, &ne, &covered);
     if (!rc) { decpipe_flush(d); rc = d.rc; }
-    if (rc) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->d2h); return rc; }
+    if (rc) { cudaStreamSynchronize(c->copy); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->d2h); return rc; }
     if (covered < orig_size) { // zero pad (adaptive_compressor.py:447-449)
         memset((uint8_t *)out_host + covered, 0, orig_size - covered);
     }
     uint32_t st[2] = {0, 0};
     CUDA_TRY(cudaMemcpyAsync(st, c->status.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->copy));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->d2h));
     if (status) { status[0] = st[0]; status[1] = st[1]; }

@@ -2,6 +2,7 @@
 // Replaces AdaptiveCompressor._adaptive_decompress (adaptive_compressor.py:396-454).
 #include "ambc_internal.h"
 #include "decode_codec.cuh"
+#include <thread>
 #include <vector>
 
 #define RAW_PIECE 65536u
@@ -24,6 +25,61 @@ static inline uint64_t nominal_out(uint32_t type, bool known, uint32_t comp, uin
     }
 }
 
+// ---- speculative helpers of the host walk ---------------------------------------------------------
+// The chain is serial (pos += header + comp_len) and every step is a cache miss in a large body.
+// For bodies over 32 MiB, helper threads walk disjoint segments ahead of time: each looks for the
+// first plausible package header at or after its segment start and follows the chain from there,
+// recording (position, type, orig, comp).  A helper may start on a false marker, but as soon as the
+// real walk lands on a recorded position the two chains coincide from there on (the successor of a
+// position is a function of the bytes), so the real walk consumes the records instead of touching
+// the body.  Anything a helper cannot vouch for (marker mismatch, END, truncation) simply ends its
+// list; the real walk reaches that position itself and applies the reference's rule.
+struct WalkRec { uint64_t pos; uint32_t type, orig, comp; };
+static uint64_t g_walk_min_bytes = 32ull << 20; // bodies below this are walked by one thread
+static unsigned g_walk_threads = 0;             // 0 = hardware concurrency (at most 8)
+// test knob (not part of include/ambc.h): lets small bodies exercise the helper threads
+extern "C" void ambc_set_walk_threads(uint64_t min_bytes, unsigned threads) { g_walk_min_bytes = min_bytes; g_walk_threads = threads; }
+
+static void spec_walk(const uint8_t *body, uint64_t len, const uint8_t *marker, uint32_t mb, uint64_t start, uint64_t stop,
+                      std::vector<WalkRec> *out)
+{
+    const uint64_t hdr = mb + 14;
+    uint64_t scan = start;
+    for (;;) {
+        // first plausible header: marker, a known-looking type, k == 0, used == orig, payload inside the body
+        uint64_t pos = scan;
+        for (; pos + hdr <= len && pos < stop; pos++) {
+            if (body[pos] != marker[0] || memcmp(body + pos, marker, mb) != 0) continue;
+            const uint8_t t = body[pos + mb];
+            uint32_t used, orig, comp;
+            memcpy(&used, body + pos + mb + 2, 4);
+            memcpy(&orig, body + pos + mb + 6, 4);
+            memcpy(&comp, body + pos + mb + 10, 4);
+            if ((t >= 1 && t <= 11) || t == 255)
+                if (body[pos + mb + 1] == 0 && used == orig && orig != 0 && pos + hdr + comp <= len) break;
+        }
+        if (pos + hdr > len || pos >= stop) return;
+        const uint64_t first = pos;
+        const size_t mark = out->size();
+        bool mismatch = false;
+        while (pos < stop && pos + hdr <= len) {
+            if (memcmp(body + pos, marker, mb) != 0) { mismatch = true; break; }
+            WalkRec r;
+            r.pos = pos;
+            r.type = body[pos + mb];
+            memcpy(&r.orig, body + pos + mb + 6, 4);
+            memcpy(&r.comp, body + pos + mb + 10, 4);
+            if (r.type == 0 || pos + hdr + r.comp > len) break;
+            out->push_back(r);
+            pos += hdr + r.comp;
+        }
+        // a chain that dies on a marker mismatch after a few steps started on marker bytes inside a
+        // payload: drop it and look for the next plausible header
+        if (mismatch && out->size() - mark < 4) { out->resize(mark); scan = first + 1; continue; }
+        return;
+    }
+}
+
 // the walk itself; emit(entry) returns false when the caller's table is full
 template <class Emit>
 static int index_walk(const uint8_t *body, uint64_t body_len, const uint8_t *marker, uint32_t mb, uint64_t orig_size,
@@ -32,17 +88,28 @@ static int index_walk(const uint8_t *body, uint64_t body_len, const uint8_t *mar
     if (!marker || mb < 1 || mb > 4 || (body_len && !body)) return ambc_fail(AMBC_E_ARG, "ambc_index_host: bad argument");
     uint64_t pos = 0, o = 0, ne = 0;
     const uint64_t hdr = mb + 14;
-    while (pos < body_len) {
-        if (pos + hdr > body_len) break;                            // :400-403
-        if (memcmp(body + pos, marker, mb) != 0)                    // :405-407
-            return ambc_fail(AMBC_E_MARKER, "Marker mismatch in chunk header.");
-        uint32_t type = body[pos + mb];
-        uint32_t orig, comp;
-        memcpy(&orig, body + pos + mb + 6, 4);
-        memcpy(&comp, body + pos + mb + 10, 4);
-        pos += hdr;
-        if (type == 0) break;                                       // :422-424
-        if (pos + comp > body_len) break;                           // :425-427
+
+    // helper threads for large bodies
+    unsigned T = 1;
+    if (body_len >= g_walk_min_bytes && body_len >= 64) {
+        T = g_walk_threads ? g_walk_threads : std::thread::hardware_concurrency();
+        T = T < 2 ? 1 : (T > 8 ? 8 : T);
+    }
+    std::vector<std::vector<WalkRec>> recs(T);
+    std::vector<std::thread> helpers;
+    std::vector<uint64_t> seg_start(T + 1, body_len);
+    for (unsigned t = 0; t < T; t++) seg_start[t] = body_len / T * t;
+    for (unsigned t = 1; t < T; t++)
+        helpers.emplace_back(spec_walk, body, body_len, marker, mb, seg_start[t], seg_start[t + 1], &recs[t]);
+    struct Joiner { std::vector<std::thread> &h; ~Joiner() { for (auto &x : h) if (x.joinable()) x.join(); } } joiner{helpers};
+    unsigned seg = 1;          // next helper segment the walk will enter
+    size_t ri = 0;             // cursor in recs[seg]
+    bool seg_joined = false;
+
+    int rc = AMBC_OK;
+    bool stop = false;
+    // one package with a verified header: entries, output offset, stop rule
+    auto process = [&](uint64_t payload, uint32_t type, uint32_t orig, uint32_t comp) {
         bool known = type == 255 || (type < 32 && ((known_mask >> type) & 1u));
         uint64_t nominal = nominal_out(type, known, comp, orig);
         uint64_t room = orig_size > o ? orig_size - o : 0;
@@ -55,25 +122,55 @@ static int index_walk(const uint8_t *body, uint64_t body_len, const uint8_t *mar
                     uint64_t piece = emitn - done < RAW_PIECE ? emitn - done : RAW_PIECE;
                     uint64_t have = comp > done ? comp - done : 0; // payload bytes left for this piece
                     ambc_pkg e;
-                    e.src_off = pos + done; e.dst_off = o + done;
+                    e.src_off = payload + done; e.dst_off = o + done;
                     e.comp_len = (uint32_t)(have < piece ? have : piece);
                     e.orig_len = (uint32_t)piece; e.type = 255; e.out_len = (uint32_t)piece;
-                    if (!emit(e, ne)) return ambc_fail(AMBC_E_CAPACITY, "ambc_index_host: table too small");
+                    if (!emit(e, ne)) { rc = ambc_fail(AMBC_E_CAPACITY, "ambc_index_host: table too small"); stop = true; return; }
                     ne++;
                     done += piece;
                 }
             } else {
                 ambc_pkg e;
-                e.src_off = pos; e.dst_off = o; e.comp_len = comp; e.orig_len = orig; e.type = type;
+                e.src_off = payload; e.dst_off = o; e.comp_len = comp; e.orig_len = orig; e.type = type;
                 e.out_len = (uint32_t)emitn;
-                if (!emit(e, ne)) return ambc_fail(AMBC_E_CAPACITY, "ambc_index_host: table too small");
+                if (!emit(e, ne)) { rc = ambc_fail(AMBC_E_CAPACITY, "ambc_index_host: table too small"); stop = true; return; }
                 ne++;
             }
         }
         o += nominal;
+        if (o >= orig_size) stop = true;                            // :444-445
+    };
+
+    while (pos < body_len && !stop) {
+        // inside a helper's segment: if the walk stands on a recorded position, take the helper's chain
+        while (seg < T && pos >= seg_start[seg + 1]) { seg++; ri = 0; seg_joined = false; }
+        if (seg < T && pos >= seg_start[seg]) {
+            if (!seg_joined) { helpers[seg - 1].join(); seg_joined = true; }
+            const std::vector<WalkRec> &R = recs[seg];
+            while (ri < R.size() && R[ri].pos < pos) ri++;
+            if (ri < R.size() && R[ri].pos == pos) {
+                while (ri < R.size() && !stop) {
+                    const WalkRec &r = R[ri++];
+                    process(r.pos + hdr, r.type, r.orig, r.comp);
+                    pos = r.pos + hdr + r.comp;
+                }
+                continue;
+            }
+        }
+        if (pos + hdr > body_len) break;                            // :400-403
+        if (memcmp(body + pos, marker, mb) != 0)                    // :405-407
+            return ambc_fail(AMBC_E_MARKER, "Marker mismatch in chunk header.");
+        uint32_t type = body[pos + mb];
+        uint32_t orig, comp;
+        memcpy(&orig, body + pos + mb + 6, 4);
+        memcpy(&comp, body + pos + mb + 10, 4);
+        pos += hdr;
+        if (type == 0) break;                                       // :422-424
+        if (pos + comp > body_len) break;                           // :425-427
+        process(pos, type, orig, comp);
         pos += comp;
-        if (o >= orig_size) break;                                  // :444-445
     }
+    if (rc) return rc;
     if (n_entries) *n_entries = ne;
     if (out_bytes) *out_bytes = o < orig_size ? o : orig_size;
     return AMBC_OK;

@@ -134,3 +134,79 @@ def test_marker_carry_windows():
             pos += len(s)
         v, have = D._bits_of(end[0], end[1], 31)
         assert end[1] == len(whole) and have == min(31, 8 * len(whole)) and (have == 0 or v == int(bits[-have:], 2))
+
+
+def _py_walk(body, orig_size, mb=4, marker=b"\xff\xff\x00\x00", known=(1, 2, 3, 4, 255)):
+    """plain restatement of adaptive_compressor.py:396-454's package walk -> ('ok', entries, covered) | ('marker',)"""
+    pos = o = 0
+    hdr = mb + 14
+    ent = []
+    while pos < len(body):
+        if pos + hdr > len(body):
+            break
+        if body[pos:pos + mb] != marker:
+            return ("marker",)
+        t = body[pos + mb]
+        orig = int.from_bytes(body[pos + mb + 6:pos + mb + 10], "little")
+        comp = int.from_bytes(body[pos + mb + 10:pos + mb + 14], "little")
+        pos += hdr
+        if t == 0 or pos + comp > len(body):
+            break
+        kn = t in known
+        nominal = comp if not kn else (orig if t == 255 else (0 if comp == 0 else (min(comp, orig) if t == 4 else orig)))
+        emit = min(nominal, max(0, orig_size - o))
+        if emit:
+            if not kn or t == 255:
+                done = 0
+                while done < emit:
+                    piece = min(65536, emit - done)
+                    have = max(0, comp - done)
+                    ent.append((pos + done, o + done, min(have, piece), piece, 255, piece))
+                    done += piece
+            else:
+                ent.append((pos, o, comp, orig, t, emit))
+        o += nominal
+        pos += comp
+        if o >= orig_size:
+            break
+    return ("ok", ent, min(o, orig_size))
+
+
+def test_index_host_helper_threads_match_serial_walk():
+    """the speculative helper threads of the host walk (large bodies) never change its result: well-formed,
+    corrupted and truncated bodies, marker bytes and fake headers inside payloads, 2..8 helpers"""
+    from adaptive_compression_b200 import engine, _lib as L
+    lib = L.lib()
+    r = np.random.RandomState(11)
+    mk = b"\xff\xff\x00\x00"
+    fake = mk + bytes([2, 0]) + (300).to_bytes(4, "little") * 2 + (40).to_bytes(4, "little")
+    parts, total = [], 0
+    for i in range(1500):
+        n = int(r.randint(1, 3000))
+        pay = bytearray(r.randint(0, 256, size=n).astype(np.uint8).tobytes())
+        if i % 7 == 0 and n > 60:
+            k = int(r.randint(0, n - 30)); pay[k:k + len(fake)] = fake[:max(0, min(len(fake), n - k))]
+        t = int(r.choice([255, 255, 255, 9]))
+        parts.append(mk + bytes([t, 0]) + n.to_bytes(4, "little") * 2 + n.to_bytes(4, "little") + bytes(pay))
+        total += n
+    body = b"".join(parts) + mk + b"\x00" * 12
+    variants = [(body, total), (body, total // 2), (body[:len(body) // 2 + 17], total), (body, total + 1000)]
+    for _ in range(12):
+        bad = bytearray(body); bad[int(r.randint(len(bad)))] ^= 1 << int(r.randint(8)); variants.append((bytes(bad), total))
+    # an END package and a marker mismatch in the middle
+    cut = sum(len(p) for p in parts[:700])
+    variants.append((body[:cut] + mk + b"\x00" * 12 + body[cut:], total))
+    bad = bytearray(body); bad[cut] ^= 0xFF; variants.append((bytes(bad), total))
+    try:
+        for threads in (2, 3, 8):
+            lib.ambc_set_walk_threads(1024, threads)
+            for b, osz in variants:
+                want = _py_walk(b, osz)
+                try:
+                    table, cov = engine.index_host(np.frombuffer(b, dtype=np.uint8), osz)
+                    got = ("ok", [tuple(int(e[k]) for k in ("src_off", "dst_off", "comp_len", "orig_len", "type", "out_len")) for e in table], cov)
+                except ValueError:
+                    got = ("marker",)
+                assert got == want, (threads, len(b), osz, got[0], want[0])
+    finally:
+        lib.ambc_set_walk_threads(32 << 20, 0)
