@@ -214,6 +214,7 @@ struct DecPipe {
     uint8_t *out_host;
     uint64_t body_len, uploaded = 0; // body bytes whose upload has been queued on the copy stream
     uint64_t filled = 0, flushed_entries = 0;
+    uint64_t piece_entries = 2048; // ramps up to DEC_PIECE_ENTRIES so the first download starts early
     int rc = AMBC_OK;
     int ev = 0, ring = 0, up = 0;
 };
@@ -243,9 +244,9 @@ static void decpipe_flush(DecPipe &d)
     // ring slot r (pinned host piece + its device copy) is free again once the kernels of its previous piece ran
     const ambc_pkg *src = (const ambc_pkg *)c->table_host + (uint64_t)d.ring * DEC_PIECE_ENTRIES;
     ambc_pkg *tab_dev = (ambc_pkg *)c->table.p + (uint64_t)d.ring * DEC_PIECE_ENTRIES;
-    // copy stream, in order: the body bytes these packages read (plus some ahead), then their table piece
+    // copy stream, in order: the body bytes these packages read, their table piece, then some body ahead
     const uint64_t need = src[d.filled - 1].src_off + src[d.filled - 1].comp_len;
-    decpipe_upload(d, need + DEC_BODY_AHEAD);
+    decpipe_upload(d, need);
     if (d.rc) return;
     cudaError_t e = cudaMemcpyAsync(tab_dev, src, d.filled * sizeof(ambc_pkg), cudaMemcpyHostToDevice, c->copy);
     if (e != cudaSuccess) { d.rc = ambc_fail(AMBC_E_CUDA, "table upload: %s", cudaGetErrorString(e)); return; }
@@ -253,6 +254,8 @@ static void decpipe_flush(DecPipe &d)
     d.up = (d.up + 1) % AMBC_MAX_PIECES;
     cudaEventRecord(up, c->copy);
     cudaStreamWaitEvent(c->stream, up, 0);
+    decpipe_upload(d, need + DEC_BODY_AHEAD);
+    if (d.rc) return;
     d.rc = ambc_decode_launch(c->in.p, tab_dev, d.filled, c->out.p, (uint32_t *)c->status.p, c->stream);
     if (d.rc) return;
     // results of this piece go home on the download stream while the walk and the next kernels continue
@@ -268,6 +271,7 @@ static void decpipe_flush(DecPipe &d)
     if (e != cudaSuccess) { d.rc = ambc_fail(AMBC_E_CUDA, "result download: %s", cudaGetErrorString(e)); return; }
     d.flushed_entries += d.filled;
     d.filled = 0;
+    if (d.piece_entries < DEC_PIECE_ENTRIES) d.piece_entries *= 2;
     // the next piece is written into the next ring slot: wait until the GPU is done with it
     if (c->ring_used[d.ring]) cudaEventSynchronize(c->ring_ev[d.ring]);
 }
@@ -277,7 +281,7 @@ static void decpipe_sink(void *user, const ambc_pkg &e)
     DecPipe &d = *(DecPipe *)user;
     if (d.rc) return;
     ((ambc_pkg *)d.c->table_host)[(uint64_t)d.ring * DEC_PIECE_ENTRIES + d.filled++] = e;
-    if (d.filled == DEC_PIECE_ENTRIES) decpipe_flush(d);
+    if (d.filled == d.piece_entries) decpipe_flush(d);
 }
 
 
