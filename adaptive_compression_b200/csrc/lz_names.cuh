@@ -38,14 +38,27 @@
 #endif
 #define LZ2_ISLOTS 8192          // slot memo entries
 
-// slot value = tag << 16 | position << 1 | single: the claiming insert stores single = 1, every
-// later arrival at the same key clears it (atomicMin with an even value, or atomicAnd)
+// slot value = tag << 14 | home << 13 | position << 1 | single: the claiming insert stores single = 1,
+// every later arrival at the same key clears it (atomicMin with an even value, or atomicAnd).
+// Pair tables hold their keys exactly: a table of 2^tbits slots takes keys below 2^W, W = tbits + 18;
+// h = lz2_hash(key) is a bijection on W-bit values, its top tbits are the home slot and its low 18 bits the
+// tag.  An entry that sits in its home slot (home = 1) is therefore identified by (slot, tag) alone -- no
+// look at the names; only an entry displaced by linear probing (home = 0) is verified through the name
+// arrays.  Keys that differ only above bit 23 (the node / length index) differ in the low 18 hash bits
+// (the fold key ^= key >> 15 carries bits 24.. down to bits 9.., the odd multiply is a bijection on the
+// low 18 bits), so that verification never confuses two nodes.
+#define LZ2_HOME 0x2000u
+__device__ __forceinline__ uint32_t lz2_hash(uint32_t key, uint32_t wmask)
+{
+    key ^= key >> 15;
+    return (key * LZ2_GOLD) & wmask;
+}
 __device__ __forceinline__ void lz2_clear(ChunkCtx &c, int slots)
 {
     for (int i = threadIdx.x * 4; i < slots; i += AMBC_BLOCK * 4)
         *(uint4 *)(c.T + i) = make_uint4(LZ2_EMPTY, LZ2_EMPTY, LZ2_EMPTY, LZ2_EMPTY);
 }
-__device__ __forceinline__ uint32_t lz2_slot_pos(uint32_t v) { return (v >> 1) & 0x7FFFu; }
+__device__ __forceinline__ uint32_t lz2_slot_pos(uint32_t v) { return (v >> 1) & 0xFFFu; }
 __device__ __forceinline__ uint32_t lz2_slot_name(uint32_t v) { return ((v >> 1) & 0xFFFu) | ((v & 1u) ? 0u : LZ2_NS); }
 
 // first occurrence of the raw key `w` (bytes of sd + p under kmask): insert p, return the slot
@@ -66,17 +79,26 @@ __device__ __forceinline__ uint32_t lz2_insert_raw(ChunkCtx &c, uint32_t w, uint
     }
 }
 
-// first occurrence of the key (S[p] = a, S[p + j] = b, tag) in a table of (mask + 1) slots.
-// Returns the slot, or 0xFFFF and sets *overflow when the table is full.
+// first occurrence of the pair key with W-bit hash h (names S[p] = a, S[p + j] = b) in a table of
+// (mask + 1) slots.  Returns the slot, or 0xFFFF and sets *overflow when the table is full.
 __device__ __forceinline__ uint32_t lz2_insert_pair(ChunkCtx &c, uint32_t mask, uint32_t h, const uint16_t *S,
-                                                    uint32_t a, uint32_t b, int p, int j, uint32_t tag, int *overflow)
+                                                    uint32_t a, uint32_t b, int p, int j, int *overflow)
 {
-    uint32_t s = h & mask;
-    const uint32_t val = (tag << 16) | ((uint32_t)p << 1) | 1u;
-    for (uint32_t probes = 0; probes <= mask; probes++) {
-        const uint32_t q = atomicCAS(&c.T[s], LZ2_EMPTY, val);
+    uint32_t s = h >> 18;
+    uint32_t val = (h << 14) | LZ2_HOME | ((uint32_t)p << 1) | 1u;
+    uint32_t q = atomicCAS(&c.T[s], LZ2_EMPTY, val);
+    if (q == LZ2_EMPTY) return s;
+    if ((q ^ val) < LZ2_HOME) { // same tag, at home: the same key
+        if (val < q) atomicMin(&c.T[s], val & ~1u);
+        else if (q & 1u) atomicAnd(&c.T[s], ~1u);
+        return s;
+    }
+    val &= ~LZ2_HOME;
+    for (uint32_t probes = 1; probes <= mask; probes++) {
+        s = (s + 1) & mask;
+        q = atomicCAS(&c.T[s], LZ2_EMPTY, val);
         if (q == LZ2_EMPTY) return s;
-        if ((q >> 16) == tag) {
+        if ((q ^ val) < LZ2_HOME) { // same tag, both displaced: the homes may differ
             const uint32_t qp = lz2_slot_pos(q);
             if (S[qp] == a && S[qp + j] == b) {
                 if (val < q) atomicMin(&c.T[s], val & ~1u);
@@ -84,7 +106,6 @@ __device__ __forceinline__ uint32_t lz2_insert_pair(ChunkCtx &c, uint32_t mask, 
                 return s;
             }
         }
-        s = (s + 1) & mask;
     }
     *overflow = 1;
     return 0xFFFFu;
@@ -172,8 +193,8 @@ __device__ inline int lz2_double(ChunkCtx &c, const uint16_t *S, uint16_t *D, in
         if (p < P) {
             const uint32_t a = S[p], b = S[p + k];
             if (a & b & LZ2_NS) {
-                const uint32_t h = ((a | (b << 16)) * LZ2_GOLD) >> (32 - 13);
-                slot = lz2_insert_pair(c, LZ2_TSLOTS - 1, h, S, a, b, p, k, 0u, &dummy);
+                const uint32_t h = lz2_hash((a & 0xFFFu) | ((b & 0xFFFu) << 12), 0x7FFFFFFFu);
+                slot = lz2_insert_pair(c, LZ2_TSLOTS - 1, h, S, a, b, p, k, &dummy);
             }
         }
         D[p] = (uint16_t)slot;
@@ -230,9 +251,9 @@ __device__ inline bool lz2_refine_flat(ChunkCtx &c, const uint16_t *S, int k, in
                     if (p + k + j <= n) {
                         const uint32_t a = S[p], b = S[p + j];
                         if (b & LZ2_NS) {
-                            const uint32_t h = ((a | (b << 16)) + (uint32_t)jj * 0x9E3779B9u) * LZ2_GOLD;
-                            if (((h >> 16) & (uint32_t)(R - 1)) == (uint32_t)r)
-                                slot = lz2_insert_pair(c, LZ2_RSLOTS - 1, h >> LZ2_RSHIFT, S, a, b, p, j, (uint32_t)jj, &overflow);
+                            const uint32_t h = lz2_hash((a & 0xFFFu) | ((b & 0xFFFu) << 12) | ((uint32_t)jj << 24), 0x7FFFFFFFu);
+                            if (((h >> 7) & (uint32_t)(R - 1)) == (uint32_t)r)
+                                slot = lz2_insert_pair(c, LZ2_RSLOTS - 1, h, S, a, b, p, j, &overflow);
                         }
                     }
                     islot[jj * np + pi] = (uint16_t)slot;
@@ -283,8 +304,7 @@ __device__ inline int lz2_refine_binary_dense(ChunkCtx &c, const uint16_t *S, in
         if (E == 0) return 0;
         // table of this round: the smallest power of two with load factor <= 1/2 (E < slot count always)
         const int tbits = min(13, max(10, 32 - __clz(LZ2_LOADINV * E - 1))); // smallest power of two >= LOADINV * E
-        const uint32_t tmask = (1u << tbits) - 1u;
-        const int tshift = 32 - tbits;
+        const uint32_t tmask = (1u << tbits) - 1u, wmask = (1u << (tbits + 18)) - 1u;
         lz2_clear(c, 1 << tbits);
         if (tid == 0) *cntB = 0;
         __syncthreads();
@@ -297,8 +317,8 @@ __device__ inline int lz2_refine_binary_dense(ChunkCtx &c, const uint16_t *S, in
             if (p + k + j <= n) {
                 const uint32_t a = S[p], b = S[p + j];
                 if (b & LZ2_NS) {
-                    const uint32_t h = ((a | (b << 16)) + (uint32_t)t * 0x9E3779B9u) * LZ2_GOLD;
-                    slot = lz2_insert_pair(c, tmask, h >> tshift, S, a, b, p, j, (uint32_t)t, &dummy);
+                    const uint32_t h = lz2_hash((a & 0xFFFu) | ((b & 0xFFFu) << 12) | ((uint32_t)t << 24), wmask);
+                    slot = lz2_insert_pair(c, tmask, h, S, a, b, p, j, &dummy);
                 }
             }
             islot[i] = (uint16_t)slot;
