@@ -190,6 +190,54 @@ def test_host_buffer_abi_pipelined(kind_mask, chunk):
     assert np.array_equal(back[:n], data) and not back[n:].any() and list(st) == [0, 0]
 
 
+def test_host_decompress_damaged_bodies():
+    """ambc_decompress_host's pipeline (helper-thread walk, granular body upload, table ring) on damaged
+    bodies of several upload granules: truncation, an END package and a marker mismatch mid-body, an
+    unknown type byte, a short orig_size -- output and error equal to the oracle's decoder
+    (adaptive_compressor.py:396-454)"""
+    import ctypes as C
+    import numpy as np
+    from adaptive_compression_b200 import _lib as L
+    from adaptive_compression_b200 import engine
+    lib = engine.require_cuda()
+    n = (96 << 20) + 777
+    t = engine.synth(n, 3)
+    dev = engine.compress_device(t, 4096)
+    body = dev.body.cpu().numpy()[:dev.body_len].copy()
+    assert body.size > (36 << 20)
+    # package starts: walk the headers on the host
+    starts, pos = [], 0
+    while pos + 18 <= body.size and body[pos + 4] != 0:
+        starts.append(pos)
+        pos += 18 + int.from_bytes(body[pos + 14:pos + 18].tobytes(), "little")
+    mid = starts[len(starts) // 2]
+    late = starts[len(starts) * 7 // 8]
+    variants = []
+    variants.append(("truncated", body[:late + 5].copy(), n))
+    v = body.copy(); v[mid:mid + 16] = np.frombuffer(b"\xff\xff\x00\x00" + b"\x00" * 12, dtype=np.uint8)
+    variants.append(("end_mid", v, n))
+    v = body.copy(); v[late + 1] ^= 0x40
+    variants.append(("marker_mismatch", v, n))
+    v = body.copy(); v[mid + 4] = 77
+    variants.append(("unknown_type", v, n))
+    variants.append(("short_orig", body.copy(), n // 3 + 11))
+    variants.append(("long_orig", body.copy(), n + 5000))
+    for name, b, osz in variants:
+        try:
+            want = O.decompress_body(b.tobytes(), osz)
+        except ValueError:
+            want = None
+        back = np.full(osz, 9, dtype=np.uint8)
+        st = (C.c_uint32 * 2)()
+        rc = lib.ambc_decompress_host(C.c_void_p(b.ctypes.data), b.size, b"\xff\xff\x00\x00", 4, L.NATIVE_MASK,
+                                      C.c_void_p(back.ctypes.data), osz, st)
+        if want is None:
+            assert rc == L.E_MARKER, (name, rc)
+        else:
+            assert rc == 0, (name, rc, lib.ambc_last_error())
+            assert back.tobytes() == want, name
+
+
 def test_dynamic_mode_files_equal_reference_files(golden, tmp_path):
     """several CHUNK_SIZE_CANDIDATES (the reference's default list and custom ones): the facade's file ==
     the file the unmodified reference wrote; stats equal; both decoders read it"""
