@@ -61,21 +61,47 @@ __device__ __forceinline__ void lz2_clear(ChunkCtx &c, int slots)
 __device__ __forceinline__ uint32_t lz2_slot_pos(uint32_t v) { return (v >> 1) & 0xFFFu; }
 __device__ __forceinline__ uint32_t lz2_slot_name(uint32_t v) { return ((v >> 1) & 0xFFFu) | ((v & 1u) ? 0u : LZ2_NS); }
 
-// first occurrence of the raw key `w` (bytes of sd + p under kmask): insert p, return the slot
-__device__ __forceinline__ uint32_t lz2_insert_raw(ChunkCtx &c, uint32_t w, uint32_t kmask, int p, int tbits = 13)
+// first occurrence of the 4-byte gram `w` at p (32 key bits do not fit the exact scheme: verified against
+// the data), table of LZ2_TSLOTS slots
+__device__ __forceinline__ uint32_t lz2_insert_raw4(ChunkCtx &c, uint32_t w, int p)
 {
-    const uint32_t tmask = (1u << tbits) - 1u;
-    uint32_t s = (w * LZ2_GOLD) >> (32 - tbits);
+    uint32_t s = (w * LZ2_GOLD) >> (32 - 13);
     const uint32_t val = ((uint32_t)p << 1) | 1u;
     for (;;) {
         const uint32_t q = atomicCAS(&c.T[s], LZ2_EMPTY, val);
         if (q == LZ2_EMPTY) return s;
-        if ((lds_u32u(c.sd + lz2_slot_pos(q)) & kmask) == w) {
+        if (lds_u32u(c.sd + lz2_slot_pos(q)) == w) {
             if (val < q) atomicMin(&c.T[s], val & ~1u);
             else if (q & 1u) atomicAnd(&c.T[s], ~1u);
             return s;
         }
-        s = (s + 1) & tmask;
+        s = (s + 1) & (LZ2_TSLOTS - 1);
+    }
+}
+
+// first occurrence of the 3-byte gram `w` (< 2^24) at p: exact key as in the pair tables
+__device__ __forceinline__ uint32_t lz2_insert_raw3(ChunkCtx &c, uint32_t w, int p, uint32_t mask, uint32_t wmask)
+{
+    const uint32_t h = lz2_hash(w, wmask);
+    uint32_t s = h >> 18;
+    uint32_t val = (h << 14) | LZ2_HOME | ((uint32_t)p << 1) | 1u;
+    uint32_t q = atomicCAS(&c.T[s], LZ2_EMPTY, val);
+    if (q == LZ2_EMPTY) return s;
+    if ((q ^ val) < LZ2_HOME) {
+        if (val < q) atomicMin(&c.T[s], val & ~1u);
+        else if (q & 1u) atomicAnd(&c.T[s], ~1u);
+        return s;
+    }
+    val &= ~LZ2_HOME;
+    for (;;) { // the table is at most 1/4 full
+        s = (s + 1) & mask;
+        q = atomicCAS(&c.T[s], LZ2_EMPTY, val);
+        if (q == LZ2_EMPTY) return s;
+        if ((q ^ val) < LZ2_HOME && (lds_u32u(c.sd + lz2_slot_pos(q)) & 0xFFFFFFu) == w) {
+            if (val < q) atomicMin(&c.T[s], val & ~1u);
+            else if (q & 1u) atomicAnd(&c.T[s], ~1u);
+            return s;
+        }
     }
 }
 
@@ -121,7 +147,7 @@ __device__ inline int lz2_level4(ChunkCtx &c, uint16_t *D)
     const int P = n - 3;
     for (int p = tid; p < n; p += AMBC_BLOCK) {
         uint32_t slot = 0xFFFFu;
-        if (p < P) slot = lz2_insert_raw(c, lds_u32u(c.sd + p), 0xFFFFFFFFu, p);
+        if (p < P) slot = lz2_insert_raw4(c, lds_u32u(c.sd + p), p);
         D[p] = (uint16_t)slot;
     }
     __syncthreads();
@@ -160,11 +186,12 @@ __device__ inline void lz2_level3(ChunkCtx &c, uint16_t *tmp)
     const uint16_t *list3 = (const uint16_t *)c.L;
     const int cnt = c.red[30];
     const int tbits = min(13, max(10, 32 - __clz(max(4 * cnt, 2) - 1))); // table sized to the list (load <= 1/4)
+    const uint32_t mask = (1u << tbits) - 1u, wmask = (1u << (tbits + 18)) - 1u;
     lz2_clear(c, 1 << tbits);
     __syncthreads();
     for (int i = tid; i < cnt; i += AMBC_BLOCK) {
         const int p = list3[i];
-        tmp[i] = (uint16_t)lz2_insert_raw(c, lds_u32u(c.sd + p) & 0xFFFFFFu, 0xFFFFFFu, p, tbits);
+        tmp[i] = (uint16_t)lz2_insert_raw3(c, lds_u32u(c.sd + p) & 0xFFFFFFu, p, mask, wmask);
     }
     __syncthreads();
     for (int i = tid; i < cnt; i += AMBC_BLOCK) {
@@ -339,8 +366,10 @@ __device__ inline int lz2_refine_binary_dense(ChunkCtx &c, const uint16_t *S, in
                     const uint32_t v = c.T[slot];
                     const uint32_t nm = lz2_slot_pos(v);
                     if (nm < p) {
-                        const int L = k + (2 * (int)t + 1) * step;
-                        if (L > (int)c.mlen[p]) { c.mlen[p] = (uint8_t)L; c.mpos[p] = (uint16_t)nm; }
+                        // after a match a participant only visits longer lengths (it goes right), and a head
+                        // at 2k held at most k before the bracket: the new length is always the longest so far
+                        c.mlen[p] = (uint8_t)(k + (2 * (int)t + 1) * step);
+                        c.mpos[p] = (uint16_t)nm;
                     } else left = true;      // head at this length: the lengths below remain
                     right = !(v & 1u);       // occurs elsewhere: the lengths above remain
                 }
