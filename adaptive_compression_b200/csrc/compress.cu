@@ -346,7 +346,8 @@ k_pack(const uint8_t *__restrict__ in, uint64_t total, uint32_t N, const uint8_t
 // chunk chain (payloads).  Separate kernels so that the fixed-grid hot path stays untouched.
 struct ChunkSpan { unsigned long long pos; uint32_t size; uint32_t pad; };
 
-__global__ void __launch_bounds__(AMBC_BLOCK, 1)
+template <int MINB> // 2: sizes up to LZ2_NMAX (two CTAs per SM like k_select), 1: larger chunks
+__global__ void __launch_bounds__(AMBC_BLOCK, MINB)
 k_select_span(const uint8_t *__restrict__ in, uint64_t total, uint32_t N, uint32_t mask, uint32_t ovh,
               uint32_t stride, const ChunkSpan *__restrict__ list, uint8_t *__restrict__ slots,
               uint8_t *__restrict__ type, uint32_t *__restrict__ comp, uint64_t n_items)
@@ -381,6 +382,22 @@ k_select_span(const uint8_t *__restrict__ in, uint64_t total, uint32_t N, uint32
         }
         __syncthreads();
     }
+}
+
+static int launch_select_span(unsigned grid, size_t smem, cudaStream_t stream, const uint8_t *in, uint64_t total, uint32_t N,
+                              uint32_t mask, uint32_t ovh, uint32_t stride, const ChunkSpan *list, uint8_t *slots,
+                              uint8_t *type, uint32_t *comp, uint64_t n_items)
+{
+    if (N <= LZ2_NMAX) {
+        CUDA_TRY(cudaFuncSetAttribute(k_select_span<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_select_span<2><<<grid, AMBC_BLOCK, smem, stream>>>(in, total, N, mask, ovh, stride, list, slots, type, comp, n_items);
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(k_select_span<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_select_span<1><<<grid, AMBC_BLOCK, smem, stream>>>(in, total, N, mask, ovh, stride, list, slots, type, comp, n_items);
+    }
+    ambc_count_launch();
+    CUDA_TRY(cudaGetLastError());
+    return AMBC_OK;
 }
 
 __global__ void __launch_bounds__(PACK_BLOCK)
@@ -723,14 +740,11 @@ extern "C" int ambc_compress_dynamic_dev(const void *in_dev, uint64_t n, const u
         for (uint64_t j = 0; j < L.n_pass; j++) {
             const uint32_t S = L.pass_size[j];
             size_t smem = S <= LZ2_NMAX ? chunkctx_fast_smem_bytes((int)S) : chunkctx_smem_bytes((int)S, (int)S);
-            CUDA_TRY(cudaFuncSetAttribute(k_select_span, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             uint8_t *tt = W + L.trial_type + j * (L.n_pos + 16);
             uint32_t *tl = (uint32_t *)(W + L.trial_len + j * (L.n_pos * 4 + 16));
             unsigned grid = (unsigned)min<uint64_t>(L.n_pos, 0x7fffffffull);
-            k_select_span<<<grid, AMBC_BLOCK, smem, stream>>>((const uint8_t *)in_dev, n, S, method_mask, ovh, (uint32_t)L.g,
-                                                             nullptr, nullptr, tt, tl, L.n_pos);
-            ambc_count_launch();
-            CUDA_TRY(cudaGetLastError());
+            if ((rc = launch_select_span(grid, smem, stream, (const uint8_t *)in_dev, n, S, method_mask, ovh, (uint32_t)L.g,
+                                         nullptr, nullptr, tt, tl, L.n_pos))) return rc;
             CUDA_TRY(cudaMemcpyAsync(h_type.data() + j * L.n_pos, tt, L.n_pos, cudaMemcpyDeviceToHost, stream));
             CUDA_TRY(cudaMemcpyAsync(h_len.data() + j * L.n_pos, tl, L.n_pos * 4, cudaMemcpyDeviceToHost, stream));
         }
@@ -795,11 +809,9 @@ extern "C" int ambc_compress_dynamic_dev(const void *in_dev, uint64_t n, const u
             return ambc_fail(AMBC_E_ARG, "per-chunk-raw pieces larger than 8192 bytes are not supported");
         }
         size_t smem = maxsz <= LZ2_NMAX ? chunkctx_fast_smem_bytes((int)maxsz) : chunkctx_smem_bytes((int)maxsz, (int)maxsz);
-        CUDA_TRY(cudaFuncSetAttribute(k_select_span, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         unsigned grid = (unsigned)min<uint64_t>(n_list, 0x7fffffffull);
-        k_select_span<<<grid, AMBC_BLOCK, smem, stream>>>((const uint8_t *)in_dev, n, maxsz, method_mask, ovh, 0, d_spans,
-                                                         W + L.slots, type, comp, n_list);
-        ambc_count_launch();
+        if ((rc = launch_select_span(grid, smem, stream, (const uint8_t *)in_dev, n, maxsz, method_mask, ovh, 0, d_spans,
+                                     W + L.slots, type, comp, n_list))) return rc;
         const unsigned gt = (unsigned)((n_list + SCAN_TILE - 1) / SCAN_TILE);
         const uint32_t sflags = 1u | 2u; // every entry is a package; no END (appended below)
         k_sizes<<<gt, 256, 0, stream>>>(type, comp, 0, n_list, maxsz, n, ovh, sflags, st, tiles);
