@@ -37,5 +37,7 @@ struct AmbcPieceOut {
     void *states;          // pinned, n_pieces * ambc_scan_state_bytes()
     cudaEvent_t *done;     // one event per piece
     cudaStream_t d2h;      // download stream
+    cudaStream_t aux;      // scan / pack stream (nullptr: same stream as k_select)
+    cudaEvent_t *sel;      // one event per piece: its k_select finished
 };
 extern "C" uint64_t ambc_scan_state_bytes(void);

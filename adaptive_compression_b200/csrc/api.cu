@@ -106,10 +106,11 @@ struct DevBuf {
 #define AMBC_MAX_PIECES 64
 struct HostCtx {
     DevBuf in, out, work, table, status;
-    cudaStream_t stream = nullptr, copy = nullptr, d2h = nullptr;
+    cudaStream_t stream = nullptr, copy = nullptr, d2h = nullptr, aux = nullptr;
     cudaEvent_t piece_ev[AMBC_MAX_PIECES] = {};
     cudaEvent_t ring_ev[4] = {};
     cudaEvent_t done_ev[AMBC_MAX_PIECES] = {};
+    cudaEvent_t sel_ev[AMBC_MAX_PIECES] = {};
     void *states = nullptr; // pinned scan states, one per piece
     bool ring_used[4] = {false, false, false, false};
     void *table_host = nullptr; // pinned ring of table pieces (ambc_decompress_host)
@@ -138,6 +139,9 @@ static int host_ctx(HostCtx **out)
         if (e != cudaSuccess) return ambc_fail(AMBC_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
         e = cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking);
         if (e != cudaSuccess) return ambc_fail(AMBC_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+        e = cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return ambc_fail(AMBC_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+        for (int i = 0; i < AMBC_MAX_PIECES; i++) cudaEventCreateWithFlags(&c->sel_ev[i], cudaEventDisableTiming);
         for (int i = 0; i < AMBC_MAX_PIECES; i++) cudaEventCreateWithFlags(&c->piece_ev[i], cudaEventDisableTiming);
         for (int i = 0; i < 4; i++) cudaEventCreateWithFlags(&c->ring_ev[i], cudaEventDisableTiming);
         for (int i = 0; i < AMBC_MAX_PIECES; i++) cudaEventCreateWithFlags(&c->done_ev[i], cudaEventDisableTiming);
@@ -177,6 +181,7 @@ extern "C" int ambc_compress_host(const void *in_host, uint64_t n, uint32_t chun
     }
     AmbcPieceOut po;
     po.out_host = out_host; po.out_cap = out_cap; po.states = c->states; po.done = c->done_ev; po.d2h = c->d2h;
+    po.aux = c->aux; po.sel = c->sel_ev;
     if (n_pieces > 1) {
         for (uint64_t k = 0; k < n_pieces; k++) {
             uint64_t b0 = k * piece_chunks * chunk, b1 = min<uint64_t>(n, b0 + piece_chunks * chunk);

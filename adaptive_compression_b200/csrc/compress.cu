@@ -542,6 +542,7 @@ int ambc_compress_dev_impl(const void *in_dev, uint64_t n, uint32_t chunk, uint3
             for (uint32_t k = 0; k < n_pieces; k++) CUDA_TRY(cudaStreamWaitEvent(stream, piece_ready[k], 0));
         const uint32_t np = pieces ? n_pieces : 1;
         const bool stream_out = pieces && po && po->out_host && po->states && po->done;
+        cudaStream_t s2 = (stream_out && po->aux && po->sel) ? po->aux : stream;
         for (uint32_t k = 0; k < np; k++) {
             const uint64_t c0 = pieces ? (uint64_t)k * piece_chunks : 0;
             const uint64_t c1 = pieces ? min<uint64_t>(L.n_chunks, c0 + piece_chunks) : L.n_chunks;
@@ -555,24 +556,32 @@ int ambc_compress_dev_impl(const void *in_dev, uint64_t n, uint32_t chunk, uint3
                                                         L.slot_stride, type, comp, &st->first_raw, c0, c1);
             ambc_count_launch();
             if (last) ambc_timing_mark(1, stream);
-            k_sizes<<<gt, 256, 0, stream>>>(type, comp, c0, c1, chunk, n, ovh, flags, st, tiles);
+            // scan + pack of piece k run on their own stream so that k_select of piece k + 1 follows at once
+            // (k_select only lowers st->first_raw to chunks of its own piece, which the scans of earlier
+            // pieces never look at)
+            if (s2 != stream) {
+                CUDA_TRY(cudaEventRecord(po->sel[k], stream));
+                CUDA_TRY(cudaStreamWaitEvent(s2, po->sel[k], 0));
+            }
+            k_sizes<<<gt, 256, 0, s2>>>(type, comp, c0, c1, chunk, n, ovh, flags, st, tiles);
             ambc_count_launch();
-            k_scan_tiles<<<1, 1024, 0, stream>>>(tiles, c0 / SCAN_TILE, (c1 + SCAN_TILE - 1) / SCAN_TILE, last ? 1 : 0, type,
-                                                 comp, L.n_chunks, chunk, n, ovh, flags, st, (uint8_t *)out_dev, out_cap,
-                                                 marker_word, marker_bytes);
+            k_scan_tiles<<<1, 1024, 0, s2>>>(tiles, c0 / SCAN_TILE, (c1 + SCAN_TILE - 1) / SCAN_TILE, last ? 1 : 0, type,
+                                             comp, L.n_chunks, chunk, n, ovh, flags, st, (uint8_t *)out_dev, out_cap,
+                                             marker_word, marker_bytes);
             ambc_count_launch();
-            k_offsets<<<gt, 256, 0, stream>>>(type, comp, c0, c1, chunk, n, ovh, flags, st, tiles, offs);
+            k_offsets<<<gt, 256, 0, s2>>>(type, comp, c0, c1, chunk, n, ovh, flags, st, tiles, offs);
             ambc_count_launch();
-            if (last) ambc_timing_mark(2, stream);
-            k_pack<<<gch, PACK_BLOCK, psmem, stream>>>((const uint8_t *)in_dev, n, chunk, W + L.slots, L.slot_stride, type,
-                                                       comp, offs, st, flags, marker_word, marker_bytes, (uint8_t *)out_dev,
-                                                       out_cap, c0, c1, pieces ? 0 : 1);
+            if (last) ambc_timing_mark(2, s2);
+            k_pack<<<gch, PACK_BLOCK, psmem, s2>>>((const uint8_t *)in_dev, n, chunk, W + L.slots, L.slot_stride, type,
+                                                   comp, offs, st, flags, marker_word, marker_bytes, (uint8_t *)out_dev,
+                                                   out_cap, c0, c1, pieces ? 0 : 1);
             ambc_count_launch();
             CUDA_TRY(cudaGetLastError());
             if (stream_out) {
                 CUDA_TRY(cudaMemcpyAsync((uint8_t *)po->states + (size_t)k * sizeof(ScanState), st, sizeof(ScanState),
-                                         cudaMemcpyDeviceToHost, stream));
-                CUDA_TRY(cudaEventRecord(po->done[k], stream));
+                                         cudaMemcpyDeviceToHost, s2));
+                CUDA_TRY(cudaEventRecord(po->done[k], s2));
+                if (last && s2 != stream) CUDA_TRY(cudaStreamWaitEvent(stream, po->done[k], 0));
             }
         }
         ambc_timing_mark(3, stream);
