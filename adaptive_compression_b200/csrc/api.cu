@@ -120,7 +120,7 @@ int ambc_index_vector(const uint8_t *body, uint64_t body_len, const uint8_t *mar
 int ambc_compress_dev_impl(const void *in_dev, uint64_t n, uint32_t chunk, uint32_t method_mask, uint32_t flags,
                            const uint8_t *marker, uint32_t marker_bytes, void *out_dev, uint64_t out_cap,
                            void *work_dev, uint64_t work_bytes, ambc_compress_result *res, cudaStream_t stream,
-                           const cudaEvent_t *piece_ready, uint64_t piece_chunks, uint32_t n_pieces,
+                           const cudaEvent_t *piece_ready, const uint64_t *piece_start, uint32_t n_pieces,
                            const AmbcPieceOut *po);
 static std::mutex g_mu;
 static HostCtx g_ctx[16];
@@ -165,16 +165,35 @@ extern "C" int ambc_compress_host(const void *in_host, uint64_t n, uint32_t chun
     if ((rc = c->out.ensure(bound))) return rc;
     if ((rc = c->work.ensure(wbytes))) return rc;
     // upload in pieces on a second stream; select / scan / pack of piece k start as soon as piece k is
-    // resident, and finished body bytes are downloaded while later pieces compute
-    const uint64_t piece_bytes_target = 64ull << 20;
-    uint64_t piece_chunks = chunk <= piece_bytes_target ? piece_bytes_target / chunk : 1;
-    piece_chunks = (piece_chunks + 2047) / 2048 * 2048; // whole scan tiles
-    uint64_t n_chunks = (n + chunk - 1) / chunk;
-    uint64_t n_pieces = (n_chunks + piece_chunks - 1) / piece_chunks;
-    if (n_pieces > AMBC_MAX_PIECES) {
-        piece_chunks = ((n_chunks + AMBC_MAX_PIECES - 1) / AMBC_MAX_PIECES + 2047) / 2048 * 2048;
-        n_pieces = (n_chunks + piece_chunks - 1) / piece_chunks;
+    // resident, and finished body bytes are downloaded while later pieces compute.  Pieces are whole scan
+    // tiles (2048 chunks); they ramp 8 -> 16 -> 32 -> 64 MiB at the front (k_select starts early) and back
+    // down at the end (little left to pack and download after the last k_select)
+    const uint64_t n_chunks = (n + chunk - 1) / chunk;
+    const uint64_t tile_bytes = 2048ull * chunk, n_tiles = (n_chunks + 2047) / 2048;
+    uint64_t unit = max<uint64_t>(1, (8ull << 20) / tile_bytes), big = max<uint64_t>(unit, (64ull << 20) / tile_bytes);
+    std::vector<uint64_t> sizes; // in tiles
+    for (;;) {
+        sizes.clear();
+        std::vector<uint64_t> ramp;
+        for (uint64_t r = unit; r < big; r *= 2) ramp.push_back(r);
+        uint64_t ramp_sum = 0;
+        for (uint64_t r : ramp) ramp_sum += r;
+        if (n_tiles >= 2 * ramp_sum + big) {
+            uint64_t mid = n_tiles - 2 * ramp_sum;
+            sizes = ramp;
+            for (; mid >= 2 * big; mid -= big) sizes.push_back(big);
+            sizes.push_back(mid);
+            for (size_t r = ramp.size(); r-- > 0;) sizes.push_back(ramp[r]);
+        } else {
+            for (uint64_t t = 0; t < n_tiles; t += big) sizes.push_back(min<uint64_t>(big, n_tiles - t));
+        }
+        if (sizes.size() <= AMBC_MAX_PIECES) break;
+        big *= 2; // (very large inputs: fewer, larger pieces)
     }
+    const uint64_t n_pieces = sizes.size();
+    uint64_t piece_start[AMBC_MAX_PIECES + 1];
+    piece_start[0] = 0;
+    for (uint64_t k = 0; k < n_pieces; k++) piece_start[k + 1] = piece_start[k] + sizes[k] * 2048;
     if (!c->states) {
         if (cudaMallocHost(&c->states, AMBC_MAX_PIECES * ambc_scan_state_bytes()) != cudaSuccess)
             return ambc_fail(AMBC_E_CUDA, "cudaMallocHost failed");
@@ -184,16 +203,16 @@ extern "C" int ambc_compress_host(const void *in_host, uint64_t n, uint32_t chun
     po.aux = c->aux; po.sel = c->sel_ev;
     if (n_pieces > 1) {
         for (uint64_t k = 0; k < n_pieces; k++) {
-            uint64_t b0 = k * piece_chunks * chunk, b1 = min<uint64_t>(n, b0 + piece_chunks * chunk);
+            uint64_t b0 = piece_start[k] * chunk, b1 = min<uint64_t>(n, piece_start[k + 1] * chunk);
             CUDA_TRY(cudaMemcpyAsync((uint8_t *)c->in.p + b0, (const uint8_t *)in_host + b0, b1 - b0, cudaMemcpyHostToDevice, c->copy));
             CUDA_TRY(cudaEventRecord(c->piece_ev[k], c->copy));
         }
         rc = ambc_compress_dev_impl(c->in.p, n, chunk, method_mask, flags, marker, marker_bytes, c->out.p, bound, c->work.p,
-                                    c->work.cap, res, c->stream, c->piece_ev, piece_chunks, (uint32_t)n_pieces, &po);
+                                    c->work.cap, res, c->stream, c->piece_ev, piece_start, (uint32_t)n_pieces, &po);
     } else {
         if (n) CUDA_TRY(cudaMemcpyAsync(c->in.p, in_host, n, cudaMemcpyHostToDevice, c->stream));
         rc = ambc_compress_dev_impl(c->in.p, n, chunk, method_mask, flags, marker, marker_bytes, c->out.p, bound, c->work.p,
-                                    c->work.cap, res, c->stream, nullptr, 0, 0, &po);
+                                    c->work.cap, res, c->stream, nullptr, nullptr, 0, &po);
     }
     if (rc) { cudaStreamSynchronize(c->copy); return rc; }
     if (map_type && res->n_chunks)

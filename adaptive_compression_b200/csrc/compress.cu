@@ -460,12 +460,13 @@ extern "C" uint64_t ambc_compress_bound(uint64_t n, uint32_t chunk, uint32_t mar
     return n + (chunks + 1) * (marker_bytes + 14) + marker_bytes + 12 + 64;
 }
 
-// piece_ready[k] (optional): event after which chunks [k * piece_chunks, (k+1) * piece_chunks) of the
-// input are resident (ambc_compress_host uploads piece-wise so that H2D overlaps k_select)
+// piece_ready[k] (optional): event after which chunks [piece_start[k], piece_start[k + 1]) of the input
+// are resident (ambc_compress_host uploads piece-wise so that H2D overlaps k_select); piece_start has
+// n_pieces + 1 ascending entries, multiples of SCAN_TILE, the last one >= the chunk count
 int ambc_compress_dev_impl(const void *in_dev, uint64_t n, uint32_t chunk, uint32_t method_mask, uint32_t flags,
                            const uint8_t *marker, uint32_t marker_bytes, void *out_dev, uint64_t out_cap,
                            void *work_dev, uint64_t work_bytes, ambc_compress_result *res, cudaStream_t stream,
-                           const cudaEvent_t *piece_ready, uint64_t piece_chunks, uint32_t n_pieces,
+                           const cudaEvent_t *piece_ready, const uint64_t *piece_start, uint32_t n_pieces,
                            const AmbcPieceOut *po);
 extern "C" uint64_t ambc_scan_state_bytes(void) { return sizeof(ScanState); }
 
@@ -475,13 +476,13 @@ extern "C" int ambc_compress_dev(const void *in_dev, uint64_t n, uint32_t chunk,
                                  void *stream_)
 {
     return ambc_compress_dev_impl(in_dev, n, chunk, method_mask, flags, marker, marker_bytes, out_dev, out_cap, work_dev,
-                                  work_bytes, res, (cudaStream_t)stream_, nullptr, 0, 0, nullptr);
+                                  work_bytes, res, (cudaStream_t)stream_, nullptr, nullptr, 0, nullptr);
 }
 
 int ambc_compress_dev_impl(const void *in_dev, uint64_t n, uint32_t chunk, uint32_t method_mask, uint32_t flags,
                            const uint8_t *marker, uint32_t marker_bytes, void *out_dev, uint64_t out_cap,
                            void *work_dev, uint64_t work_bytes, ambc_compress_result *res, cudaStream_t stream,
-                           const cudaEvent_t *piece_ready, uint64_t piece_chunks, uint32_t n_pieces,
+                           const cudaEvent_t *piece_ready, const uint64_t *piece_start, uint32_t n_pieces,
                            const AmbcPieceOut *po)
 {
     if (!res || !marker || marker_bytes < 1 || marker_bytes > 4 || chunk == 0)
@@ -537,15 +538,17 @@ int ambc_compress_dev_impl(const void *in_dev, uint64_t n, uint32_t chunk, uint3
         CUDA_TRY(cudaFuncSetAttribute(k_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
         // piece-wise run (host-buffer path): select / scan / pack of piece k are queued behind the
         // upload of piece k; the finished body bytes of a piece go home while later pieces compute
-        const bool pieces = piece_ready && n_pieces > 1 && piece_chunks && piece_chunks % SCAN_TILE == 0;
+        bool pieces = piece_ready && n_pieces > 1 && piece_start && piece_start[0] == 0 && piece_start[n_pieces] >= L.n_chunks;
+        for (uint32_t k = 0; pieces && k < n_pieces; k++)
+            pieces = piece_start[k] % SCAN_TILE == 0 && piece_start[k] < piece_start[k + 1];
         if (!pieces && piece_ready)
             for (uint32_t k = 0; k < n_pieces; k++) CUDA_TRY(cudaStreamWaitEvent(stream, piece_ready[k], 0));
         const uint32_t np = pieces ? n_pieces : 1;
         const bool stream_out = pieces && po && po->out_host && po->states && po->done;
         cudaStream_t s2 = (stream_out && po->aux && po->sel) ? po->aux : stream;
         for (uint32_t k = 0; k < np; k++) {
-            const uint64_t c0 = pieces ? (uint64_t)k * piece_chunks : 0;
-            const uint64_t c1 = pieces ? min<uint64_t>(L.n_chunks, c0 + piece_chunks) : L.n_chunks;
+            const uint64_t c0 = pieces ? piece_start[k] : 0;
+            const uint64_t c1 = pieces ? min<uint64_t>(L.n_chunks, piece_start[k + 1]) : L.n_chunks;
             if (c0 >= c1) break;
             const bool last = c1 == L.n_chunks;
             const unsigned gch = (unsigned)min<uint64_t>(c1 - c0, 0x7fffffffull);
