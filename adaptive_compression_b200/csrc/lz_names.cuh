@@ -324,10 +324,11 @@ __device__ inline int lz2_refine_binary_dense(ChunkCtx &c, const uint16_t *S, in
 {
     const int n = c.n, tid = threadIdx.x, lane = tid & 31;
     uint16_t *A = (uint16_t *)c.L, *B = A + LZ2_LISTCAP, *islot = B + LZ2_LISTCAP;
-    volatile int *cntB = c.red + 29;
-    int E = np, dummy = 0;
+    int E = np, dummy = 0, round = 0;
     PHASE_DECL
-    for (int step = k >> 1; step >= 1; step >>= 1) {
+    for (int step = k >> 1; step >= 1; step >>= 1, round++) {
+        // two alternating counters: the one of this round was last read two rounds ago
+        volatile int *cntB = c.red + 28 + (round & 1);
         if (E == 0) return 0;
         // table of this round: the smallest power of two with load factor <= 1/2 (E < slot count always)
         const int tbits = min(13, max(10, 32 - __clz(LZ2_LOADINV * E - 1))); // smallest power of two >= LOADINV * E
@@ -393,7 +394,6 @@ __device__ inline int lz2_refine_binary_dense(ChunkCtx &c, const uint16_t *S, in
         PHASE(18);
         if (ov) return 1;
         E = *cntB;
-        __syncthreads(); // everybody has read the count before it is reset
         uint16_t *tmp = A; A = B; B = tmp;
     }
     return 0;
