@@ -47,7 +47,11 @@ struct ChunkCtx {
     uint16_t *nameA;   // LZ2_NMAX first-occurrence names (two buffers, alternating levels)
     uint16_t *nameB;
     uint8_t *L;        // LZ2_LBYTES of list memory: participant / item lists and the slot memo
+    // Huffman code table by symbol; survives the Dictionary trial (the rest of the Huffman scratch does not)
+    uint32_t *hcode;   // [256]
+    uint8_t *hlen;     // [256]
 };
+#define AMBC_HTAB_BYTES 1280
 
 #define LZ2_NMAX 4096
 #define LZ2_TSLOTS 8192
@@ -77,6 +81,7 @@ __host__ __device__ inline size_t chunkctx_smem_bytes(int N, int pcap)
            + r16(nb * 4) * 2                  // bmask, reach
            + r16(nb)                          // estart
            + 128                              // red
+           + AMBC_HTAB_BYTES                  // hcode, hlen
            + LZ2_BYTES;                       // T, nameA, nameB, fol
 }
 
@@ -98,6 +103,7 @@ __device__ inline void chunkctx_carve(ChunkCtx &c, uint8_t *base, int N, int pca
     c.reach = (uint32_t *)p; p += r16(nb * 4);
     c.estart = p; p += r16(nb);
     c.red = (int *)p; p += 128;
+    c.hcode = (uint32_t *)p; c.hlen = p + 1024; p += AMBC_HTAB_BYTES;
     c.T = (uint32_t *)p; p += LZ2_TSLOTS * 4;
     c.nameA = (uint16_t *)p; p += LZ2_NMAX * 2;
     c.nameB = (uint16_t *)p; p += LZ2_NMAX * 2;
@@ -114,7 +120,7 @@ __host__ __device__ inline size_t chunkctx_fast_smem_bytes(int N)
 {
     size_t nb = (size_t)(N + 31) / 32;
     return r16((size_t)N) + AMBC_PAD + LZ2_TSLOTS * 4 + 2 * LZ2_NMAX * 2 + LZ2_LBYTES
-           + r16((size_t)N) + r16(2 * (size_t)N) + 1024 + r16(nb * 4) * 2 + r16(nb) + 128;
+           + r16((size_t)N) + r16(2 * (size_t)N) + 1024 + r16(nb * 4) * 2 + r16(nb) + 128 + AMBC_HTAB_BYTES;
 }
 __device__ inline void chunkctx_carve_fast(ChunkCtx &c, uint8_t *base, int N)
 {
@@ -139,7 +145,8 @@ __device__ inline void chunkctx_carve_fast(ChunkCtx &c, uint8_t *base, int N)
     c.bmask = (uint32_t *)p; p += r16(nb * 4);
     c.reach = (uint32_t *)p; p += r16(nb * 4);
     c.estart = p; p += r16(nb);
-    c.red = (int *)p;
+    c.red = (int *)p; p += 128;
+    c.hcode = (uint32_t *)p; c.hlen = p + 1024;
     c.pcap = N;
     c.n = 0;
 }
@@ -753,14 +760,19 @@ __device__ __forceinline__ void lz_zero_mlen(ChunkCtx &c)
     __syncthreads();
 }
 
-// Payload -> c.pay (as far as pcap allows).  Returns the exact payload length.  Collective.
-__device__ inline int chunk_lz_encode(ChunkCtx &c)
+// Payload -> c.pay (as far as pcap allows).  Returns the exact payload length, or LZ_ABORTED when the
+// match search proved early that the length cannot stay below `cutoff` (the caller already holds a
+// payload that short).  Collective.
+#define LZ_ABORTED 0x7fffffff
+__device__ inline int chunk_lz_encode(ChunkCtx &c, int cutoff = LZ_ABORTED)
 {
     const int n = c.n, tid = threadIdx.x;
     lz_zero_mlen(c);
     bool done = false;
     if (c.T && n <= LZ2_NMAX && !LZ_FORCE_BUCKETS) {
-        done = lz2_match_all(c);
+        const int r = lz2_match_all(c, cutoff);
+        if (r == 2) return LZ_ABORTED;
+        done = r == 0;
         if (!done) lz_zero_mlen(c); // a table overflowed (pathological key skew): redo with the bucket search
     }
     if (!done) lz_match_all_buckets(c);
@@ -878,17 +890,18 @@ struct HuffScratch {
     uint32_t *firstpos; // [256]
     uint8_t *leafsym;   // [256] symbol of sorted leaf j
 };
-__device__ inline HuffScratch huff_scratch(uint8_t *X)
+__device__ inline HuffScratch huff_scratch(ChunkCtx &c)
 {
     HuffScratch h;
+    uint8_t *X = c.X;
     h.key = (uint32_t *)X;
     h.nodeW = (uint32_t *)(X + 1024);
     h.lead = (uint16_t *)(X + 3072);
     h.parent = (uint16_t *)(X + 4096);
     h.nbit = X + 5120;
-    h.lenOf = X + 5632;
+    h.lenOf = c.hlen;
     h.order = X + 5888;
-    h.codeOf = (uint32_t *)(X + 6144);
+    h.codeOf = c.hcode;
     h.firstpos = (uint32_t *)(X + 7168);
     h.leafsym = X + 8192;
     return h;

@@ -38,7 +38,7 @@ k_codec_encode(int method, const uint8_t *__restrict__ in, const uint64_t *__res
                     if (f.K <= 1) len = AMBC_CODEC_INDEX_ERROR;
                     else if (f.K == 256) len = AMBC_CODEC_VALUE_ERROR;
                     else {
-                        HuffScratch hs = huff_scratch(c.X);
+                        HuffScratch hs = huff_scratch(c);
                         int bits = chunk_huff_build(c, hs, f.K);
                         len = chunk_huff_emit(c, hs, f.K, bits);
                     }
@@ -88,7 +88,7 @@ k_should_use(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off
             chunk_load(c, in + a, n);
             ChunkFeatures f;
             chunk_features(c, f);
-            HuffScratch hs = huff_scratch(c.X);
+            HuffScratch hs = huff_scratch(c);
             // the plug-in reports the exact Python-order sum, not the tree sum
             chunk_first_order(c, hs.firstpos, hs.order);
             H = chunk_entropy_ordered(c, f.K, hs.order);

@@ -39,7 +39,7 @@ __device__ SelectOut select_chunk(ChunkCtx &c, uint32_t mask, int ovh)
     PHASE_DECL
     chunk_features(c, f);
     PHASE(1);
-    HuffScratch hs = huff_scratch(c.X);
+    HuffScratch hs = huff_scratch(c);
 
     // gates (compression_methods.py:154-180, 315-343, 551-574)
     bool rle_ok = (mask & 2u) && eligible(1, n) && n >= 4 &&
@@ -57,27 +57,45 @@ __device__ SelectOut select_chunk(ChunkCtx &c, uint32_t mask, int ovh)
     }
     // Delta (id 4) always produces n bytes, so (n + overhead)/n > 1 never wins (:574-577).
 
+    // The reference tries the methods in id order and keeps the first strictly smaller payload (:575).
+    // The order of evaluation below differs, the outcome does not: a method's trial is skipped or cut
+    // short only when its payload provably cannot end up as the winner.
     int best_type = 255, best_len = 0x7fffffff;
     if (rle_ok) {
         int len = 2 * f.rle_pairs;
         if (len + ovh < n) { best_type = 1; best_len = len; }
     }
+    // Huffman lower bound from the entropy: bits >= max(n, n*H)
+    int hf_lb = 0x7fffffff;
+    if (hf_ok) hf_lb = 1 + 5 * f.K + 4 + (int)ceil(fmax((double)n, (double)n * f.H - 0.01) / 8.0);
+    // Huffman first when the Dictionary method looks weak (many distinct trigrams): its size then cuts
+    // the match search short (lz2_match_all).  Its code table survives the search in c.hcode / c.hlen.
+    const bool hf_first = hf_ok && lz_ok && n <= LZ2_NMAX && 100 * f.distinct3 >= 43 * min(1000, n);
+    int hf_len = 0x7fffffff, hf_bits = 0; // hf_len: built, and a candidate against RLE
+    if (hf_first && hf_lb < best_len && hf_lb + ovh < n) {
+        hf_bits = chunk_huff_build(c, hs, f.K);
+        const int len = 1 + 5 * f.K + 4 + ((hf_bits + 7) >> 3);
+        if (len < best_len && len + ovh < n) hf_len = len;
+    }
     if (lz_ok) {
-        // a Dictionary payload can never be shorter than lz_lower_bound(n): skip the trial
-        // when it cannot win (strict '<' keeps the earlier method on ties, :575)
+        // a Dictionary payload can never be shorter than lz_lower_bound(n): skip the trial when it cannot
+        // win.  It ends up as the winner only if it is < the RLE payload and <= the Huffman payload.
+        const int cutoff = hf_len == 0x7fffffff ? best_len : min(best_len, hf_len + 1);
         int lb = lz_lower_bound(n);
-        if (lb < best_len && lb + ovh < n) {
+        if (lb < cutoff && lb + ovh < n) {
             PHASE(10);
-            int len = chunk_lz_encode(c);
+            int len = chunk_lz_encode(c, hf_first ? cutoff : LZ_ABORTED);
             PHASE(11);
             if (len < best_len && len + ovh < n) { best_type = 2; best_len = len; }
         }
     }
-    if (hf_ok) {
-        // lower bound from the entropy: bits >= max(n, n*H)
-        double lbits = fmax((double)n, (double)n * f.H - 0.01);
-        int lb = 1 + 5 * f.K + 4 + (int)ceil(lbits / 8.0);
-        if (lb < best_len && lb + ovh < n) {
+    if (hf_first) {
+        if (hf_len < best_len) {
+            best_type = 3; best_len = hf_len;
+            chunk_huff_emit(c, hs, f.K, hf_bits);
+        }
+    } else if (hf_ok) {
+        if (hf_lb < best_len && hf_lb + ovh < n) {
             int bits = chunk_huff_build(c, hs, f.K);
             int len = 1 + 5 * f.K + 4 + ((bits + 7) >> 3);
             if (len < best_len && len + ovh < n) {

@@ -138,11 +138,11 @@ __device__ __forceinline__ uint32_t lz2_insert_pair(ChunkCtx &c, uint32_t mask, 
 }
 
 // name_4 (D) for every position, matches of length 4.  Returns "any match".
-__device__ inline int lz2_level4(ChunkCtx &c, uint16_t *D)
+__device__ inline int lz2_level4(ChunkCtx &c, uint16_t *D, bool count)
 {
     const int n = c.n, tid = threadIdx.x;
     lz2_clear(c, LZ2_TSLOTS);
-    if (tid == 0) c.red[30] = 0; // length of the level-3 candidate list
+    if (tid == 0) { c.red[30] = 0; c.red[27] = 0; c.red[26] = 0; } // level-3 list length; match counts at 4 / 8
     __syncthreads();
     const int P = n - 3;
     for (int p = tid; p < n; p += AMBC_BLOCK) {
@@ -164,7 +164,7 @@ __device__ inline int lz2_level4(ChunkCtx &c, uint16_t *D)
             uint32_t nm = (uint32_t)p;
             if (slot != 0xFFFFu) nm = lz2_slot_name(c.T[slot]);
             D[p] = (uint16_t)nm;
-            if ((nm & 0xFFFu) < (uint32_t)p) { c.mlen[p] = 4; c.mpos[p] = (uint16_t)(nm & 0xFFFu); nonhead = 1; }
+            if ((nm & 0xFFFu) < (uint32_t)p) { c.mlen[p] = 4; c.mpos[p] = (uint16_t)(nm & 0xFFFu); nonhead++; }
             else head3 = p + 3 <= n; // (positions past n - 4 are their own name)
         }
         const uint32_t m = __ballot_sync(FULL_MASK, head3);
@@ -174,6 +174,10 @@ __device__ inline int lz2_level4(ChunkCtx &c, uint16_t *D)
             base = __shfl_sync(FULL_MASK, base, 0);
             if (head3) list3[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)p;
         }
+    }
+    if (count) { // number of positions with a match of >= 4 bytes (early-abort bound of lz2_match_all)
+        const int w = warp_sum(nonhead);
+        if (lane == 0 && w) atomicAdd(c.red + 27, w);
     }
     return __syncthreads_or(nonhead);
 }
@@ -206,7 +210,7 @@ __device__ inline void lz2_level3(ChunkCtx &c, uint16_t *tmp)
 // heads by construction and do not enter the table.  Also lists the participants of the bracket
 // (k, 2k) in c.L: heads of their 2k-gram whose k-gram occurs elsewhere, with room for k+1 bytes
 // (count in c.red[30]).  Returns "any match of 2k bytes".
-__device__ inline int lz2_double(ChunkCtx &c, const uint16_t *S, uint16_t *D, int k)
+__device__ inline int lz2_double(ChunkCtx &c, const uint16_t *S, uint16_t *D, int k, bool count = false)
 {
     const int n = c.n, tid = threadIdx.x, lane = tid & 31;
     lz2_clear(c, LZ2_TSLOTS);
@@ -240,7 +244,7 @@ __device__ inline int lz2_double(ChunkCtx &c, const uint16_t *S, uint16_t *D, in
             D[p] = (uint16_t)nm;
             if ((nm & 0xFFFu) < (uint32_t)p) {
                 c.mlen[p] = (uint8_t)(2 * k); c.mpos[p] = (uint16_t)(nm & 0xFFFu);
-                nonhead = 1;
+                nonhead++;
             } else part = p <= Pmax && (S[p] & LZ2_NS);
         }
         const uint32_t m = __ballot_sync(FULL_MASK, part);
@@ -250,6 +254,10 @@ __device__ inline int lz2_double(ChunkCtx &c, const uint16_t *S, uint16_t *D, in
             base = __shfl_sync(FULL_MASK, base, 0);
             if (part) plist[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)p;
         }
+    }
+    if (count) {
+        const int w = warp_sum(nonhead);
+        if (lane == 0 && w) atomicAdd(c.red + 26, w);
     }
     return __syncthreads_or(nonhead);
 }
@@ -430,30 +438,54 @@ __device__ inline bool lz2_refine(ChunkCtx &c, const uint16_t *S, const uint16_t
     return lz2_refine_flat(c, S, k, c.red[30], plist, (uint16_t *)(c.L + 8192));
 }
 
+// Lower bound on the Dictionary payload of ANY parse of n bytes in which at most `a` tokens start at a
+// position with a match of >= 8 bytes (they cover at most 32 bytes for 4 payload bytes), at most `b` at a
+// position whose longest match has 4..7 bytes (at most 7 bytes for 4), and every other token covers at most
+// 3 bytes for 4 or 1 byte for 2 (compression_methods.py:211-232).  Tokens may be cut short, so the bound
+// holds for the greedy parse whatever it turns out to be.
+__device__ __forceinline__ int lz2_small_cost(int r) { return 4 * (r / 3) + 2 * (r % 3); }
+__device__ inline int lz2_count_bound(int n, int a_avail, int b_avail)
+{
+    const int a = min(a_avail, n >> 5);
+    int rem = n - 32 * a;
+    if (a < a_avail) return 4 * a + min(4, lz2_small_cost(rem));
+    const int b = min(b_avail, rem / 7);
+    rem -= 7 * b;
+    if (b < b_avail) return 4 * a + 4 * b + min(4, lz2_small_cost(rem));
+    return 4 * a + 4 * b + lz2_small_cost(rem);
+}
+
 // mlen / mpos for every position of the chunk (c.mlen zeroed by the caller).  n <= LZ2_NMAX.
-__device__ inline bool lz2_match_all(ChunkCtx &c)
+// Returns 0 = done, 1 = a table overflowed (run the bucket search), 2 = given up: after the 8-byte level
+// the counts of positions with matches of >= 4 and >= 8 bytes prove a payload of at least `cutoff` bytes.
+__device__ inline int lz2_match_all(ChunkCtx &c, int cutoff)
 {
     uint16_t *A = c.nameA, *B = c.nameB;
-    if (c.n < 3) return true;
+    if (c.n < 3) return 0;
+    const bool bounded = cutoff < 0x7fffffff;
     PHASE_DECL // (dev-only phase timeline, see chunk_codec.cuh)
-    const int any4 = lz2_level4(c, A);
+    const int any4 = lz2_level4(c, A, bounded);
     PHASE(2);
     lz2_level3(c, B);
     PHASE(3);
-    if (!any4) return true;
-    const int any8 = lz2_double(c, A, B, 4);
+    if (!any4) return 0;
+    const int any8 = lz2_double(c, A, B, 4, bounded);
     PHASE(4);
-    if (!lz2_refine(c, A, B, 4)) return false;
+    if (bounded) { // (the counters were complete at the barrier that ended lz2_double)
+        const int n4 = c.red[27], n8 = c.red[26];
+        if (lz2_count_bound(c.n, n8, n4 - n8) >= cutoff) return 2;
+    }
+    if (!lz2_refine(c, A, B, 4)) return 1;
     PHASE(5);
-    if (!any8) return true;
+    if (!any8) return 0;
     const int any16 = lz2_double(c, B, A, 8);
     PHASE(6);
-    if (!lz2_refine(c, B, A, 8)) return false;
+    if (!lz2_refine(c, B, A, 8)) return 1;
     PHASE(7);
-    if (!any16) return true;
+    if (!any16) return 0;
     lz2_double(c, A, B, 16);
     PHASE(8);
     const bool ok = lz2_refine(c, A, B, 16);
     PHASE(9);
-    return ok;
+    return ok ? 0 : 1;
 }
