@@ -3,6 +3,7 @@
 #include "ambc_internal.h"
 #include "decode_codec.cuh"
 #include <thread>
+#include <cstdlib>
 #include <vector>
 
 #define RAW_PIECE 65536u
@@ -92,7 +93,13 @@ static int index_walk(const uint8_t *body, uint64_t body_len, const uint8_t *mar
     // helper threads for large bodies
     unsigned T = 1;
     if (body_len >= g_walk_min_bytes && body_len >= 64) {
-        T = g_walk_threads ? g_walk_threads : std::thread::hardware_concurrency();
+        T = g_walk_threads;
+        if (!T) { // the host cores, shared with the other ranks of this node (torchrun sets LOCAL_WORLD_SIZE)
+            T = std::thread::hardware_concurrency();
+            const char *lws = getenv("LOCAL_WORLD_SIZE");
+            const unsigned ranks = lws ? (unsigned)atoi(lws) : 1u;
+            if (ranks > 1) T /= ranks;
+        }
         T = T < 2 ? 1 : (T > 8 ? 8 : T);
     }
     std::vector<std::vector<WalkRec>> recs(T);
