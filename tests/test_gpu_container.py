@@ -81,6 +81,38 @@ def test_body_fuzz_vs_oracle(eng, chunk):
     assert not bad, bad
 
 
+def test_selection_small_alphabets_vs_oracle(eng):
+    """the Huffman-first order of k_select and its early stop of a Dictionary trial that cannot win
+    (small alphabets, varying skew, sprinkled repeats and runs) never change the outcome: body and
+    method map equal to the oracle's in-order trial of every method (adaptive_compressor.py:537-590)"""
+    r = np.random.RandomState(77)
+    seen = np.zeros(5, dtype=np.int64)
+    for it in range(60):
+        chunk = int(r.choice([1024, 2048, 4096, 4096, 3000]))
+        parts = []
+        for _ in range(int(r.randint(3, 16))):
+            n = chunk if r.rand() < 0.8 else int(r.randint(1, chunk + 1))
+            K = int(r.choice([2, 3, 4, 6, 8, 12, 16, 20, 32, 64, 128, 200]))
+            w = r.rand(K) ** float(r.choice([0.5, 1, 2, 4, 8]))
+            a = r.choice(K, size=n, p=w / w.sum()).astype(np.uint8)
+            a = (a * int(r.choice([1, 3, 7])) + int(r.randint(0, 200))).astype(np.uint8)
+            for _ in range(int(r.choice([0, 2, 30, 100, 300, 600]))):
+                L = int(r.choice([3, 4, 5, 7, 8, 9, 12, 16, 31, 32, 40]))
+                if n > 2 * L + 2:
+                    s_, d_ = int(r.randint(0, n - L)), int(r.randint(0, n - L))
+                    a[d_:d_ + L] = a[s_:s_ + L].copy()
+            if r.rand() < 0.15:
+                s_ = int(r.randint(0, n)); a[s_:s_ + int(r.randint(1, 600))] = int(r.randint(256))
+            parts.append(a)
+        data = np.concatenate(parts).tobytes()
+        body, pm, o = gpu_body(eng, data, chunk)
+        want, wpm = O.compress_body(data, chunk)
+        assert [tuple(p) for p in pm] == [tuple(p) for p in wpm], (it, chunk)
+        assert body == want, (it, chunk)
+        seen += np.array(o.usage[:5])
+    assert seen[1] and seen[2] and seen[3], seen  # RLE, Dictionary and Huffman winners all occur
+
+
 def test_method_masks(eng):
     data = inputs.mixed_file(10, 4096, 909)
     for methods in [(1,), (2,), (3,), (4,), (1, 3), (2, 4), (1, 2, 3, 4), ()]:
