@@ -31,6 +31,14 @@ class ChunkInfo(C.Structure):
                 ("pad", C.c_uint32)]
 
 
+class ShardRec(C.Structure):
+    _fields_ = [("packed_bytes", C.c_uint64), ("first_raw", C.c_int64)]
+
+
+class ShardSlot(C.Structure):
+    _fields_ = [("offset", C.c_uint64), ("state", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 class Pkg(C.Structure):
     _fields_ = [("src_off", C.c_uint64), ("dst_off", C.c_uint64), ("comp_len", C.c_uint32),
                 ("orig_len", C.c_uint32), ("type", C.c_uint32), ("out_len", C.c_uint32)]
@@ -75,6 +83,8 @@ _SIGS = {
                                        C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.c_void_p]),
     "ambc_find_marker_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint32),
                                        C.POINTER(C.c_uint64), C.c_void_p]),
+    "ambc_shard_place": (C.c_int, [C.POINTER(ShardRec), C.c_uint32, C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32,
+                                   C.POINTER(ShardSlot)]),
     "ambc_synth_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),
     "ambc_enable_timing": (None, [C.c_int]),
     "ambc_last_timing": (C.c_int, [C.POINTER(C.c_float)]),

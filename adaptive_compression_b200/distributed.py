@@ -49,6 +49,20 @@ def fold_placement(records):
     return out
 
 
+def fold_placement_native(records, first_chunks, chunk, marker_bytes=4):
+    """the same fold through the C-ABI (ambc_shard_place): -> list of (offset, state); for ranks inside
+    the raw tail the offset is the place of their input bytes in the global body"""
+    import ctypes as C
+    from . import _lib as L
+    n = len(records)
+    recs = (L.ShardRec * n)(*[L.ShardRec(int(b), int(fr)) for b, fr in records])
+    fc = (C.c_uint64 * n)(*[int(x) for x in first_chunks])
+    out = (L.ShardSlot * n)()
+    L.check(L.lib().ambc_shard_place(recs, n, fc, chunk, marker_bytes, out))
+    names = ("packed", "raw_starts_here", "in_raw_tail")
+    return [(int(o.offset), names[o.state]) for o in out]
+
+
 def _device():
     return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
 

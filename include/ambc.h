@@ -252,6 +252,25 @@ int ambc_synth_dev(void *out_dev, uint64_t offset, uint64_t n, uint64_t seed, ui
 void ambc_enable_timing(int on);
 int ambc_last_timing(float *ms4);
 
+/* ---- multi-GPU placement ------------------------------------------------------------
+ * Shards are contiguous chunk ranges compressed independently ("as if no earlier shard had hit a chunk
+ * without a winner").  Every rank all-gathers one 16-byte record (the only exchange of the data path;
+ * torch.distributed / NCCL moves it, this call folds it): packed_bytes = bytes of its local body before
+ * its first raw chunk (END and local raw package removed), first_raw = GLOBAL index of its first chunk
+ * without a winner or -1.  The fold applies the rest-of-file-raw rule (adaptive_compressor.py:586-590)
+ * across shards: out[r].offset = byte offset of rank r's contribution in the global body and
+ * out[r].state = AMBC_SHARD_PACKED (its packed fragment), AMBC_SHARD_RAW_STARTS (packed part, then the
+ * header of the one global raw package and its input from the raw chunk on) or AMBC_SHARD_IN_RAW_TAIL
+ * (its input bytes, verbatim, inside that package).  first_chunk[r] = global index of rank r's first
+ * chunk.  Pure host arithmetic; needs no device. */
+typedef struct { uint64_t packed_bytes; int64_t first_raw; } ambc_shard_rec;
+typedef struct { uint64_t offset; uint32_t state; uint32_t reserved; } ambc_shard_slot;
+#define AMBC_SHARD_PACKED 0
+#define AMBC_SHARD_RAW_STARTS 1
+#define AMBC_SHARD_IN_RAW_TAIL 2
+int ambc_shard_place(const ambc_shard_rec *recs, uint32_t n_ranks, const uint64_t *first_chunk, uint32_t chunk,
+                     uint32_t marker_bytes, ambc_shard_slot *out);
+
 /* pinned host memory helpers for callers without their own allocator */
 void *ambc_host_alloc(uint64_t bytes);
 void ambc_host_free(void *p);

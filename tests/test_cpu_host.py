@@ -210,3 +210,29 @@ def test_index_host_helper_threads_match_serial_walk():
                 assert got == want, (threads, len(b), osz, got[0], want[0])
     finally:
         lib.ambc_set_walk_threads(32 << 20, 0)
+
+
+def test_shard_place_c_abi_matches_python_fold():
+    """ambc_shard_place (host-only entry of the C-ABI) == distributed.fold_placement, and the offsets of
+    ranks inside the raw tail == what shard_fragment computes"""
+    from adaptive_compression_b200 import distributed as D
+    r = np.random.RandomState(5)
+    for _ in range(200):
+        world = int(r.randint(1, 9))
+        chunk = int(r.choice([1024, 4096]))
+        per = int(r.randint(1, 50))
+        first_chunks = [k * per for k in range(world)]
+        recs = []
+        for k in range(world):
+            fr = -1 if r.rand() < 0.7 else first_chunks[k] + int(r.randint(0, per))
+            recs.append((int(r.randint(0, per * chunk)), fr))
+        want = D.fold_placement(recs)
+        got = D.fold_placement_native(recs, first_chunks, chunk)
+        assert [s for _, s in got] == [s for _, s in want]
+        g = next((fr for _, fr in recs if fr >= 0), None)
+        for k, ((off, state), (woff, _)) in enumerate(zip(got, want)):
+            if state != "in_raw_tail":
+                assert off == woff
+            else:
+                packed_total = sum(nb for nb, _ in recs[:next(i for i, (_, fr) in enumerate(recs) if fr >= 0) + 1])
+                assert off == packed_total + 18 + (first_chunks[k] * chunk - g * chunk)
