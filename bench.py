@@ -78,7 +78,10 @@ def cpu_port_run(sample_bytes, steps, warmup, threads):
             td += t2 - t1
     back = np.concatenate([decs[t][:origs[t]] for t in range(threads)])
     assert np.array_equal(back, data), "CPU port round trip failed"
-    return {"compress_s": tc / steps, "decompress_s": td / steps, "bytes": sample_bytes}
+    # the slices are chunk-aligned, so their bodies without the 16-byte END packages, concatenated, plus one
+    # END are the body of the whole sample (the corpus has a winner in every chunk: no raw tail)
+    body = np.concatenate([outs[t][:max(0, lens[t] - 16)] for t in range(threads)] + [outs[0][lens[0] - 16:lens[0]]])
+    return {"compress_s": tc / steps, "decompress_s": td / steps, "bytes": sample_bytes, "body": body}
 
 
 def cpu_sample_bytes(args, threads, budget_s=10.0):
@@ -409,9 +412,15 @@ def run_b200(args):
             args.cpu_sample_mib = cpu_sample_bytes(args, threads) >> 20
             r = cpu_port_run(args.cpu_sample_mib << 20, 1, 0, threads)
             v = (args.cpu_sample_mib << 20) / (r["compress_s"] + r["decompress_s"]) / 1e9
+            # same-run parity: the CUDA body of the sample == the CPU port's body, byte for byte
+            chk = engine.compress_device(t_in[:args.cpu_sample_mib << 20], CHUNK)
+            same = chk.body_len == r["body"].size and bool(
+                torch.equal(chk.body[:chk.body_len].cpu(), torch.from_numpy(r["body"])))
+            assert same, "parity: CUDA body differs from the CPU port's body on the baseline sample"
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "compress_gbps": (args.cpu_sample_mib << 20) / r["compress_s"] / 1e9,
                                     "decompress_gbps": (args.cpu_sample_mib << 20) / r["decompress_s"] / 1e9,
+                                    "parity": "CUDA body == CPU port body on the sample (%d bytes), bit-exact" % r["body"].size,
                                     "sample": "first %d MiB of the same corpus, one pass; C restatement of the reference "
                                               "(oracle/), %d threads; the Python reference itself runs at ~7 KB/s on one "
                                               "core (BASELINE.md §2)" % (args.cpu_sample_mib, threads)}
