@@ -553,22 +553,29 @@ __device__ inline int dec_huff(DecCtx &d, int len, int orig)
     start[tid + 1] = min(nbits, (uint32_t)(tid + 1) * S); // provisional
     __syncthreads();
     const uint32_t lim = min(nbits, (uint32_t)(tid + 1) * S);
+    uint32_t my_start = 0xFFFFFFFFu, my_end = lim, my_cnt = 0; // (my_end: the provisional start of the next range)
     for (int iter = 0; iter <= AMBC_BLOCK; iter++) {
-        uint32_t pos = start[tid], c = 0;
-        while (pos < lim) {
-            int l;
-            huff_next(h, bits, pos, nbits, &l);
-            if (l == 0) { pos = nbits; break; } // incomplete tail code: nothing more decodes
-            pos += l; c++;
+        const uint32_t st = start[tid];
+        bool changed = false;
+        if (st != my_start) { // a range whose start did not move decodes to the same end: nothing to redo
+            uint32_t pos = st, c = 0;
+            while (pos < lim) {
+                int l;
+                huff_next(h, bits, pos, nbits, &l);
+                if (l == 0) { pos = nbits; break; } // incomplete tail code: nothing more decodes
+                pos += l; c++;
+            }
+            if (pos > nbits) pos = nbits;
+            changed = my_end != pos;
+            my_start = st; my_end = pos; my_cnt = c;
         }
-        if (pos > nbits) pos = nbits;
-        bool changed = start[tid + 1] != pos;
         __syncthreads();
-        start[tid + 1] = pos;
-        cnt[tid] = c;
+        if (changed) start[tid + 1] = my_end;
         int any = __syncthreads_or(changed);
         if (!any) break;
     }
+    cnt[tid] = my_cnt;
+    __syncthreads();
     int total;
     int o = block_excl_scan((int)cnt[tid], d.red, &total);
     const int limit = max(orig, 1); // stops after the append that reaches orig_len (:464-468)
