@@ -265,7 +265,7 @@ __device__ inline void chunk_features(ChunkCtx &c, ChunkFeatures &f)
     // RLE pair count: a run of R bytes -> ceil(R/255) pairs (:95-109).  Only needed (and only
     // defined) when the RLE gate holds (:177-180), which is rare outside run-heavy data.
     int pairs = 0;
-    const bool rle_gate = n >= 4 && __ddiv_rn((double)f.rep, (double)(min(1000, n) - 1)) > 0.3;
+    const bool rle_gate = n >= 4 && 10 * f.rep > 3 * (min(1000, n) - 1); // == rep / (s - 1) > 0.3 in fp64
     if (rle_gate) {
         for (int s = tid; s < nsl; s += AMBC_BLOCK) {
             uint32_t w = c.bmask[s];

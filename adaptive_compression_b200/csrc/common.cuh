@@ -35,12 +35,7 @@ __device__ __forceinline__ int warp_incl_scan(int v)
     return v;
 }
 
-__device__ __forceinline__ int warp_sum(int v)
-{
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL_MASK, v, d);
-    return v;
-}
+__device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(FULL_MASK, v); } // one REDUX
 
 // The per-warp partials of a block reduction are combined by every warp with a shuffle scan over
 // lanes 0 .. AMBC_WARPS-1 (a loop over the partials costs AMBC_WARPS loads per thread).

@@ -42,10 +42,11 @@ __device__ SelectOut select_chunk(ChunkCtx &c, uint32_t mask, int ovh)
     HuffScratch hs = huff_scratch(c);
 
     // gates (compression_methods.py:154-180, 315-343, 551-574)
-    bool rle_ok = (mask & 2u) && eligible(1, n) && n >= 4 &&
-                  __ddiv_rn((double)f.rep, (double)(min(1000, n) - 1)) > 0.3;
-    bool lz_ok = (mask & 4u) && eligible(2, n) && n >= 100 &&
-                 __ddiv_rn((double)f.distinct3, (double)min(1000, n)) < 0.8;
+    // (the fp64 quotients rep / (s - 1) > 0.3 and distinct / s < 0.8 as exact integer compares: the
+    // operands are below 1000, so a quotient that is not exactly 3/10 or 8/10 is at least 1e-4 away
+    // from it, and the exact ones round to the very doubles the literals denote)
+    bool rle_ok = (mask & 2u) && eligible(1, n) && n >= 4 && 10 * f.rep > 3 * (min(1000, n) - 1);
+    bool lz_ok = (mask & 4u) && eligible(2, n) && n >= 100 && 10 * f.distinct3 < 8 * min(1000, n);
     bool hf_ok = (mask & 8u) && eligible(3, n) && n >= 100 && f.K >= 2 && f.K <= 255;
     if (hf_ok) {
         double H = f.H;
