@@ -173,7 +173,8 @@ struct ChunkFeatures {
     int distinct3;  // distinct trigrams among the first min(n-3, 1000) positions (:333-336)
     int K;          // distinct byte values
     int rle_pairs;  // (byte,count) pairs RLE would emit -- defined only when the RLE gate holds
-    double H;       // entropy, parallel sum (order-insensitive to ~1e-13)
+    float H;        // entropy in fp32 (|error| < 3e-4): decides the Huffman gate away from 7.0 and bounds its size;
+                    // near 7.0 the caller sums in fp64 in the reference's order (chunk_entropy_ordered)
 };
 
 // extract byte j (compile-time after unrolling) of a 32-byte slice held in two uint4
@@ -288,15 +289,16 @@ __device__ inline void chunk_features(ChunkCtx &c, ChunkFeatures &f)
     }
     PHASE(25);
 
-    // entropy (:566-574), tree sum; the caller resolves near-threshold cases in order
-    double hsum = 0.0;
+    // entropy (:566-574) in fp32; the caller resolves near-threshold cases in fp64, in the reference's order
+    float hsum = 0.0f;
     int k = 0;
+    const float inv_n = 1.0f / (float)n;
     for (int b = tid; b < 256; b += AMBC_BLOCK) {
         uint32_t cnt = c.hist[b];
         if (cnt) {
             k++;
-            double p = __ddiv_rn((double)cnt, (double)n);
-            hsum -= p * log2(p);
+            const float p = (float)cnt * inv_n;
+            hsum -= p * __log2f(p);
         }
     }
     {   // one block reduction for pairs, K and H
@@ -304,12 +306,12 @@ __device__ inline void chunk_features(ChunkCtx &c, ChunkFeatures &f)
         int a = warp_sum(pairs), b = warp_sum(k);
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) hsum += __shfl_xor_sync(FULL_MASK, hsum, d);
-        double *redd = (double *)(redx + 2 * AMBC_WARPS);
+        float *redd = (float *)(redx + 2 * AMBC_WARPS);
         if (lane == 0) { redx[w] = a; redx[AMBC_WARPS + w] = b; redd[w] = hsum; }
         __syncthreads();
-        double rh = 0.0;
+        float rh = lane < AMBC_WARPS ? redd[lane] : 0.0f;
 #pragma unroll
-        for (int i = 0; i < AMBC_WARPS; i++) rh += redd[i]; // fixed order: the same sum in every thread
+        for (int d = 16; d > 0; d >>= 1) rh += __shfl_xor_sync(FULL_MASK, rh, d); // (xor tree: the same sum in every lane)
         f.rle_pairs = warp_sum(lane < AMBC_WARPS ? redx[lane] : 0);
         f.K = warp_sum(lane < AMBC_WARPS ? redx[AMBC_WARPS + lane] : 0);
         f.H = rh;

@@ -49,12 +49,10 @@ __device__ SelectOut select_chunk(ChunkCtx &c, uint32_t mask, int ovh)
     bool lz_ok = (mask & 4u) && eligible(2, n) && n >= 100 && 10 * f.distinct3 < 8 * min(1000, n);
     bool hf_ok = (mask & 8u) && eligible(3, n) && n >= 100 && f.K >= 2 && f.K <= 255;
     if (hf_ok) {
-        double H = f.H;
-        if (fabs(H - 7.0) < 1e-9) { // resolve in the reference's summation order
+        if (fabsf(f.H - 7.0f) < 0.02f) { // near the threshold: fp64, in the reference's summation order (:566-574)
             chunk_first_order(c, hs.firstpos, hs.order);
-            H = chunk_entropy_ordered(c, f.K, hs.order);
-        }
-        hf_ok = H < 7.0;
+            hf_ok = chunk_entropy_ordered(c, f.K, hs.order) < 7.0;
+        } else hf_ok = f.H < 7.0f;
     }
     // Delta (id 4) always produces n bytes, so (n + overhead)/n > 1 never wins (:574-577).
 
@@ -68,7 +66,8 @@ __device__ SelectOut select_chunk(ChunkCtx &c, uint32_t mask, int ovh)
     }
     // Huffman lower bound from the entropy: bits >= max(n, n*H)
     int hf_lb = 0x7fffffff;
-    if (hf_ok) hf_lb = 1 + 5 * f.K + 4 + (int)ceil(fmax((double)n, (double)n * f.H - 0.01) / 8.0);
+    // (f.H is within 3e-4 of the entropy: 0.002 and the 0.01 keep the bound below n * H whatever fp32 rounds to)
+    if (hf_ok) hf_lb = 1 + 5 * f.K + 4 + (int)ceilf(fmaxf((float)n, (float)n * (f.H - 0.002f) - 0.01f) * 0.125f);
     // Huffman first when the Dictionary method looks weak (many distinct trigrams): its size then cuts
     // the match search short (lz2_match_all).  Its code table survives the search in c.hcode / c.hlen.
     const bool hf_first = hf_ok && lz_ok && n <= LZ2_NMAX && 100 * f.distinct3 >= 43 * min(1000, n);
