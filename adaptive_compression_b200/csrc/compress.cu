@@ -32,7 +32,7 @@ __device__ __forceinline__ bool eligible(int id, int n)
 }
 
 // Evaluate one chunk already staged in c; leaves the winner's payload in c.pay.
-__device__ SelectOut select_chunk(ChunkCtx &c, uint32_t mask, int ovh)
+__device__ SelectOut select_chunk(ChunkCtx &c, uint32_t mask, int ovh, unsigned int *trial = nullptr)
 {
     const int n = c.n;
     ChunkFeatures f;
@@ -70,7 +70,8 @@ __device__ SelectOut select_chunk(ChunkCtx &c, uint32_t mask, int ovh)
     if (hf_ok) hf_lb = 1 + 5 * f.K + 4 + (int)ceilf(fmaxf((float)n, (float)n * (f.H - 0.002f) - 0.01f) * 0.125f);
     // Huffman first when the Dictionary method looks weak (many distinct trigrams): its size then cuts
     // the match search short (lz2_match_all).  Its code table survives the search in c.hcode / c.hlen.
-    const bool hf_first = hf_ok && lz_ok && n <= LZ2_NMAX && 100 * f.distinct3 >= 43 * min(1000, n);
+    const bool hf_first = hf_ok && lz_ok && n <= LZ2_NMAX && 100 * f.distinct3 >= 34 * min(1000, n);
+    const bool lz_weak = 100 * f.distinct3 >= 43 * min(1000, n);
     int hf_len = 0x7fffffff, hf_bits = 0; // hf_len: built, and a candidate against RLE
     if (hf_first && hf_lb < best_len && hf_lb + ovh < n) {
         hf_bits = chunk_huff_build(c, hs, f.K);
@@ -84,9 +85,36 @@ __device__ SelectOut select_chunk(ChunkCtx &c, uint32_t mask, int ovh)
         int lb = lz_lower_bound(n);
         if (lb < cutoff && lb + ovh < n) {
             PHASE(10);
-            int len = chunk_lz_encode(c, hf_first ? cutoff : LZ_ABORTED);
-            PHASE(11);
-            if (len < best_len && len + ovh < n) { best_type = 2; best_len = len; }
+            // Prefix trial (a gamble on speed, never on the outcome): with a Huffman payload in hand and a
+            // fair share of distinct trigrams the Dictionary method usually loses clearly.  The exact parse
+            // of the first 5/8 of the chunk (positions below n1 see the same 32-byte look-ahead as in the
+            // whole chunk, so their tokens are the real ones) then already costs more than the cutoff:
+            // tokens starting below n1 cost at least lenp - 62 (the prefix parse may end with <= 31 bytes
+            // of tokens starting at or after n1, <= 2 payload bytes per byte), and the n - np bytes behind
+            // the prefix need at least 4 bytes per 32.  When the bound does not reach the cutoff the whole
+            // chunk is parsed as usual; `trial` counts attempts / aborts per launch and switches the gamble
+            // off where it keeps failing.
+            bool aborted = false;
+            if (hf_first && !lz_weak && hf_len != 0x7fffffff && n >= 2048 && trial) {
+                const unsigned int att = trial[0], hit = trial[1];
+                if (att < 64u || 4u * hit >= 3u * att) {
+                    const int np = ((5 * n / 8) & ~31) + 31;
+                    c.n = np;
+                    const int lenp = chunk_lz_encode(c);
+                    c.n = n;
+                    const int r = n - np;
+                    aborted = lenp - 62 + 4 * (r >> 5) + min(4, 2 * (r & 31)) >= cutoff;
+                    if (threadIdx.x == 0) {
+                        atomicAdd(&trial[0], 1u);
+                        if (aborted) atomicAdd(&trial[1], 1u);
+                    }
+                }
+            }
+            if (!aborted) {
+                int len = chunk_lz_encode(c, (hf_first && lz_weak) ? cutoff : LZ_ABORTED);
+                PHASE(11);
+                if (len < best_len && len + ovh < n) { best_type = 2; best_len = len; }
+            }
         }
     }
     if (hf_first) {
@@ -119,7 +147,8 @@ __device__ SelectOut select_chunk(ChunkCtx &c, uint32_t mask, int ovh)
 __global__ void __launch_bounds__(AMBC_BLOCK, KSEL_MINB)
 k_select(const uint8_t *__restrict__ in, uint64_t total, uint32_t N, uint32_t mask, uint32_t ovh,
          uint8_t *__restrict__ slots, uint64_t slot_stride, uint8_t *__restrict__ type,
-         uint32_t *__restrict__ comp, unsigned long long *first_raw, uint64_t chunk_begin, uint64_t n_chunks)
+         uint32_t *__restrict__ comp, unsigned long long *first_raw, uint64_t chunk_begin, uint64_t n_chunks,
+         unsigned int *trial)
 {
     extern __shared__ uint4 smem4[];
     ChunkCtx c;
@@ -129,7 +158,7 @@ k_select(const uint8_t *__restrict__ in, uint64_t total, uint32_t N, uint32_t ma
         uint64_t off = i * (uint64_t)N;
         int n = (int)min((uint64_t)N, total - off);
         chunk_load(c, in + off, n);
-        SelectOut o = select_chunk(c, mask, (int)ovh);
+        SelectOut o = select_chunk(c, mask, (int)ovh, trial);
         __syncthreads();
         if (o.type != 255) {
             uint8_t *dst = slots + i * slot_stride; // 16-byte aligned
@@ -156,6 +185,7 @@ struct ScanState {
     unsigned long long payload_bytes;
     unsigned long long usage[5];
     unsigned long long carry;      // body bytes before the chunks not yet scanned (piece-wise runs)
+    unsigned int trial[2];         // prefix trials of k_select in this run: attempts, aborts (speed heuristic only)
 };
 
 __device__ __forceinline__ uint64_t pkg_size(uint64_t i, const uint8_t *type, const uint32_t *comp, uint32_t N,
@@ -574,7 +604,7 @@ int ambc_compress_dev_impl(const void *in_dev, uint64_t n, uint32_t chunk, uint3
             if (pieces) CUDA_TRY(cudaStreamWaitEvent(stream, piece_ready[k], 0));
             if (k == 0) ambc_timing_mark(0, stream);
             k_select<<<gch, AMBC_BLOCK, smem, stream>>>((const uint8_t *)in_dev, n, chunk, method_mask, ovh, W + L.slots,
-                                                        L.slot_stride, type, comp, &st->first_raw, c0, c1);
+                                                        L.slot_stride, type, comp, &st->first_raw, c0, c1, st->trial);
             ambc_count_launch();
             if (last) ambc_timing_mark(1, stream);
             // scan + pack of piece k run on their own stream so that k_select of piece k + 1 follows at once
