@@ -31,6 +31,19 @@ while time.time() - t0 < budget:
         if r.rand() < 0.15:
             s = int(r.randint(0, n)); a[s:s + int(r.randint(1, 600))] = int(r.randint(256))
         parts.append(a)
+    if r.rand() < 0.5:  # record-like text: fixed field layouts with random digits / words (the prefix-trial regime)
+        rows = []
+        words = [b"alpha", b"beta", b"gamma", b"delta", b"eps", b"GET", b"POST", b"/v1/items/", b"ok", b"ERROR", b"warn"]
+        fmt = [int(r.randint(0, 4)) for _ in range(int(r.randint(3, 9)))]
+        while sum(len(x) for x in rows) < chunk * int(r.randint(3, 12)):
+            row = []
+            for f in fmt:
+                if f == 0: row.append(b"%d" % r.randint(0, 10 ** int(r.randint(1, 9))))
+                elif f == 1: row.append(words[int(r.randint(len(words)))])
+                elif f == 2: row.append(b"%d.%02d" % (r.randint(0, 1000), r.randint(0, 100)))
+                else: row.append(b"2026-%02d-%02d" % (r.randint(1, 13), r.randint(1, 29)))
+            rows.append(b",".join(row) + b"\n")
+        parts = [np.frombuffer(b"".join(rows), dtype=np.uint8)]
     data = np.concatenate(parts)
     out = engine.compress_device(torch.from_numpy(data).cuda(), chunk)
     body = out.body.cpu().numpy()[:out.body_len].tobytes()
