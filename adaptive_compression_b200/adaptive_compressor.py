@@ -284,9 +284,13 @@ class AdaptiveCompressor:
         out, status = engine.decompress_device(t_body, hdr["original_size"], self.marker_bytes_aligned, known,
                                                gpu_index=True)
         decompressed = out.cpu().numpy()
+        md5 = {}
+        th = threading.Thread(target=lambda: md5.setdefault("d", hashlib.md5(decompressed).digest()))
+        th.start()  # the checksum (a serial chain, GIL released) runs while the file is written
         decompressed.tofile(output_file)
+        th.join()
         self.last_status = status
-        if hashlib.md5(decompressed).digest() != hdr["checksum"]:
+        if md5["d"] != hdr["checksum"]:  # (the output file stays, as in the reference: written at :294, checked at :297-299)
             raise ValueError("Checksum mismatch => possibly corrupted file.")
         elapsed = time.time() - start_t
         dsize = int(decompressed.size)
