@@ -96,8 +96,15 @@ __device__ SelectOut select_chunk(ChunkCtx &c, uint32_t mask, int ovh, unsigned 
             // off where it keeps failing.
             bool aborted = false;
             if (hf_first && !lz_weak && hf_len != 0x7fffffff && n >= 2048 && trial) {
-                const unsigned int att = trial[0], hit = trial[1];
-                if (att < 64u || 4u * hit >= 3u * att) {
+                // one thread reads the counters (other CTAs update them all the time): the whole block must
+                // take the same branch, the calls below are collective
+                if (threadIdx.x == 0) {
+                    const unsigned int att = ((volatile unsigned int *)trial)[0], hit = ((volatile unsigned int *)trial)[1];
+                    c.red[25] = (att < 64u || 4u * hit >= 3u * att) ? 1 : 0;
+                }
+                __syncthreads();
+                const bool go = c.red[25] != 0;
+                if (go) {
                     const int np = ((5 * n / 8) & ~31) + 31;
                     c.n = np;
                     const int lenp = chunk_lz_encode(c);
