@@ -225,7 +225,7 @@ __device__ inline void chunk_features(ChunkCtx &c, ChunkFeatures &f)
     int rep = 0, small = 0;
     if (n >= 4) {
         const int ss = min(1000, n);
-        const int step = max(1, n / ss);
+        const int step = n < 2000 ? 1 : n / 1000; // == max(1, n // ss); constant divisor instead of a runtime division in every thread
         for (int i = tid * step; i < n - 1; i += AMBC_BLOCK * step) {
             int x = c.sd[i], y = c.sd[i + 1];
             rep += (x == y);
