@@ -70,8 +70,11 @@ __device__ SelectOut select_chunk(ChunkCtx &c, uint32_t mask, int ovh, unsigned 
     if (hf_ok) hf_lb = 1 + 5 * f.K + 4 + (int)ceilf(fmaxf((float)n, (float)n * (f.H - 0.002f) - 0.01f) * 0.125f);
     // Huffman first when the Dictionary method looks weak (many distinct trigrams): its size then cuts
     // the match search short (lz2_match_all).  Its code table survives the search in c.hcode / c.hlen.
-    const bool hf_first = hf_ok && lz_ok && n <= LZ2_NMAX && 100 * f.distinct3 >= 34 * min(1000, n);
-    const bool lz_weak = 100 * f.distinct3 >= 43 * min(1000, n);
+    // Chunks above LZ2_NMAX bytes always go Huffman first: their Dictionary trial is the window-aware
+    // bucket search, twenty times the cost of a prefix trial with the names search (below).
+    const bool big = n > LZ2_NMAX;
+    const bool hf_first = hf_ok && lz_ok && (big || 100 * f.distinct3 >= 34 * min(1000, n));
+    const bool lz_weak = !big && 100 * f.distinct3 >= 43 * min(1000, n);
     int hf_len = 0x7fffffff, hf_bits = 0; // hf_len: built, and a candidate against RLE
     if (hf_first && hf_lb < best_len && hf_lb + ovh < n) {
         hf_bits = chunk_huff_build(c, hs, f.K);
@@ -95,23 +98,29 @@ __device__ SelectOut select_chunk(ChunkCtx &c, uint32_t mask, int ovh, unsigned 
             // chunk is parsed as usual; `trial` counts attempts / aborts per launch and switches the gamble
             // off where it keeps failing.
             bool aborted = false;
-            if (hf_first && !lz_weak && hf_len != 0x7fffffff && n >= 2048 && trial) {
+            if (hf_first && !lz_weak && hf_len != 0x7fffffff && n >= 2048 && (trial || big) && c.T) {
                 // one thread reads the counters (other CTAs update them all the time): the whole block must
-                // take the same branch, the calls below are collective
+                // take the same branch, the calls below are collective.  Big chunks always try: the prefix
+                // (the first LZ2_NMAX - 1 bytes, all inside the window of every position) costs a twentieth
+                // of their bucket search.
                 if (threadIdx.x == 0) {
-                    const unsigned int att = ((volatile unsigned int *)trial)[0], hit = ((volatile unsigned int *)trial)[1];
-                    c.red[25] = (att < 64u || 4u * hit >= 3u * att) ? 1 : 0;
+                    int go = 1;
+                    if (!big) {
+                        const unsigned int att = ((volatile unsigned int *)trial)[0], hit = ((volatile unsigned int *)trial)[1];
+                        go = (att < 64u || 4u * hit >= 3u * att) ? 1 : 0;
+                    }
+                    c.red[25] = go;
                 }
                 __syncthreads();
                 const bool go = c.red[25] != 0;
                 if (go) {
-                    const int np = ((5 * n / 8) & ~31) + 31;
+                    const int np = big ? LZ2_NMAX - 1 : ((5 * n / 8) & ~31) + 31;
                     c.n = np;
                     const int lenp = chunk_lz_encode(c);
                     c.n = n;
                     const int r = n - np;
                     aborted = lenp - 62 + 4 * (r >> 5) + min(4, 2 * (r & 31)) >= cutoff;
-                    if (threadIdx.x == 0) {
+                    if (threadIdx.x == 0 && !big) {
                         atomicAdd(&trial[0], 1u);
                         if (aborted) atomicAdd(&trial[1], 1u);
                     }

@@ -13,7 +13,7 @@ budget = float(sys.argv[2]) if len(sys.argv) > 2 else 60.0
 r = np.random.RandomState(seed)
 t0 = time.time(); files = 0; chunks = 0; usage = np.zeros(5, dtype=np.int64)
 while time.time() - t0 < budget:
-    chunk = int(r.choice([1024, 2048, 4096, 4096, 4096, 3000]))
+    chunk = int(r.choice([1024, 2048, 4096, 4096, 4096, 3000, 8192, 6000]))
     parts = []
     for _ in range(int(r.randint(4, 40))):
         n = chunk if r.rand() < 0.8 else int(r.randint(1, chunk + 1))
