@@ -14,6 +14,8 @@
 #include "ambc_internal.h"
 #include <vector>
 #include "chunk_codec.cuh"
+#include "select_fast.cuh"
+#include <cstdlib>
 
 
 // per-chunk decision ------------------------------------------------------------------------
@@ -188,6 +190,43 @@ k_select(const uint8_t *__restrict__ in, uint64_t total, uint32_t N, uint32_t ma
         }
         __syncthreads();
     }
+}
+
+// round-2 kernel (select_fast.cuh): 128 threads and ~38 KB of shared memory per chunk, five CTAs per SM
+template <int NMAX>
+__global__ void __launch_bounds__(SF_T, NMAX <= 4096 ? 5 : 2)
+k_select_fast(const uint8_t *__restrict__ in, uint64_t total, uint32_t N, uint32_t mask, uint32_t ovh,
+              uint8_t *__restrict__ slots, uint64_t slot_stride, uint8_t *__restrict__ type,
+              uint32_t *__restrict__ comp, unsigned long long *first_raw, uint64_t chunk_begin, uint64_t n_chunks)
+{
+    extern __shared__ uint4 smem4[];
+    SfCtx<NMAX> c;
+    sf_carve<NMAX>(c, (uint8_t *)smem4);
+    for (uint64_t i = chunk_begin + blockIdx.x; i < n_chunks; i += gridDim.x) {
+        const uint64_t off = i * (uint64_t)N;
+        const int n = (int)min((uint64_t)N, total - off);
+        sf_load<NMAX>(c, in + off, n);
+        const SfOut o = sf_select<NMAX>(c, mask, (int)ovh);
+        __syncthreads();
+        if (o.type != 255) {
+            uint8_t *dst = slots + i * slot_stride; // 16-byte aligned
+            const int nv = (o.len + 15) >> 4;
+            for (int k = threadIdx.x; k < nv; k += SF_T) ((uint4 *)dst)[k] = ((const uint4 *)c.pay)[k];
+        }
+        if (threadIdx.x == 0) {
+            type[i] = (uint8_t)o.type;
+            comp[i] = (uint32_t)o.len;
+            if (o.type == 255) atomicMin(first_raw, (unsigned long long)i);
+        }
+        __syncthreads();
+    }
+}
+// dev knob: AMBC_SELECT=old keeps the round-1 kernel (A/B timing)
+static bool use_fast_select(uint32_t chunk)
+{
+    static int mode = -1;
+    if (mode < 0) { const char *e = getenv("AMBC_SELECT"); mode = (e && !strcmp(e, "old")) ? 0 : 1; }
+    return mode == 1 && chunk <= 4096;
 }
 
 // ---- package-size scan ---------------------------------------------------------------------
@@ -600,6 +639,7 @@ int ambc_compress_dev_impl(const void *in_dev, uint64_t n, uint32_t chunk, uint3
         size_t psmem = 32 + (((size_t)chunk + 15) & ~(size_t)15) + 32;
         CUDA_TRY(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute(k_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+        CUDA_TRY(cudaFuncSetAttribute(k_select_fast<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SfCfg<4096>::SMEM));
         // piece-wise run (host-buffer path): select / scan / pack of piece k are queued behind the
         // upload of piece k; the finished body bytes of a piece go home while later pieces compute
         bool pieces = piece_ready && n_pieces > 1 && piece_start && piece_start[0] == 0 && piece_start[n_pieces] >= L.n_chunks;
@@ -619,8 +659,13 @@ int ambc_compress_dev_impl(const void *in_dev, uint64_t n, uint32_t chunk, uint3
             const unsigned gt = (unsigned)((c1 - c0 + SCAN_TILE - 1) / SCAN_TILE);
             if (pieces) CUDA_TRY(cudaStreamWaitEvent(stream, piece_ready[k], 0));
             if (k == 0) ambc_timing_mark(0, stream);
-            k_select<<<gch, AMBC_BLOCK, smem, stream>>>((const uint8_t *)in_dev, n, chunk, method_mask, ovh, W + L.slots,
-                                                        L.slot_stride, type, comp, &st->first_raw, c0, c1, st->trial);
+            if (use_fast_select(chunk))
+                k_select_fast<4096><<<gch, SF_T, SfCfg<4096>::SMEM, stream>>>((const uint8_t *)in_dev, n, chunk, method_mask, ovh,
+                                                                             W + L.slots, L.slot_stride, type, comp,
+                                                                             &st->first_raw, c0, c1);
+            else
+                k_select<<<gch, AMBC_BLOCK, smem, stream>>>((const uint8_t *)in_dev, n, chunk, method_mask, ovh, W + L.slots,
+                                                            L.slot_stride, type, comp, &st->first_raw, c0, c1, st->trial);
             ambc_count_launch();
             if (last) ambc_timing_mark(1, stream);
             // scan + pack of piece k run on their own stream so that k_select of piece k + 1 follows at once
@@ -719,6 +764,12 @@ int ambc_compress_dev_impl(const void *in_dev, uint64_t n, uint32_t chunk, uint3
 }
 
 #ifdef AMBC_PHASE_TIMING
+extern "C" int ambc_sf_phase_read(unsigned long long *out48, int reset)
+{
+    cudaMemcpyFromSymbol(out48, g_sf, sizeof(unsigned long long) * 48);
+    if (reset) { unsigned long long z[48] = {0}; cudaMemcpyToSymbol(g_sf, z, sizeof z); }
+    return 0;
+}
 extern "C" int ambc_phase_read(unsigned long long *out32, int reset)
 {
     cudaMemcpyFromSymbol(out32, g_phase, sizeof(unsigned long long) * 32);

@@ -1,0 +1,1025 @@
+// select_fast.cuh -- the chunk trial / select step (adaptive_compressor.py:537-590) for chunks of at most
+// NMAX bytes, round-2 design: one CTA of 128 threads per chunk, ~38 KB of shared memory, five CTAs per SM.
+//
+// What changed against chunk_codec.cuh / lz_names.cuh (round 1), and why:
+//   * The Dictionary trial (compression_methods.py:195-234, 283-313) no longer computes the longest match of
+//     all n positions.  The greedy parse visits a few hundred of them, so the match search is LAZY:
+//       1. positions are bucket-sorted by a hash of their 3 bytes (stable, ascending inside a bucket): one
+//          counting sort with per-warp counters (packed u16, one 64-bit word per bucket), shared atomics only;
+//       2. the scatter pass also yields a bitmap "some earlier position shares my bucket" -- a superset of
+//          "my 3-gram occurred before", so runs of literals are skipped with bit scans;
+//       3. the parse runs as 16 speculative chains (8 lanes each, one per n/16-byte segment).  At a visited
+//          position the 8 lanes compare 8 bucket entries per step against the look-ahead (ascending order:
+//          the scan stops at the first entry >= p, or as soon as a candidate reaches the cap of
+//          min(32, n - p) bytes); the packed key (len << 16 | 0xFFFF - pos) makes the group maximum the
+//          reference's "first strictly longer match" (earliest position among the longest);
+//       4. greedy chains that start at different positions meet quickly (they share every literal and the
+//          end of every match shorter than the cap), so the true chain is stitched from the speculative ones:
+//          a segment is re-parsed from its true entry only until it hits a position its speculative chain
+//          visited.  Match results are a function of the position alone and are memoised (eval bitmap).
+//     The result is exact for any input: candidates are a superset, every length is verified on the bytes.
+//   * Shared-memory atomics on this part are as cheap as stores (measured: 2.6 cycles per warp instruction,
+//     tools/ubench), __match_any_sync costs 64 -- it is used only for the rare lanes of a 32-position block
+//     that collide in a bucket.
+//   * Huffman (compression_methods.py:354-405, 472-549) is built before the Dictionary trial, so its exact
+//     size is the trial's cutoff; the trial is skipped when its lower bound cannot beat it.
+//   * RLE (compression_methods.py:78-114) decides from the run-boundary bitmap alone; a chunk whose RLE payload
+//     is at most the smallest payload the other methods can produce skips histogram, entropy and all trials.
+//
+// Everything is block-collective for blockDim.x == SF_T.
+#pragma once
+#include "common.cuh"
+
+#define SF_T 128                 // threads per CTA
+#define SF_W (SF_T / 32)         // warps
+#define SF_G 8                   // lanes per parse group
+#define SF_NG (SF_T / SF_G)      // parse groups = speculative chains
+#define SF_PAD 64                // zero bytes behind the chunk
+static_assert(SF_W == 4, "the per-bucket counter word holds four 16-bit fields, one per warp");
+
+// dev-only phase timeline (build with -DAMBC_PHASE_TIMING): thread 0 of every CTA adds the clock64() delta since
+// its previous mark to g_sf[id]; SF_COUNT adds work counters
+#ifdef AMBC_PHASE_TIMING
+__device__ unsigned long long g_sf[48];
+#define SF_PH_DECL long long sf_t = clock64();
+#define SF_PH(id) do { if (threadIdx.x == 0) { long long now_ = clock64(); atomicAdd(&g_sf[id], (unsigned long long)(now_ - sf_t)); sf_t = now_; } } while (0)
+#define SF_COUNT(id, v) atomicAdd(&g_sf[id], (unsigned long long)(v))
+#else
+#define SF_PH_DECL
+#define SF_PH(id)
+#define SF_COUNT(id, v)
+#endif
+
+template <int NMAX> struct SfCfg {
+    static constexpr int HB = NMAX > 4096 ? 12 : 11;          // hash bits
+    static constexpr int NB = 1 << HB;                        // buckets
+    static constexpr int NWORDS = NMAX / 32;                  // bitmap words
+    static constexpr int A_BYTES = NB * 8;                    // region A: counters | trigram set | Huffman scratch | mlen + mpos
+    static_assert(A_BYTES >= NMAX * 3 + 64, "mlen + mpos overlay region A");
+    static constexpr int OFF_SD = 0;
+    static constexpr int OFF_A = OFF_SD + NMAX + SF_PAD;
+    static constexpr int OFF_ORD = OFF_A + A_BYTES;           // ord (u16 per position) | payload buffer
+    static constexpr int OFF_BSTART = OFF_ORD + NMAX * 2;
+    static constexpr int OFF_BITS = OFF_BSTART + (((NB + 1) * 2 + 15) & ~15);
+    static constexpr int OFF_HIST = OFF_BITS + 6 * NWORDS * 4;
+    static constexpr int OFF_HCODE = OFF_HIST + 1024;
+    static constexpr int OFF_MISC = OFF_HCODE + 1280;
+    static constexpr int SMEM = OFF_MISC + 512;
+};
+
+template <int NMAX> struct SfCtx {
+    uint8_t *sd;         // chunk bytes + SF_PAD zero bytes
+    uint8_t *A;          // region A
+    uint16_t *ord;       // bucket-sorted positions
+    uint8_t *pay;        // winner's payload (overlays ord)
+    uint16_t *bstart;    // NB + 1 bucket starts
+    uint32_t *bmask, *has3, *eval, *vis, *vis2, *ism; // bitmaps, NWORDS words each
+    uint32_t *hist;      // 256 byte counts
+    uint32_t *hcode;     // [256] Huffman code by symbol
+    uint8_t *hlen;       // [256] Huffman code length by symbol
+    int *red;            // 32 ints of reduction scratch
+    int *gst;            // group state: 4 x SF_NG ints
+    int n;
+    // views of region A
+    __device__ __forceinline__ uint8_t *mlen() const { return A; }
+    __device__ __forceinline__ uint16_t *mpos() const { return (uint16_t *)(A + NMAX); }
+};
+
+template <int NMAX> __device__ __forceinline__ void sf_carve(SfCtx<NMAX> &c, uint8_t *base)
+{
+    using C = SfCfg<NMAX>;
+    c.sd = base + C::OFF_SD;
+    c.A = base + C::OFF_A;
+    c.ord = (uint16_t *)(base + C::OFF_ORD);
+    c.pay = base + C::OFF_ORD;
+    c.bstart = (uint16_t *)(base + C::OFF_BSTART);
+    uint32_t *b = (uint32_t *)(base + C::OFF_BITS);
+    c.bmask = b; c.has3 = b + C::NWORDS; c.eval = b + 2 * C::NWORDS; c.vis = b + 3 * C::NWORDS;
+    c.vis2 = b + 4 * C::NWORDS; c.ism = b + 5 * C::NWORDS;
+    c.hist = (uint32_t *)(base + C::OFF_HIST);
+    c.hcode = (uint32_t *)(base + C::OFF_HCODE);
+    c.hlen = base + C::OFF_HCODE + 1024;
+    c.red = (int *)(base + C::OFF_MISC);
+    c.gst = c.red + 32;
+    c.n = 0;
+}
+
+// ---- block helpers for SF_T threads ------------------------------------------------------------------
+__device__ __forceinline__ int sf_block_sum(int v, volatile int *red)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = __reduce_add_sync(FULL_MASK, v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    return red[0] + red[1] + red[2] + red[3];
+}
+// two sums at once
+__device__ __forceinline__ void sf_block_sum2(int &a, int &b, volatile int *red)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    a = __reduce_add_sync(FULL_MASK, a);
+    b = __reduce_add_sync(FULL_MASK, b);
+    __syncthreads();
+    if (lane == 0) { red[w] = a; red[4 + w] = b; }
+    __syncthreads();
+    a = red[0] + red[1] + red[2] + red[3];
+    b = red[4] + red[5] + red[6] + red[7];
+}
+__device__ __forceinline__ int sf_block_excl_scan(int v, volatile int *red, int *total)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int inc = warp_incl_scan(v);
+    __syncthreads();
+    if (lane == 31) red[w] = inc;
+    __syncthreads();
+    const int r0 = red[0], r1 = red[1], r2 = red[2], r3 = red[3];
+    *total = r0 + r1 + r2 + r3;
+    const int base = (w > 0 ? r0 : 0) + (w > 1 ? r1 : 0) + (w > 2 ? r2 : 0);
+    return base + inc - v;
+}
+
+__device__ __forceinline__ uint32_t sf_hash3(uint32_t tri, int hb) { return (tri * 2654435761u) >> (32 - hb); }
+
+// ---- load ------------------------------------------------------------------------------------------------
+template <int NMAX> __device__ inline void sf_load(SfCtx<NMAX> &c, const uint8_t *__restrict__ src, int n)
+{
+    const int tid = threadIdx.x;
+    c.n = n;
+    if ((((uintptr_t)src) & 15) == 0) {
+        const int nv = n >> 4;
+        const uint4 *s4 = (const uint4 *)src;
+        uint4 *d4 = (uint4 *)c.sd;
+        for (int i = tid; i < nv; i += SF_T) d4[i] = __ldg(s4 + i);
+        for (int i = (nv << 4) + tid; i < n; i += SF_T) c.sd[i] = __ldg(src + i);
+    } else {
+        for (int i = tid; i < n; i += SF_T) c.sd[i] = __ldg(src + i);
+    }
+    const int padend = ((n + 15) & ~15) + SF_PAD;
+    for (int i = n + tid; i < padend; i += SF_T) c.sd[i] = 0;
+    // all six bitmaps start empty
+    for (int i = tid; i < 6 * SfCfg<NMAX>::NWORDS; i += SF_T) c.bmask[i] = 0;
+    __syncthreads();
+}
+
+// ---- run-boundary bitmap, RLE gate and pair count (compression_methods.py:95-109, 165-180) ---------------
+// bmask bit p = (p == 0 || sd[p] != sd[p-1]).  rep = sampled positions i with sd[i] == sd[i+1].
+// Returns rep (block-wide); *pairs = number of (byte, count) pairs RLE emits -- computed only when the gate holds.
+template <int NMAX> __device__ inline bool sf_rle_features(SfCtx<NMAX> &c, int *pairs_out)
+{
+    const int n = c.n, tid = threadIdx.x;
+    const int nw = (n + 31) >> 5;
+    const int ss = min(1000, n);
+    const int step = n < 4 ? 1 : max(1, n / ss);
+    int rep = 0;
+    for (int wd = tid; wd < nw; wd += SF_T) {
+        const uint4 a = *(const uint4 *)(c.sd + 32 * wd);
+        const uint4 b = *(const uint4 *)(c.sd + 32 * wd + 16);
+        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t prevw = wd ? ((uint32_t)c.sd[32 * wd - 1] << 24) : 0;
+        uint32_t mask = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t sh = __funnelshift_l(prevw, w[k], 8); // byte j-1 under byte j
+            const uint32_t x = w[k] ^ sh;
+            const uint32_t y = ((x | ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu)) & 0x80808080u) >> 7; // 1 per non-zero byte
+            mask |= ((y * 0x01020408u) >> 24 & 0xFu) << (4 * k);
+            prevw = w[k];
+        }
+        if (wd == 0) mask |= 1u;
+        const int m = min(32, n - 32 * wd);
+        const uint32_t valid = m == 32 ? 0xFFFFFFFFu : ((1u << m) - 1u);
+        mask &= valid;
+        c.bmask[wd] = mask;
+        // equal-to-next bits: e[j] = sd[32wd+j] == sd[32wd+j+1], for positions below n-1
+        const uint32_t nextb = (c.sd[32 * wd + 32] != (b.w >> 24)) ? 1u : 0u;
+        uint32_t eq = ~((mask >> 1) | (nextb << 31));
+        const int m1 = min(32, n - 1 - 32 * wd); // positions with a successor
+        eq &= m1 >= 32 ? 0xFFFFFFFFu : (m1 <= 0 ? 0u : ((1u << m1) - 1u));
+        uint32_t S;
+        if (step == 1) S = 0xFFFFFFFFu;
+        else if (step == 4) S = 0x11111111u;
+        else {
+            S = 0;
+            int first = (step - (32 * wd) % step) % step;
+            for (int j = first; j < 32; j += step) S |= 1u << j;
+        }
+        rep += __popc(eq & S);
+    }
+    rep = sf_block_sum(rep, c.red); // (also publishes bmask)
+    // gate: rep / (ss - 1) > 0.3 in fp64 == 10 * rep > 3 * (ss - 1) (operands below 1000: quotients other than
+    // exactly 3/10 are >= 1e-4 away from it, and the exact one rounds to the double the literal denotes)
+    const bool gate = n >= 4 && 10 * rep > 3 * (ss - 1);
+    if (!gate) { *pairs_out = 0; return false; }
+    int pairs = 0;
+    for (int wd = tid; wd < nw; wd += SF_T) {
+        const uint32_t mask = c.bmask[wd];
+        if (mask) {
+            pairs += __popc(mask);
+            // only the last run that starts in this word can be longer than 31 bytes
+            const int p = 32 * wd + 31 - __clz(mask);
+            int q = n;
+            for (int w2 = wd + 1; w2 < nw; w2++) {
+                const uint32_t m2 = c.bmask[w2];
+                if (m2) { q = 32 * w2 + __ffs(m2) - 1; break; }
+            }
+            const int R = q - p;
+            if (R > 255) pairs += (R + 254) / 255 - 1;
+        }
+    }
+    *pairs_out = sf_block_sum(pairs, c.red);
+    return true;
+}
+
+// RLE payload -> c.pay (requires bmask).  Returns the length.
+template <int NMAX> __device__ inline int sf_rle_emit(SfCtx<NMAX> &c)
+{
+    const int n = c.n, tid = threadIdx.x;
+    const int nw = (n + 31) >> 5;
+    // words per thread, contiguous, so that one scan places everything (NMAX / 32 <= 2 * SF_T)
+    const int wpt = (nw + SF_T - 1) / SF_T;
+    int pairs = 0;
+    for (int wd = tid * wpt; wd < min(nw, (tid + 1) * wpt); wd++) {
+        const uint32_t mask = c.bmask[wd];
+        if (mask) {
+            pairs += __popc(mask);
+            const int p = 32 * wd + 31 - __clz(mask);
+            int q = n;
+            for (int w2 = wd + 1; w2 < nw; w2++) {
+                const uint32_t m2 = c.bmask[w2];
+                if (m2) { q = 32 * w2 + __ffs(m2) - 1; break; }
+            }
+            const int R = q - p;
+            if (R > 255) pairs += (R + 254) / 255 - 1;
+        }
+    }
+    int total;
+    int off = 2 * sf_block_excl_scan(pairs, c.red, &total);
+    __syncthreads(); // (pay overlays nothing RLE needs, but the scan scratch is reused below)
+    for (int wd = tid * wpt; wd < min(nw, (tid + 1) * wpt); wd++) {
+        uint32_t mask = c.bmask[wd];
+        while (mask) {
+            const int bit = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int p = 32 * wd + bit;
+            int q;
+            if (mask) q = 32 * wd + __ffs(mask) - 1;
+            else {
+                q = n;
+                for (int w2 = wd + 1; w2 < nw; w2++) {
+                    const uint32_t m2 = c.bmask[w2];
+                    if (m2) { q = 32 * w2 + __ffs(m2) - 1; break; }
+                }
+            }
+            int R = q - p;
+            const uint8_t v = c.sd[p];
+            while (R > 0) {
+                const int cnt = R > 255 ? 255 : R;
+                if (off + 2 <= NMAX) { c.pay[off] = v; c.pay[off + 1] = (uint8_t)cnt; }
+                off += 2;
+                R -= cnt;
+            }
+        }
+    }
+    __syncthreads();
+    return 2 * total;
+}
+
+// ---- histogram, distinct byte values, entropy, distinct trigrams -------------------------------------
+struct SfStats { int K; int distinct3; float H; };
+
+template <int NMAX> __device__ inline void sf_stats(SfCtx<NMAX> &c, bool want_tri, SfStats &s)
+{
+    const int n = c.n, tid = threadIdx.x;
+    uint32_t *tri = (uint32_t *)c.A; // 2048-slot open-addressing set (8 KB of region A)
+    for (int i = tid; i < 256; i += SF_T) c.hist[i] = 0;
+    if (want_tri)
+        for (int i = tid; i < 2048 / 4; i += SF_T) ((uint4 *)tri)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    const int nw = (n + 31) >> 5;
+    for (int wd = tid; wd < nw; wd += SF_T) {
+        const uint4 a = *(const uint4 *)(c.sd + 32 * wd);
+        const uint4 b = *(const uint4 *)(c.sd + 32 * wd + 16);
+        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        const int m = min(32, n - 32 * wd);
+        // runs of equal bytes inside the slice are added at once (text has runs of blanks, binary of zeros)
+        uint32_t cur = w[0] & 0xFFu, cnt = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            if (j < m) {
+                const uint32_t v = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                if (v == cur) cnt++;
+                else { atomicAdd(&c.hist[cur], cnt); cur = v; cnt = 1; }
+            }
+        }
+        atomicAdd(&c.hist[cur], cnt);
+    }
+    // distinct trigrams among the first min(n - 3, 1000) positions (compression_methods.py:326-343)
+    int ins = 0;
+    if (want_tri) {
+        const int cnt3 = min(n - 3, min(1000, n));
+        for (int i = tid; i < cnt3; i += SF_T) {
+            const uint32_t t = lds_u32u(c.sd + i) & 0xFFFFFFu;
+            const uint32_t key = t + 1;
+            uint32_t h = (t * 2654435761u) >> 21;
+            for (;;) {
+                const uint32_t old = atomicCAS(&tri[h], 0u, key);
+                if (old == 0u) { ins++; break; }
+                if (old == key) break;
+                h = (h + 1) & 2047;
+            }
+        }
+    }
+    __syncthreads();
+    // entropy in fp32 (compression_methods.py:566-574); the caller redoes near-threshold cases in fp64
+    float hsum = 0.0f;
+    int k = 0;
+    const float inv_n = 1.0f / (float)n;
+    for (int b = tid; b < 256; b += SF_T) {
+        const uint32_t cnt = c.hist[b];
+        if (cnt) {
+            k++;
+            const float p = (float)cnt * inv_n;
+            hsum -= p * __log2f(p);
+        }
+    }
+    const int lane = tid & 31, w = tid >> 5;
+    k = __reduce_add_sync(FULL_MASK, k);
+    ins = __reduce_add_sync(FULL_MASK, ins);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) hsum += __shfl_xor_sync(FULL_MASK, hsum, d);
+    __syncthreads();
+    if (lane == 0) { c.red[w] = k; c.red[4 + w] = ins; ((float *)c.red)[8 + w] = hsum; }
+    __syncthreads();
+    s.K = c.red[0] + c.red[1] + c.red[2] + c.red[3];
+    s.distinct3 = c.red[4] + c.red[5] + c.red[6] + c.red[7];
+    const float *rf = (const float *)c.red;
+    s.H = (rf[8] + rf[9]) + (rf[10] + rf[11]);
+    __syncthreads();
+}
+
+// ---- Huffman ---------------------------------------------------------------------------------------
+// scratch inside region A (dead before the Dictionary index is built, free again after the trial)
+struct SfHuff {
+    uint32_t *ck;       // [256] compacted keys (count << 8 | symbol)
+    uint32_t *nodeW;    // [512] (weight << 8 | leader), sorted leaves then merged nodes
+    uint16_t *parent;   // [512]
+    uint8_t *nbit;      // [512]
+    uint8_t *leafsym;   // [256]
+    uint32_t *firstpos; // [256]
+    uint8_t *order;     // [256] symbols in first-occurrence order
+    uint32_t *bw;       // bit words of the stream (NMAX bytes + 16), behind the rest
+};
+template <int NMAX> __device__ __forceinline__ SfHuff sf_huff_scratch(SfCtx<NMAX> &c)
+{
+    SfHuff h;
+    uint8_t *X = c.A;
+    h.ck = (uint32_t *)X;
+    h.nodeW = (uint32_t *)(X + 1024);
+    h.parent = (uint16_t *)(X + 3072);
+    h.nbit = X + 4096;
+    h.leafsym = X + 4608;
+    h.firstpos = (uint32_t *)(X + 4864);
+    h.order = X + 5888;
+    h.bw = (uint32_t *)(X + 6144);
+    return h;
+}
+static_assert(6144 + 4096 + 16 <= SfCfg<4096>::A_BYTES && 6144 + 8192 + 16 <= SfCfg<8192>::A_BYTES, "Huffman scratch fits region A");
+
+// first-occurrence order of the byte values (Counter insertion order, compression_methods.py:368-370 / :566)
+template <int NMAX> __device__ inline void sf_first_order(SfCtx<NMAX> &c, SfHuff &h, int K)
+{
+    const int n = c.n, tid = threadIdx.x;
+    for (int i = tid; i < 256; i += SF_T) h.firstpos[i] = 0xFFFFFFFFu;
+    __syncthreads();
+    volatile uint32_t *fpv = h.firstpos;
+    for (int s = tid; 8 * s < n; s += SF_T) { // ascending sweep: the guards fail almost always after the first pass
+        const uint2 w = *(const uint2 *)(c.sd + 8 * s);
+        const int m = min(8, n - 8 * s);
+        uint32_t prev = 0x100u;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t v = ((j < 4 ? w.x : w.y) >> (8 * (j & 3))) & 0xFFu;
+            if (j < m && v != prev && fpv[v] > (uint32_t)(8 * s + j)) atomicMin(&h.firstpos[v], (uint32_t)(8 * s + j));
+            prev = v;
+        }
+    }
+    __syncthreads();
+    // rank of each present symbol by first position (K <= 256 keys, all distinct)
+    int *cntK = c.red + 16;
+    if (tid == 0) *cntK = 0;
+    __syncthreads();
+    for (int b = tid; b < 256; b += SF_T) {
+        const uint32_t fp = h.firstpos[b];
+        if (fp != 0xFFFFFFFFu) h.ck[atomicAdd(cntK, 1)] = (fp << 8) | (uint32_t)b;
+    }
+    __syncthreads();
+    for (int j = tid; j < K; j += SF_T) {
+        const uint32_t key = h.ck[j];
+        int r = 0;
+        for (int x = 0; x < K; x++) r += (h.ck[x] < key);
+        h.order[r] = (uint8_t)(key & 0xFFu);
+    }
+    __syncthreads();
+}
+
+// exact Python-order entropy: e -= p * log2(p) over the Counter's insertion order, no FMA contraction
+template <int NMAX> __device__ inline double sf_entropy_ordered(SfCtx<NMAX> &c, SfHuff &h, int K)
+{
+    volatile double *out = (volatile double *)(c.red + 20);
+    if (threadIdx.x == 0) {
+        double e = 0.0;
+        for (int r = 0; r < K; r++) {
+            const double p = __ddiv_rn((double)c.hist[h.order[r]], (double)c.n);
+            e = __dsub_rn(e, __dmul_rn(p, log2(p)));
+        }
+        out[0] = e;
+    }
+    __syncthreads();
+    const double e = out[0];
+    __syncthreads();
+    return e;
+}
+
+// The reference's tree for the counts in c.hist (2 <= K <= 256): repeatedly merge the two smallest nodes under
+// (weight, leader); lo gets bit 0, hi bit 1; leader(merged) = leader(lo) (compression_methods.py:482-494).
+// Leaves are sorted by (weight, symbol) and merged nodes come out in that order, so two queues suffice.
+// Fills c.hlen / c.hcode, returns the total number of code bits.
+template <int NMAX> __device__ inline int sf_huff_build(SfCtx<NMAX> &c, SfHuff &h, int K)
+{
+    const int tid = threadIdx.x;
+    int *cntK = c.red + 16;
+    if (tid == 0) *cntK = 0;
+    for (int b = tid; b < 256; b += SF_T) { c.hlen[b] = 0; c.hcode[b] = 0; }
+    __syncthreads();
+    for (int b = tid; b < 256; b += SF_T) {
+        const uint32_t cnt = c.hist[b];
+        if (cnt) h.ck[atomicAdd(cntK, 1)] = (cnt << 8) | (uint32_t)b;
+    }
+    __syncthreads();
+    for (int j = tid; j < K; j += SF_T) { // rank sort: keys are distinct
+        const uint32_t key = h.ck[j];
+        int r = 0;
+        for (int x = 0; x < K; x++) r += (h.ck[x] < key);
+        h.nodeW[r] = key;
+        h.leafsym[r] = (uint8_t)(key & 0xFFu);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int li = 0, mi = K, t = K;
+        uint32_t kl = h.nodeW[0];
+        uint32_t km = 0xFFFFFFFFu;
+        for (int it = 0; it < K - 1; it++) {
+            int pick[2];
+            uint32_t pk[2];
+#pragma unroll
+            for (int z = 0; z < 2; z++) {
+                const bool hasL = li < K, hasM = mi < t;
+                const bool takeL = (hasL && hasM) ? kl < km : hasL;
+                if (takeL) {
+                    pick[z] = li; pk[z] = kl;
+                    li++;
+                    if (li < K) kl = h.nodeW[li];
+                } else {
+                    pick[z] = mi; pk[z] = km;
+                    mi++;
+                    if (mi < t) km = h.nodeW[mi];
+                }
+            }
+            const uint32_t nk = (((pk[0] >> 8) + (pk[1] >> 8)) << 8) | (pk[0] & 0xFFu);
+            h.nodeW[t] = nk;
+            h.parent[pick[0]] = (uint16_t)t; h.nbit[pick[0]] = 0;
+            h.parent[pick[1]] = (uint16_t)t; h.nbit[pick[1]] = 1;
+            if (mi == t) km = nk;
+            t++;
+        }
+    }
+    __syncthreads();
+    const int root = 2 * K - 2;
+    int bits = 0;
+    for (int j = tid; j < K; j += SF_T) {
+        int node = j, len = 0;
+        uint32_t code = 0;
+        while (node != root) {
+            code |= (uint32_t)h.nbit[node] << len;
+            len++;
+            node = h.parent[node];
+        }
+        const int sym = h.leafsym[j];
+        c.hlen[sym] = (uint8_t)len;
+        c.hcode[sym] = code;
+        bits += len * (int)c.hist[sym];
+    }
+    return sf_block_sum(bits, c.red);
+}
+
+// Payload (table in first-occurrence order + bit count + MSB-first bit stream, compression_methods.py:379-403)
+// -> c.pay.  Requires sf_huff_build (c.hcode / c.hlen) and region A free.
+template <int NMAX> __device__ inline int sf_huff_emit(SfCtx<NMAX> &c, SfHuff &h, int K, int total_bits)
+{
+    const int n = c.n, tid = threadIdx.x;
+    sf_first_order(c, h, K);
+    const int hdr = 1 + 5 * K + 4;
+    const int nbytes = (total_bits + 7) >> 3;
+    if (tid == 0) c.pay[0] = (uint8_t)K;
+    for (int r = tid; r < K; r += SF_T) {
+        const int o = 1 + 5 * r;
+        if (o + 5 <= NMAX) {
+            const int sym = h.order[r];
+            c.pay[o] = (uint8_t)sym;
+            store_u32le(c.pay + o + 1, c.hist[sym]);
+        }
+    }
+    if (tid == 0 && hdr <= NMAX) store_u32le(c.pay + hdr - 4, (uint32_t)total_bits);
+    const int nwords = (total_bits + 31) >> 5;
+    const int wcap = min(nwords, NMAX / 4 + 1);
+    for (int i = tid; i < wcap; i += SF_T) h.bw[i] = 0;
+    // 32-byte slices, contiguous per thread
+    const int nsl = (n + 31) >> 5;
+    const int spt = (nsl + SF_T - 1) / SF_T;
+    int mybits = 0;
+    for (int s = tid * spt; s < min(nsl, (tid + 1) * spt); s++) {
+        const uint4 a = *(const uint4 *)(c.sd + 32 * s);
+        const uint4 b = *(const uint4 *)(c.sd + 32 * s + 16);
+        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        const int m = min(32, n - 32 * s);
+#pragma unroll
+        for (int j = 0; j < 32; j++)
+            if (j < m) mybits += c.hlen[(w[j >> 2] >> (8 * (j & 3))) & 0xFFu];
+    }
+    int tot;
+    const int g = sf_block_excl_scan(mybits, c.red, &tot); // (its barriers also order the zeroing of bw)
+    {
+        int wi = g >> 5, used = g & 31;
+        uint32_t cur = 0;
+        bool first = true; // the first and last words of a thread may be shared with its neighbours
+        for (int s = tid * spt; s < min(nsl, (tid + 1) * spt); s++) {
+            const uint4 a = *(const uint4 *)(c.sd + 32 * s);
+            const uint4 b = *(const uint4 *)(c.sd + 32 * s + 16);
+            const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            const int m = min(32, n - 32 * s);
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                if (j < m) {
+                    const int sym = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                    const uint32_t code = c.hcode[sym];
+                    const int l = c.hlen[sym];
+                    const int space = 32 - used;
+                    if (l < space) {
+                        cur |= code << (space - l);
+                        used += l;
+                    } else {
+                        cur |= code >> (l - space);
+                        if (wi < wcap) { if (first) atomicOr(&h.bw[wi], cur); else h.bw[wi] = cur; }
+                        first = false;
+                        wi++;
+                        used = l - space;
+                        cur = used ? code << (32 - used) : 0u;
+                    }
+                }
+            }
+        }
+        if (used && wi < wcap) atomicOr(&h.bw[wi], cur);
+    }
+    __syncthreads();
+    for (int k = tid; k < nbytes; k += SF_T)
+        if (hdr + k < NMAX) c.pay[hdr + k] = (uint8_t)(h.bw[k >> 2] >> (24 - 8 * (k & 3)));
+    __syncthreads();
+    return hdr + nbytes;
+}
+
+// ---- Dictionary: index --------------------------------------------------------------------------------
+// Lower bound of the Dictionary payload for n bytes: the first token is a literal, every other token covers
+// at most 32 bytes (lookahead_size) for at least 2 bytes of output.
+__host__ __device__ inline int sf_lz_lower_bound(int n)
+{
+    if (n <= 0) return 0;
+    const int r = (n - 1) % 32;
+    return 2 + 4 * ((n - 1) / 32) + (2 * r < 4 ? 2 * r : 4);
+}
+
+// Stable bucket sort of the positions [0, n - 2) by the hash of their 3 bytes: c.ord (ascending inside each
+// bucket), c.bstart, and c.has3 bit p = "an earlier position lies in p's bucket".
+template <int NMAX> __device__ inline void sf_lz_index(SfCtx<NMAX> &c)
+{
+    using C = SfCfg<NMAX>;
+    const int n = c.n, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int P = n - 2;                          // positions with 3 bytes
+    const int nblk = (P + 31) >> 5;               // 32-position blocks
+    const int Rw = (nblk + SF_W - 1) / SF_W;      // blocks per warp, contiguous: warp order == position order
+    uint64_t *cnt64 = (uint64_t *)c.A;            // per bucket: four u16 fields, one per warp
+    uint32_t *cnt32 = (uint32_t *)c.A;
+    volatile uint16_t *cnt16 = (volatile uint16_t *)c.A;
+    SF_PH_DECL
+    for (int i = tid; i < C::NB / 2; i += SF_T) ((uint4 *)c.A)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    const uint32_t inc = (w & 1) ? 0x10000u : 1u;
+    const int fsel = w >> 1;
+    // pass 1: counts (order irrelevant)
+    for (int r = 0; r < Rw; r++) {
+        const int p = 32 * (w * Rw + r) + lane;
+        if (p < P) {
+            const uint32_t h = sf_hash3(lds_u32u(c.sd + p) & 0xFFFFFFu, C::HB);
+            atomicAdd(&cnt32[2 * h + fsel], inc);
+        }
+    }
+    __syncthreads();
+    SF_PH(10);
+    {   // exclusive scan over (bucket-major, warp-minor); thread owns BPT consecutive buckets
+        constexpr int BPT = C::NB / SF_T;
+        uint64_t x[BPT];
+        uint32_t run = 0;
+#pragma unroll
+        for (int k = 0; k < BPT; k += 2) {
+            const ulonglong2 v = *(const ulonglong2 *)(cnt64 + BPT * tid + k);
+            x[k] = v.x; x[k + 1] = v.y;
+        }
+#pragma unroll
+        for (int k = 0; k < BPT; k++) {
+            const uint64_t v = x[k];
+            const uint64_t incl = v + (v << 16) + (v << 32) + (v << 48); // inclusive prefix of the four fields
+            x[k] = (incl - v) + (uint64_t)run * 0x0001000100010001ull;
+            run += (uint32_t)(incl >> 48);
+        }
+        int tot;
+        const uint32_t base = (uint32_t)sf_block_excl_scan((int)run, c.red, &tot);
+        const uint64_t b4 = (uint64_t)base * 0x0001000100010001ull;
+#pragma unroll
+        for (int k = 0; k < BPT; k += 2) {
+            ulonglong2 v;
+            v.x = x[k] + b4; v.y = x[k + 1] + b4;
+            *(ulonglong2 *)(cnt64 + BPT * tid + k) = v;
+            c.bstart[BPT * tid + k] = (uint16_t)v.x;
+            c.bstart[BPT * tid + k + 1] = (uint16_t)v.y;
+        }
+        if (tid == 0) c.bstart[C::NB] = (uint16_t)P;
+    }
+    __syncthreads();
+    SF_PH(11);
+    // pass 2: ordered scatter.  A warp walks its blocks in ascending order; inside a block the lanes that share a
+    // bucket (rare) are ranked by lane with one __match_any_sync among themselves.
+    for (int r = 0; r < Rw; r++) {
+        const int blk = w * Rw + r;
+        if (blk >= nblk) break;
+        const int p = 32 * blk + lane;
+        const bool valid = p < P;
+        uint32_t h = 0, c0 = 0;
+        if (valid) {
+            h = sf_hash3(lds_u32u(c.sd + p) & 0xFFFFFFu, C::HB);
+            c0 = cnt16[4 * h + w];
+        }
+        __syncwarp();
+        if (valid) atomicAdd(&cnt32[2 * h + fsel], inc);
+        __syncwarp();
+        uint32_t m = 0;
+        if (valid) m = (uint32_t)cnt16[4 * h + w] - c0;
+        const bool multi = valid && m > 1;
+        const uint32_t cm = __ballot_sync(FULL_MASK, multi);
+        uint32_t cl = 0;
+        if (multi) {
+            const uint32_t peers = __match_any_sync(cm, h);
+            cl = __popc(peers & ((1u << lane) - 1u));
+        }
+        const uint32_t slot = c0 + cl;
+        bool has = false;
+        if (valid) {
+            c.ord[slot] = (uint16_t)p;
+            has = slot > (uint32_t)c.bstart[h];
+        }
+        const uint32_t hw = __ballot_sync(FULL_MASK, has);
+        if (lane == 0) c.has3[blk] = hw;
+    }
+    __syncthreads();
+    SF_PH(12);
+}
+
+// ---- Dictionary: lazy match evaluation ---------------------------------------------------------------
+// Longest match for position p among the earlier entries of its bucket (earliest among the longest), by the
+// SF_G lanes of a group.  Returns len << 16 | (0xFFFF - pos), or 0 when no match of >= 3 bytes exists.
+template <int NMAX> __device__ __forceinline__ uint32_t sf_evaluate(const SfCtx<NMAX> &c, int p, uint32_t gmask, int sub)
+{
+    using C = SfCfg<NMAX>;
+    const int n = c.n;
+    const uint8_t *sp = c.sd + p;
+    const uint32_t *pwb = (const uint32_t *)((uintptr_t)sp & ~(uintptr_t)3);
+    const uint32_t psh = ((uintptr_t)sp & 3) * 8;
+    const uint32_t wp0 = __funnelshift_r(pwb[0], pwb[1], psh);
+    const int cap = min(32, n - p);
+    const uint32_t h = sf_hash3(wp0 & 0xFFFFFFu, C::HB);
+    const int i0 = c.bstart[h], i1 = c.bstart[h + 1];
+    uint32_t best = 0;
+    if (sub == 0) SF_COUNT(30, 1);
+    for (int i = i0 + sub;; i += SF_G) {
+        if (sub == 0) SF_COUNT(31, 1);
+        const int q = i < i1 ? (int)c.ord[i] : 0x7FFF;
+        const bool stop = q >= p;                          // ascending: nothing behind it is earlier than p
+        bool cand = !stop;
+        if (NMAX > 4096) cand = cand && (q + 4096 >= p);   // window_size (compression_methods.py:294)
+        uint32_t key = 0;
+        if (cand) {
+            const uint8_t *sq = c.sd + q;
+            const uint32_t *qwb = (const uint32_t *)((uintptr_t)sq & ~(uintptr_t)3);
+            const uint32_t qsh = ((uintptr_t)sq & 3) * 8;
+            uint32_t qlo = qwb[1];
+            uint32_t x = __funnelshift_r(qwb[0], qlo, qsh) ^ wp0;
+            if ((x & 0xFFFFFFu) == 0) {
+                int len;
+                if (x) len = 3;
+                else {
+                    len = 32;
+                    uint32_t plo = pwb[1];
+#pragma unroll 1
+                    for (int k = 1; k < 8; k++) {
+                        const uint32_t qhi = qwb[k + 1], phi = pwb[k + 1];
+                        x = __funnelshift_r(qlo, qhi, qsh) ^ __funnelshift_r(plo, phi, psh);
+                        SF_COUNT(32, 1);
+                        if (x) { len = 4 * k + ((__ffs(x) - 1) >> 3); break; }
+                        if (4 * k + 4 >= cap) break; // (the rest lies beyond the look-ahead)
+                        qlo = qhi; plo = phi;
+                    }
+                }
+                len = min(len, cap);
+                key = ((uint32_t)len << 16) | (uint32_t)(0xFFFF - q);
+            }
+        }
+        key = max(key, __shfl_xor_sync(gmask, key, 1));
+        key = max(key, __shfl_xor_sync(gmask, key, 2));
+        key = max(key, __shfl_xor_sync(gmask, key, 4));
+        best = max(best, key);
+        const uint32_t anystop = __ballot_sync(gmask, stop) & gmask;
+        if (anystop || (int)(best >> 16) >= cap) break;
+    }
+    return best;
+}
+
+// One chain: tokens from position p until the chain leaves [.., s1).  FIX = false: speculative chain of a
+// segment (marks c.vis).  FIX = true: the true chain entering the segment at p; marks c.vis2 and stops as
+// soon as it meets the speculative chain (returns -1 - meeting position).  Otherwise returns the exit position.
+template <int NMAX, bool FIX>
+__device__ __forceinline__ int sf_chain(SfCtx<NMAX> &c, int p, int s1, uint32_t gmask, int sub)
+{
+    uint32_t *mark = FIX ? c.vis2 : c.vis;
+    uint8_t *mlen = c.mlen();
+    uint16_t *mpos = c.mpos();
+    while (p < s1) {
+        // next position at or after p whose bucket holds an earlier entry; everything before it is a literal
+        int nx;
+        {
+            int wd = p >> 5;
+            uint32_t hw = c.has3[wd] & (0xFFFFFFFFu << (p & 31));
+            for (;;) {
+                if (hw) { nx = 32 * wd + __ffs(hw) - 1; break; }
+                wd++;
+                if (32 * wd >= s1) { nx = s1; break; }
+                hw = c.has3[wd];
+            }
+            nx = min(nx, s1);
+        }
+        if (nx > p) {
+            int lim = nx;
+            if (FIX) { // does the speculative chain visit one of the literals [p, nx)?
+                int wd = p >> 5;
+                uint32_t vw = c.vis[wd] & (0xFFFFFFFFu << (p & 31));
+                for (;;) {
+                    if (vw) { lim = min(nx, 32 * wd + __ffs(vw) - 1); break; }
+                    wd++;
+                    if (32 * wd >= nx) break;
+                    vw = c.vis[wd];
+                }
+            }
+            if (sub == 0) { // set bits [p, lim)
+                for (int wd = p >> 5; 32 * wd < lim; wd++) {
+                    const int lo = max(p, 32 * wd) & 31, hi = min(lim, 32 * wd + 32) - 32 * wd; // bits [lo, hi)
+                    const uint32_t bits = (hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & (0xFFFFFFFFu << lo);
+                    mark[wd] |= bits;
+                }
+            }
+            __syncwarp(gmask);
+            if (FIX && lim < nx) return -1 - lim;
+            p = nx;
+            if (p >= s1) break;
+        }
+        const uint32_t bit = 1u << (p & 31);
+        const int wd = p >> 5;
+        if (FIX && (c.vis[wd] & bit)) return -1 - p;
+        int L;
+        if (c.eval[wd] & bit) L = mlen[p];
+        else {
+            const uint32_t key = sf_evaluate<NMAX>(c, p, gmask, sub);
+            L = (int)(key >> 16);
+            if (sub == 0) {
+                mlen[p] = (uint8_t)L;
+                mpos[p] = (uint16_t)(0xFFFF - (key & 0xFFFFu));
+                c.eval[wd] |= bit;
+                if (L >= 3) c.ism[wd] |= bit;
+            }
+        }
+        if (sub == 0) mark[wd] |= bit;
+        __syncwarp(gmask);
+        p += L >= 3 ? L : 1;
+    }
+    return p;
+}
+
+// Exact Dictionary payload length of the chunk; afterwards c.vis2 holds the token-start bitmap of the true
+// chain, c.ism marks the match tokens, mlen / mpos hold their lengths and sources.  Requires sf_lz_index.
+template <int NMAX> __device__ inline int sf_lz_parse(SfCtx<NMAX> &c)
+{
+    using C = SfCfg<NMAX>;
+    const int n = c.n, tid = threadIdx.x, lane = tid & 31;
+    const int sub = lane & (SF_G - 1), grp = tid / SF_G;
+    const uint32_t gmask = ((1u << SF_G) - 1u) << (lane & ~(SF_G - 1));
+    const int seg = max(32, (((n + SF_NG - 1) / SF_NG) + 31) & ~31);
+    const int s0 = grp * seg, s1 = min(n, s0 + seg);
+    int *gspec = c.gst, *gcur = c.gst + SF_NG, *gdone = c.gst + 2 * SF_NG, *gmerge = c.gst + 3 * SF_NG;
+    SF_PH_DECL
+    // speculative chains
+    int ex = s0;
+    if (s0 < n) ex = sf_chain<NMAX, false>(c, s0, s1, gmask, sub);
+    if (sub == 0) { gspec[grp] = ex; gcur[grp] = ex; gdone[grp] = s0; gmerge[grp] = s0; }
+    SF_PH(13);
+    __syncthreads();
+    SF_PH(14);
+    // stitch: the true chain enters segment g where the true chain of segment g - 1 left it
+    for (int round = 0; round < SF_NG; round++) {
+        const int e = grp == 0 ? 0 : gcur[grp - 1];
+        const bool redo = s0 < n && grp > 0 && e != gdone[grp];
+        __syncthreads(); // every gcur has been read
+        if (redo) {
+            for (int wd = (s0 >> 5) + sub; 32 * wd < s1; wd += SF_G) c.vis2[wd] = 0;
+            __syncwarp(gmask);
+            int cur, mg;
+            if (e >= s1) { cur = e; mg = s1; }
+            else {
+                const int x = sf_chain<NMAX, true>(c, e, s1, gmask, sub);
+                if (x < 0) { mg = -1 - x; cur = gspec[grp]; }
+                else { mg = s1; cur = x; }
+            }
+            if (sub == 0) { gcur[grp] = cur; gmerge[grp] = mg; gdone[grp] = e; }
+        }
+        if (!__syncthreads_or(redo)) break;
+    }
+    SF_PH(15);
+    // token starts of the true chain: vis2 | (vis at or behind the meeting point)
+    int bytes = 0;
+    for (int wd = tid; wd < C::NWORDS; wd += SF_T) {
+        uint32_t reach = 0;
+        if (32 * wd < n) {
+            const int g = (32 * wd) / seg;
+            const int mg = gmerge[g];
+            uint32_t keep;
+            if (mg <= 32 * wd) keep = 0xFFFFFFFFu;
+            else if (mg >= 32 * wd + 32) keep = 0;
+            else keep = 0xFFFFFFFFu << (mg - 32 * wd);
+            reach = c.vis2[wd] | (c.vis[wd] & keep);
+            bytes += 2 * __popc(reach) + 2 * __popc(reach & c.ism[wd]);
+        }
+        c.vis2[wd] = reach;
+    }
+    return sf_block_sum(bytes, c.red);
+}
+
+// Dictionary payload -> c.pay (after sf_lz_parse; ord is dead by now)
+template <int NMAX> __device__ inline void sf_lz_emit(SfCtx<NMAX> &c)
+{
+    using C = SfCfg<NMAX>;
+    const int n = c.n, tid = threadIdx.x;
+    const int nw = (n + 31) >> 5;
+    const int wpt = (nw + SF_T - 1) / SF_T; // words per thread, contiguous
+    int bytes = 0;
+    for (int wd = tid * wpt; wd < min(nw, (tid + 1) * wpt); wd++) {
+        const uint32_t reach = c.vis2[wd];
+        bytes += 2 * __popc(reach) + 2 * __popc(reach & c.ism[wd]);
+    }
+    int total;
+    int off = sf_block_excl_scan(bytes, c.red, &total);
+    uint16_t *pay16 = (uint16_t *)c.pay; // token offsets are even
+    const uint8_t *mlen = c.mlen();
+    const uint16_t *mpos = c.mpos();
+    for (int wd = tid * wpt; wd < min(nw, (tid + 1) * wpt); wd++) {
+        uint32_t reach = c.vis2[wd];
+        const uint32_t mm = c.ism[wd];
+        while (reach) {
+            const int bit = __ffs(reach) - 1;
+            reach &= reach - 1;
+            const int p = 32 * wd + bit;
+            if ((mm >> bit) & 1u) {
+                if (off + 4 <= NMAX) {
+                    const int d = p - (int)mpos[p];
+                    pay16[off >> 1] = (uint16_t)(1u | ((uint32_t)(d & 0xFF) << 8));
+                    pay16[(off >> 1) + 1] = (uint16_t)((uint32_t)(d >> 8) | ((uint32_t)mlen[p] << 8));
+                }
+                off += 4;
+            } else {
+                if (off + 2 <= NMAX) pay16[off >> 1] = (uint16_t)((uint32_t)c.sd[p] << 8);
+                off += 2;
+            }
+        }
+    }
+    (void)C::NB;
+    __syncthreads();
+}
+
+// ---- the decision ------------------------------------------------------------------------------------
+struct SfOut { int type; int len; };
+
+// size-range eligibility (adaptive_compressor.py:114-127, tested on the clamped size :565-567)
+__device__ __forceinline__ bool sf_eligible(int id, int n)
+{
+    switch (id) {
+    case 1: return n >= 32 && n <= 4096;
+    case 2: return n >= 128 && n <= 8192;
+    case 3: return n >= 32 && n <= 8192;
+    case 4: return n >= 32 && n <= 4096;
+    }
+    return false;
+}
+
+// Evaluate the chunk staged by sf_load; the winner's payload is left in c.pay.  The outcome is the reference's
+// (methods in id order, the first strictly smaller payload wins, benefit test len + ovh < n); the order of
+// evaluation is not: a trial is skipped when its payload provably cannot end up as the winner.
+template <int NMAX> __device__ SfOut sf_select(SfCtx<NMAX> &c, uint32_t mask, int ovh)
+{
+    const int n = c.n;
+    SfOut o;
+    o.type = 255; o.len = n;
+    const bool rle_el = (mask & 2u) && sf_eligible(1, n);
+    const bool lz_el = (mask & 4u) && sf_eligible(2, n) && n >= 100;
+    const bool hf_el = (mask & 8u) && sf_eligible(3, n) && n >= 100;
+    // Delta (id 4) always produces n bytes, so (n + overhead) / n > 1 never wins (adaptive_compressor.py:574-577).
+    if (!rle_el && !lz_el && !hf_el) return o;
+
+    SF_PH_DECL
+    int best_type = 255, best_len = 0x7fffffff;
+    if (rle_el) {
+        int pairs;
+        if (sf_rle_features(c, &pairs)) {
+            const int len = 2 * pairs;
+            if (len + ovh < n) { best_type = 1; best_len = len; }
+        }
+    }
+    SF_PH(1);
+    // smallest payloads the other two methods can produce: RLE at or below both wins outright
+    const int lz_min = lz_el ? sf_lz_lower_bound(n) : 0x7fffffff;
+    const int hf_min = hf_el ? 1 + 5 * 2 + 4 + ((n + 7) >> 3) : 0x7fffffff;
+    if (best_type == 1 && best_len <= lz_min && best_len <= hf_min) {
+        sf_rle_emit(c);
+        o.type = 1; o.len = best_len;
+        return o;
+    }
+    if (lz_el || hf_el) {
+        SfStats st;
+        sf_stats(c, lz_el, st);
+        SF_PH(2);
+        SfHuff hs = sf_huff_scratch(c);
+        // gates (compression_methods.py:315-343, 551-574); the quotient distinct / s < 0.8 as an exact integer compare
+        const bool lz_ok = lz_el && 10 * st.distinct3 < 8 * min(1000, n);
+        bool hf_ok = hf_el && st.K >= 2 && st.K <= 255;
+        if (hf_ok) {
+            if (fabsf(st.H - 7.0f) < 0.02f) { // near the threshold: fp64, in the reference's summation order
+                sf_first_order(c, hs, st.K);
+                hf_ok = sf_entropy_ordered(c, hs, st.K) < 7.0;
+            } else hf_ok = st.H < 7.0f;
+        }
+        int hf_len = 0x7fffffff, hf_bits = 0;
+        if (hf_ok) {
+            // entropy lower bound (st.H is within 3e-4 of the entropy): bits >= max(n, n * H)
+            const int lb = 1 + 5 * st.K + 4 + (int)ceilf(fmaxf((float)n, (float)n * (st.H - 0.002f) - 0.01f) * 0.125f);
+            if (lb < best_len && lb + ovh < n) {
+                hf_bits = sf_huff_build(c, hs, st.K);
+                const int len = 1 + 5 * st.K + 4 + ((hf_bits + 7) >> 3);
+                if (len < best_len && len + ovh < n) hf_len = len;
+            }
+        }
+        SF_PH(3);
+        if (lz_ok) {
+            // the Dictionary payload wins iff it is < the RLE payload, <= the Huffman payload and beneficial
+            int cutoff = min(best_len, n - ovh);
+            if (hf_len != 0x7fffffff) cutoff = min(cutoff, hf_len + 1);
+            if (lz_min < cutoff) {
+                sf_lz_index(c);
+                SF_PH(4);
+                const int len = sf_lz_parse(c);
+                SF_PH(5);
+                if (len < cutoff) {
+                    sf_lz_emit(c);
+                    SF_PH(6);
+                    o.type = 2; o.len = len;
+                    return o;
+                }
+            }
+        }
+        if (hf_len != 0x7fffffff) { // (already known to beat RLE and to be beneficial)
+            __syncthreads();
+            sf_huff_emit(c, hs, st.K, hf_bits);
+            SF_PH(7);
+            o.type = 3; o.len = hf_len;
+            return o;
+        }
+    }
+    if (best_type == 1) {
+        sf_rle_emit(c);
+        o.type = 1; o.len = best_len;
+    }
+    return o;
+}
