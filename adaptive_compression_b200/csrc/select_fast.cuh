@@ -32,7 +32,7 @@
 
 #define SF_T 128                 // threads per CTA
 #define SF_W (SF_T / 32)         // warps
-#define SF_G 8                   // lanes per parse group
+#define SF_G 8                   // lanes per parse group = sub-buckets of a trigram class (see sf_lz_index)
 #define SF_NG (SF_T / SF_G)      // parse groups = speculative chains
 #define SF_PAD 64                // zero bytes behind the chunk
 static_assert(SF_W == 4, "the per-bucket counter word holds four 16-bit fields, one per warp");
@@ -64,7 +64,7 @@ template <int NMAX> struct SfCfg {
     static constexpr int OFF_HIST = OFF_BITS + 6 * NWORDS * 4;
     static constexpr int OFF_HCODE = OFF_HIST + 1024;
     static constexpr int OFF_MISC = OFF_HCODE + 1280;
-    static constexpr int SMEM = OFF_MISC + 512;
+    static constexpr int SMEM = OFF_MISC + 128 + 16 * SF_NG;
 };
 
 template <int NMAX> struct SfCtx {
@@ -79,6 +79,7 @@ template <int NMAX> struct SfCtx {
     uint8_t *hlen;       // [256] Huffman code length by symbol
     int *red;            // 32 ints of reduction scratch
     int *gst;            // group state: 4 x SF_NG ints
+    uint32_t sdb, ordb, bstb; // 32-bit shared-window addresses of sd / ord / bstart (ld.shared with 32-bit address math)
     int n;
     // views of region A
     __device__ __forceinline__ uint8_t *mlen() const { return A; }
@@ -101,7 +102,22 @@ template <int NMAX> __device__ __forceinline__ void sf_carve(SfCtx<NMAX> &c, uin
     c.hlen = base + C::OFF_HCODE + 1024;
     c.red = (int *)(base + C::OFF_MISC);
     c.gst = c.red + 32;
+    c.sdb = (uint32_t)__cvta_generic_to_shared(c.sd);
+    c.ordb = (uint32_t)__cvta_generic_to_shared(c.ord);
+    c.bstb = (uint32_t)__cvta_generic_to_shared(c.bstart);
     c.n = 0;
+}
+
+// loads from the shared window by 32-bit address (read-only data of the parse: the chunk, ord, bstart).  Address
+// arithmetic on generic pointers made ptxas emit 64-bit adds and generic LD.E for the unaligned word loads.
+__device__ __forceinline__ uint32_t sf_lds32(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t sf_lds16(uint32_t a) { uint32_t v; asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t sf_lds8(uint32_t a) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+// unaligned 32-bit load at shared-window address a
+__device__ __forceinline__ uint32_t sf_ldsu(uint32_t a)
+{
+    const uint32_t b = a & ~3u;
+    return __funnelshift_r(sf_lds32(b), sf_lds32(b + 4), (a & 3u) * 8);
 }
 
 // ---- block helpers for SF_T threads ------------------------------------------------------------------
@@ -598,8 +614,32 @@ __host__ __device__ inline int sf_lz_lower_bound(int n)
     return 2 + 4 * ((n - 1) / 32) + (2 * r < 4 ? 2 * r : 4);
 }
 
-// Stable bucket sort of the positions [0, n - 2) by the hash of their 3 bytes: c.ord (ascending inside each
-// bucket), c.bstart, and c.has3 bit p = "an earlier position lies in p's bucket".
+// entry of ord: position | fingerprint of the 4th byte in the spare high bits
+template <int NMAX> struct SfOrd {
+    static constexpr int POSB = NMAX > 4096 ? 13 : 12;
+    static constexpr uint32_t POSMASK = (1u << POSB) - 1u;
+    __device__ static __forceinline__ uint32_t fp(uint32_t b)
+    {
+        return POSB == 12 ? ((b ^ (b >> 4)) & 0xFu) : ((b ^ (b >> 2) ^ (b >> 5)) & 0x7u);
+    }
+};
+static_assert(SF_G == 8, "one lane per sub-bucket of a trigram class");
+// bucket of the position whose four bytes are w4: the top HB - 3 bits of the trigram hash (the class), then 3 bits
+// of the 4th byte.  The matches of >= 4 bytes of a position lie in its own bucket, those of exactly 3 bytes in the
+// 8 buckets of its class.  (With one bucket per trigram hash, zero-padded binary records put 200+ entries in front
+// of every visited position: 300 k warp instructions per chunk, ncu.)
+template <int NMAX> __device__ __forceinline__ uint32_t sf_bucket(uint32_t w4, uint32_t *hprod)
+{
+    using C = SfCfg<NMAX>;
+    const uint32_t hp = (w4 & 0xFFFFFFu) * 2654435761u;
+    const uint32_t b4 = w4 >> 24;
+    *hprod = hp;
+    return ((hp >> (32 - (C::HB - 3))) << 3) | ((b4 ^ (b4 >> 3) ^ (b4 >> 6)) & 7u);
+}
+
+// Stable bucket sort of the positions [0, n - 2) (sf_bucket; ascending inside each bucket): c.ord, c.bstart, and
+// c.has3 bit p = "an earlier position has a trigram with the same HB-bit hash" (a superset of "the trigram at p
+// occurred before": everything else is a literal for sure).
 template <int NMAX> __device__ inline void sf_lz_index(SfCtx<NMAX> &c)
 {
     using C = SfCfg<NMAX>;
@@ -610,17 +650,21 @@ template <int NMAX> __device__ inline void sf_lz_index(SfCtx<NMAX> &c)
     uint64_t *cnt64 = (uint64_t *)c.A;            // per bucket: four u16 fields, one per warp
     uint32_t *cnt32 = (uint32_t *)c.A;
     volatile uint16_t *cnt16 = (volatile uint16_t *)c.A;
+    uint32_t *fo = (uint32_t *)c.ord;             // first position per trigram hash (NB entries; ord is written later)
     SF_PH_DECL
     for (int i = tid; i < C::NB / 2; i += SF_T) ((uint4 *)c.A)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < C::NB / 4; i += SF_T) ((uint4 *)fo)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
     __syncthreads();
     const uint32_t inc = (w & 1) ? 0x10000u : 1u;
     const int fsel = w >> 1;
-    // pass 1: counts (order irrelevant)
+    // pass 1: counts (order irrelevant) and first positions
     for (int r = 0; r < Rw; r++) {
         const int p = 32 * (w * Rw + r) + lane;
         if (p < P) {
-            const uint32_t h = sf_hash3(lds_u32u(c.sd + p) & 0xFFFFFFu, C::HB);
-            atomicAdd(&cnt32[2 * h + fsel], inc);
+            uint32_t hp;
+            const uint32_t b = sf_bucket<NMAX>(lds_u32u(c.sd + p), &hp);
+            atomicAdd(&cnt32[2 * b + fsel], inc);
+            atomicMin(&fo[hp >> (32 - C::HB)], (uint32_t)p);
         }
     }
     __syncthreads();
@@ -654,6 +698,17 @@ template <int NMAX> __device__ inline void sf_lz_index(SfCtx<NMAX> &c)
         }
         if (tid == 0) c.bstart[C::NB] = (uint16_t)P;
     }
+    // literal filter: bit p = the first position of p's trigram hash lies before p
+    for (int blk = w; blk < nblk; blk += SF_W) {
+        const int p = 32 * blk + lane;
+        bool has = false;
+        if (p < P) {
+            const uint32_t hp = (lds_u32u(c.sd + p) & 0xFFFFFFu) * 2654435761u;
+            has = fo[hp >> (32 - C::HB)] < (uint32_t)p;
+        }
+        const uint32_t hw = __ballot_sync(FULL_MASK, has);
+        if (lane == 0) c.has3[blk] = hw;
+    }
     __syncthreads();
     SF_PH(11);
     // pass 2: ordered scatter.  A warp walks its blocks in ascending order; inside a block the lanes that share a
@@ -663,221 +718,307 @@ template <int NMAX> __device__ inline void sf_lz_index(SfCtx<NMAX> &c)
         if (blk >= nblk) break;
         const int p = 32 * blk + lane;
         const bool valid = p < P;
-        uint32_t h = 0, c0 = 0;
+        uint32_t b = 0, c0 = 0, w4 = 0;
         if (valid) {
-            h = sf_hash3(lds_u32u(c.sd + p) & 0xFFFFFFu, C::HB);
-            c0 = cnt16[4 * h + w];
+            uint32_t hp;
+            w4 = lds_u32u(c.sd + p);
+            b = sf_bucket<NMAX>(w4, &hp);
+            c0 = cnt16[4 * b + w];
         }
         __syncwarp();
-        if (valid) atomicAdd(&cnt32[2 * h + fsel], inc);
+        if (valid) atomicAdd(&cnt32[2 * b + fsel], inc);
         __syncwarp();
         uint32_t m = 0;
-        if (valid) m = (uint32_t)cnt16[4 * h + w] - c0;
+        if (valid) m = (uint32_t)cnt16[4 * b + w] - c0;
         const bool multi = valid && m > 1;
         const uint32_t cm = __ballot_sync(FULL_MASK, multi);
         uint32_t cl = 0;
         if (multi) {
-            const uint32_t peers = __match_any_sync(cm, h);
+            const uint32_t peers = __match_any_sync(cm, b);
             cl = __popc(peers & ((1u << lane) - 1u));
         }
-        const uint32_t slot = c0 + cl;
-        bool has = false;
-        if (valid) {
-            c.ord[slot] = (uint16_t)p;
-            has = slot > (uint32_t)c.bstart[h];
-        }
-        const uint32_t hw = __ballot_sync(FULL_MASK, has);
-        if (lane == 0) c.has3[blk] = hw;
+        if (valid) c.ord[c0 + cl] = (uint16_t)((uint32_t)p | (SfOrd<NMAX>::fp(w4 >> 24) << SfOrd<NMAX>::POSB));
     }
     __syncthreads();
     SF_PH(12);
 }
 
-// ---- Dictionary: lazy match evaluation ---------------------------------------------------------------
-// Longest match for position p among the earlier entries of its bucket (earliest among the longest), by the
-// SF_G lanes of a group.  Returns len << 16 | (0xFFFF - pos), or 0 when no match of >= 3 bytes exists.
-template <int NMAX> __device__ __forceinline__ uint32_t sf_evaluate(const SfCtx<NMAX> &c, int p, uint32_t gmask, int sub)
+// Longest match for the positions p of the groups with need == true (earliest among the longest, capped at
+// min(32, n - p): compression_methods.py:283-313), by the SF_G lanes of each group; warp-uniform.
+// Returns len << 16 | (0xFFFF - pos), or 0 when no match of >= 3 bytes exists.
+template <int NMAX> __device__ __forceinline__ uint32_t sf_evaluate(const SfCtx<NMAX> &c, int p, bool need)
 {
     using C = SfCfg<NMAX>;
-    const int n = c.n;
-    const uint8_t *sp = c.sd + p;
-    const uint32_t *pwb = (const uint32_t *)((uintptr_t)sp & ~(uintptr_t)3);
-    const uint32_t psh = ((uintptr_t)sp & 3) * 8;
-    const uint32_t wp0 = __funnelshift_r(pwb[0], pwb[1], psh);
+    const int n = c.n, lane = threadIdx.x & 31;
+    const int sub = lane & (SF_G - 1);
+    const int gsh = lane & ~(SF_G - 1);
+    const uint32_t pa = c.sdb + (need ? p : 0);
+    const uint32_t pab = pa & ~3u, psh = (pa & 3u) * 8;
+    const uint32_t plo1 = sf_lds32(pab + 4);
+    const uint32_t wp0 = __funnelshift_r(sf_lds32(pab), plo1, psh);
+    const uint32_t fpp = SfOrd<NMAX>::fp(wp0 >> 24);
     const int cap = min(32, n - p);
-    const uint32_t h = sf_hash3(wp0 & 0xFFFFFFu, C::HB);
-    const int i0 = c.bstart[h], i1 = c.bstart[h + 1];
+    uint32_t hp;
+    const uint32_t own = sf_bucket<NMAX>(wp0, &hp);
+    int i = 0, i1 = 0;
+    if (need) {
+        i = (int)sf_lds16(c.bstb + 2 * own) + sub;
+        i1 = (int)sf_lds16(c.bstb + 2 * own + 2);
+    }
+    // (A) matches of >= 4 bytes: the earlier entries of p's own bucket, SF_G per step, ascending
     uint32_t best = 0;
-    if (sub == 0) SF_COUNT(30, 1);
-    for (int i = i0 + sub;; i += SF_G) {
-        if (sub == 0) SF_COUNT(31, 1);
-        const int q = i < i1 ? (int)c.ord[i] : 0x7FFF;
-        const bool stop = q >= p;                          // ascending: nothing behind it is earlier than p
-        bool cand = !stop;
-        if (NMAX > 4096) cand = cand && (q + 4096 >= p);   // window_size (compression_methods.py:294)
+    uint32_t pbyte = 0; // byte of the look-ahead at offset len(best): a longer candidate has to match it
+    bool more = need;
+    if (sub == 0 && need) SF_COUNT(30, 1);
+    while (__any_sync(FULL_MASK, more)) {
         uint32_t key = 0;
-        if (cand) {
-            const uint8_t *sq = c.sd + q;
-            const uint32_t *qwb = (const uint32_t *)((uintptr_t)sq & ~(uintptr_t)3);
-            const uint32_t qsh = ((uintptr_t)sq & 3) * 8;
-            uint32_t qlo = qwb[1];
-            uint32_t x = __funnelshift_r(qwb[0], qlo, qsh) ^ wp0;
-            if ((x & 0xFFFFFFu) == 0) {
-                int len;
-                if (x) len = 3;
-                else {
-                    len = 32;
-                    uint32_t plo = pwb[1];
+        bool stop = true;
+        if (more) {
+            if (sub == 0) SF_COUNT(31, 1);
+            const uint32_t e = i < i1 ? sf_lds16(c.ordb + 2 * i) : 0xFFFFu;
+            const int q = (int)(e & SfOrd<NMAX>::POSMASK);
+            stop = q >= p;                                   // ascending: nothing behind it is earlier than p
+            bool cand = !stop && (e >> SfOrd<NMAX>::POSB) == fpp;
+            if (NMAX > 4096) cand = cand && (q + 4096 >= p); // window_size (compression_methods.py:294)
+            const int bl = (int)(best >> 16);
+            if (cand && bl >= 4) cand = sf_lds8(c.sdb + q + bl) == pbyte; // only a strictly longer match counts
+            if (cand) {
+                const uint32_t qa = c.sdb + q;
+                const uint32_t qab = qa & ~3u, qsh = (qa & 3u) * 8;
+                uint32_t qlo = sf_lds32(qab + 4);
+                uint32_t x = __funnelshift_r(sf_lds32(qab), qlo, qsh) ^ wp0;
+                if (x == 0) {
+                    int len = 32;
+                    uint32_t plo = plo1;
 #pragma unroll 1
                     for (int k = 1; k < 8; k++) {
-                        const uint32_t qhi = qwb[k + 1], phi = pwb[k + 1];
+                        if (4 * k >= cap) break; // (the rest lies beyond the look-ahead)
+                        const uint32_t qhi = sf_lds32(qab + 4 * k + 4), phi = sf_lds32(pab + 4 * k + 4);
                         x = __funnelshift_r(qlo, qhi, qsh) ^ __funnelshift_r(plo, phi, psh);
                         SF_COUNT(32, 1);
                         if (x) { len = 4 * k + ((__ffs(x) - 1) >> 3); break; }
-                        if (4 * k + 4 >= cap) break; // (the rest lies beyond the look-ahead)
                         qlo = qhi; plo = phi;
                     }
+                    len = min(len, cap);
+                    key = ((uint32_t)len << 16) | (uint32_t)(0xFFFF - q);
                 }
-                len = min(len, cap);
-                key = ((uint32_t)len << 16) | (uint32_t)(0xFFFF - q);
             }
         }
-        key = max(key, __shfl_xor_sync(gmask, key, 1));
-        key = max(key, __shfl_xor_sync(gmask, key, 2));
-        key = max(key, __shfl_xor_sync(gmask, key, 4));
-        best = max(best, key);
-        const uint32_t anystop = __ballot_sync(gmask, stop) & gmask;
-        if (anystop || (int)(best >> 16) >= cap) break;
+#pragma unroll
+        for (int d = 1; d < SF_G; d <<= 1) key = max(key, __shfl_xor_sync(FULL_MASK, key, d));
+        const bool gstop = ((__ballot_sync(FULL_MASK, stop) >> gsh) & ((1u << SF_G) - 1u)) != 0;
+        if (more) {
+            if (key > best) {
+                best = key;
+                pbyte = sf_lds8(pa + (best >> 16));
+            }
+            if (gstop || (int)(best >> 16) >= cap) more = false;
+            i += SF_G;
+        }
     }
+    // (B) no match of >= 4 bytes (possible only when fewer than 4 bytes remain... or none exists): the earliest
+    // earlier position with the same 3 bytes, one lane per bucket of the class
+    const bool needB = need && (best >> 16) < 4;
+    if (__any_sync(FULL_MASK, needB)) {
+        uint32_t q3 = 0xFFFFu;
+        if (needB) {
+            const uint32_t b = (own & ~7u) | (uint32_t)sub;
+            int j = (int)sf_lds16(c.bstb + 2 * b);
+            const int j1 = (int)sf_lds16(c.bstb + 2 * b + 2);
+            for (; j < j1; j++) {
+                const uint32_t q = sf_lds16(c.ordb + 2 * j) & SfOrd<NMAX>::POSMASK;
+                if ((int)q >= p) break;
+                if (NMAX > 4096 && (int)q + 4096 < p) continue;
+                if (((sf_ldsu(c.sdb + q) ^ wp0) & 0xFFFFFFu) == 0) { q3 = q; break; }
+            }
+        }
+#pragma unroll
+        for (int d = 1; d < SF_G; d <<= 1) q3 = min(q3, __shfl_xor_sync(FULL_MASK, q3, d));
+        if (needB && q3 != 0xFFFFu) best = (3u << 16) | (0xFFFFu - q3);
+    }
+    (void)C::NB;
     return best;
 }
 
-// One chain: tokens from position p until the chain leaves [.., s1).  FIX = false: speculative chain of a
-// segment (marks c.vis).  FIX = true: the true chain entering the segment at p; marks c.vis2 and stops as
-// soon as it meets the speculative chain (returns -1 - meeting position).  Otherwise returns the exit position.
+// ---- Dictionary: lazy match evaluation ---------------------------------------------------------------
+// All chains of a warp advance in lockstep: every loop below is warp-uniform (full-mask votes and shuffles), a
+// chain = a group of SF_G lanes that share p and take the same branches.  (A first version ran each group in its
+// own while loop with group masks: the groups drifted apart and the warp issued every group's path separately,
+// 11 of 32 lanes active, ncu.)
+//
+// One step of all chains: tokens from position p until the chain leaves [.., s1).  FIX = false: speculative
+// chain of a segment (marks c.vis).  FIX = true: the true chain entering the segment at p; marks c.vis2 and stops
+// as soon as it meets the speculative chain (result -1 - meeting position).  Otherwise result = exit position.
 template <int NMAX, bool FIX>
-__device__ __forceinline__ int sf_chain(SfCtx<NMAX> &c, int p, int s1, uint32_t gmask, int sub)
+__device__ __forceinline__ int sf_chains(SfCtx<NMAX> &c, int p, int s1, bool act)
 {
+    const int lane = threadIdx.x & 31;
+    const int sub = lane & (SF_G - 1);
     uint32_t *mark = FIX ? c.vis2 : c.vis;
     uint8_t *mlen = c.mlen();
     uint16_t *mpos = c.mpos();
-    while (p < s1) {
-        // next position at or after p whose bucket holds an earlier entry; everything before it is a literal
-        int nx;
-        {
-            int wd = p >> 5;
-            uint32_t hw = c.has3[wd] & (0xFFFFFFFFu << (p & 31));
-            for (;;) {
-                if (hw) { nx = 32 * wd + __ffs(hw) - 1; break; }
-                wd++;
-                if (32 * wd >= s1) { nx = s1; break; }
-                hw = c.has3[wd];
-            }
-            nx = min(nx, s1);
-        }
-        if (nx > p) {
-            int lim = nx;
-            if (FIX) { // does the speculative chain visit one of the literals [p, nx)?
+    int result = p;
+    act = act && p < s1;
+    while (__any_sync(FULL_MASK, act)) {
+        if ((threadIdx.x & 31) == 0) SF_COUNT(FIX ? 34 : 33, 1);
+        if (sub == 0 && act) SF_COUNT(FIX ? 36 : 35, 1);
+        // (1) literals: everything before the next position whose trigram hash occurred earlier
+        if (act) {
+            int nx;
+            {
                 int wd = p >> 5;
-                uint32_t vw = c.vis[wd] & (0xFFFFFFFFu << (p & 31));
+                uint32_t hw = c.has3[wd] & (0xFFFFFFFFu << (p & 31));
                 for (;;) {
-                    if (vw) { lim = min(nx, 32 * wd + __ffs(vw) - 1); break; }
+                    if (hw) { nx = 32 * wd + __ffs(hw) - 1; break; }
                     wd++;
-                    if (32 * wd >= nx) break;
-                    vw = c.vis[wd];
+                    if (32 * wd >= s1) { nx = s1; break; }
+                    hw = c.has3[wd];
+                }
+                nx = min(nx, s1);
+            }
+            if (nx > p) {
+                int lim = nx;
+                if (FIX) { // does the speculative chain visit one of the literals [p, nx)?
+                    int wd = p >> 5;
+                    uint32_t vw = c.vis[wd] & (0xFFFFFFFFu << (p & 31));
+                    for (;;) {
+                        if (vw) { lim = min(nx, 32 * wd + __ffs(vw) - 1); break; }
+                        wd++;
+                        if (32 * wd >= nx) break;
+                        vw = c.vis[wd];
+                    }
+                }
+                for (int wd = (p >> 5) + sub; 32 * wd < lim; wd += SF_G) { // set bits [p, lim): one word per lane
+                    const int lo = max(p, 32 * wd) & 31, hi = min(lim, 32 * wd + 32) - 32 * wd;
+                    mark[wd] |= (hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & (0xFFFFFFFFu << lo);
+                }
+                if (FIX && lim < nx) { result = -1 - lim; act = false; }
+                else {
+                    p = nx;
+                    if (p >= s1) { result = p; act = false; }
                 }
             }
-            if (sub == 0) { // set bits [p, lim)
-                for (int wd = p >> 5; 32 * wd < lim; wd++) {
-                    const int lo = max(p, 32 * wd) & 31, hi = min(lim, 32 * wd + 32) - 32 * wd; // bits [lo, hi)
-                    const uint32_t bits = (hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & (0xFFFFFFFFu << lo);
-                    mark[wd] |= bits;
-                }
-            }
-            __syncwarp(gmask);
-            if (FIX && lim < nx) return -1 - lim;
-            p = nx;
-            if (p >= s1) break;
         }
+        __syncwarp();
+        // (2) the token at p
         const uint32_t bit = 1u << (p & 31);
         const int wd = p >> 5;
-        if (FIX && (c.vis[wd] & bit)) return -1 - p;
-        int L;
-        if (c.eval[wd] & bit) L = mlen[p];
-        else {
-            const uint32_t key = sf_evaluate<NMAX>(c, p, gmask, sub);
-            L = (int)(key >> 16);
-            if (sub == 0) {
-                mlen[p] = (uint8_t)L;
-                mpos[p] = (uint16_t)(0xFFFF - (key & 0xFFFFu));
-                c.eval[wd] |= bit;
-                if (L >= 3) c.ism[wd] |= bit;
+        int L = 0;
+        bool need = false;
+        if (act) {
+            if (FIX && (c.vis[wd] & bit)) { result = -1 - p; act = false; }
+            else if (c.eval[wd] & bit) L = mlen[p];
+            else need = true;
+        }
+        if (__any_sync(FULL_MASK, need)) {
+            const uint32_t best = sf_evaluate<NMAX>(c, p, need);
+            if (need) {
+                L = (int)(best >> 16);
+                if (sub == 0) {
+                    mlen[p] = (uint8_t)L;
+                    mpos[p] = (uint16_t)(0xFFFF - (best & 0xFFFFu));
+                    c.eval[wd] |= bit;
+                    if (L >= 3) c.ism[wd] |= bit;
+                }
             }
         }
-        if (sub == 0) mark[wd] |= bit;
-        __syncwarp(gmask);
-        p += L >= 3 ? L : 1;
+        if (act) {
+            if (sub == 0) mark[wd] |= bit;
+            p += L >= 3 ? L : 1;
+            if (p >= s1) { result = p; act = false; }
+        }
+        __syncwarp();
     }
-    return p;
+    return result;
 }
 
-// Exact Dictionary payload length of the chunk; afterwards c.vis2 holds the token-start bitmap of the true
-// chain, c.ism marks the match tokens, mlen / mpos hold their lengths and sources.  Requires sf_lz_index.
-template <int NMAX> __device__ inline int sf_lz_parse(SfCtx<NMAX> &c)
+// The true chain through [r0, r1) (multiples of 32, r1 may be n), entered at `entry` (r0 <= entry): the token
+// starts go to c.vis2, *bytes = payload bytes of the tokens that start inside the range.  Returns the position
+// at which the chain leaves the range.  Block-collective.
+template <int NMAX> __device__ inline int sf_lz_parse_range(SfCtx<NMAX> &c, int r0, int r1, int entry, int *bytes_out)
 {
-    using C = SfCfg<NMAX>;
-    const int n = c.n, tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int sub = lane & (SF_G - 1), grp = tid / SF_G;
-    const uint32_t gmask = ((1u << SF_G) - 1u) << (lane & ~(SF_G - 1));
-    const int seg = max(32, (((n + SF_NG - 1) / SF_NG) + 31) & ~31);
-    const int s0 = grp * seg, s1 = min(n, s0 + seg);
+    if (entry >= r1) { *bytes_out = 0; return entry; }
+    const int seg = max(32, ((((r1 - r0) + SF_NG - 1) / SF_NG) + 31) & ~31);
+    const int s0 = r0 + grp * seg, s1 = min(r1, s0 + seg);
+    const int start = grp == 0 ? entry : s0;
+    const int last = (r1 - r0 - 1) / seg; // last group with a segment
     int *gspec = c.gst, *gcur = c.gst + SF_NG, *gdone = c.gst + 2 * SF_NG, *gmerge = c.gst + 3 * SF_NG;
     SF_PH_DECL
     // speculative chains
-    int ex = s0;
-    if (s0 < n) ex = sf_chain<NMAX, false>(c, s0, s1, gmask, sub);
-    if (sub == 0) { gspec[grp] = ex; gcur[grp] = ex; gdone[grp] = s0; gmerge[grp] = s0; }
+    const int ex = sf_chains<NMAX, false>(c, start, s1, s0 < r1);
+    if (sub == 0) { gspec[grp] = ex; gcur[grp] = ex; gdone[grp] = start; gmerge[grp] = s0; }
     SF_PH(13);
     __syncthreads();
     SF_PH(14);
     // stitch: the true chain enters segment g where the true chain of segment g - 1 left it
     for (int round = 0; round < SF_NG; round++) {
-        const int e = grp == 0 ? 0 : gcur[grp - 1];
-        const bool redo = s0 < n && grp > 0 && e != gdone[grp];
+        const int e = grp == 0 ? entry : gcur[grp - 1];
+        const bool redo = s0 < r1 && grp > 0 && e != gdone[grp];
         __syncthreads(); // every gcur has been read
-        if (redo) {
-            for (int wd = (s0 >> 5) + sub; 32 * wd < s1; wd += SF_G) c.vis2[wd] = 0;
-            __syncwarp(gmask);
-            int cur, mg;
-            if (e >= s1) { cur = e; mg = s1; }
-            else {
-                const int x = sf_chain<NMAX, true>(c, e, s1, gmask, sub);
-                if (x < 0) { mg = -1 - x; cur = gspec[grp]; }
+        if (threadIdx.x == 0) SF_COUNT(37, 1);
+        if (sub == 0 && redo) SF_COUNT(38, 1);
+        if (__any_sync(FULL_MASK, redo)) {
+            if (redo)
+                for (int wd = (s0 >> 5) + sub; 32 * wd < s1; wd += SF_G) c.vis2[wd] = 0;
+            __syncwarp();
+            const int x = sf_chains<NMAX, true>(c, e, s1, redo && e < s1);
+            if (redo && sub == 0) {
+                int cur, mg;
+                if (e >= s1) { cur = e; mg = s1; }
+                else if (x < 0) { mg = -1 - x; cur = gspec[grp]; }
                 else { mg = s1; cur = x; }
+                gcur[grp] = cur; gmerge[grp] = mg; gdone[grp] = e;
             }
-            if (sub == 0) { gcur[grp] = cur; gmerge[grp] = mg; gdone[grp] = e; }
         }
         if (!__syncthreads_or(redo)) break;
     }
     SF_PH(15);
     // token starts of the true chain: vis2 | (vis at or behind the meeting point)
     int bytes = 0;
-    for (int wd = tid; wd < C::NWORDS; wd += SF_T) {
-        uint32_t reach = 0;
-        if (32 * wd < n) {
-            const int g = (32 * wd) / seg;
-            const int mg = gmerge[g];
-            uint32_t keep;
-            if (mg <= 32 * wd) keep = 0xFFFFFFFFu;
-            else if (mg >= 32 * wd + 32) keep = 0;
-            else keep = 0xFFFFFFFFu << (mg - 32 * wd);
-            reach = c.vis2[wd] | (c.vis[wd] & keep);
-            bytes += 2 * __popc(reach) + 2 * __popc(reach & c.ism[wd]);
-        }
+    for (int wd = (r0 >> 5) + tid; 32 * wd < r1; wd += SF_T) {
+        const int g = (32 * wd - r0) / seg;
+        const int mg = gmerge[g];
+        uint32_t keep;
+        if (mg <= 32 * wd) keep = 0xFFFFFFFFu;
+        else if (mg >= 32 * wd + 32) keep = 0;
+        else keep = 0xFFFFFFFFu << (mg - 32 * wd);
+        const uint32_t reach = c.vis2[wd] | (c.vis[wd] & keep);
+        bytes += 2 * __popc(reach) + 2 * __popc(reach & c.ism[wd]);
         c.vis2[wd] = reach;
     }
-    return sf_block_sum(bytes, c.red);
+    const int exitp = gcur[last];
+    *bytes_out = sf_block_sum(bytes, c.red); // (its barriers also keep gcur alive until everybody has read it)
+    return exitp;
 }
+
+// Exact Dictionary payload length of the chunk, or SF_ABORTED as soon as the exact cost of a prefix plus the
+// smallest possible cost of the rest (4 bytes per 32) reaches `cutoff` (staged == true: the chunk is parsed in
+// three stages; a speed gamble for chunks whose Dictionary payload is expected to lose, never a change of the
+// outcome).  Afterwards c.vis2 holds the token-start bitmap of the true chain, c.ism marks the match tokens,
+// mlen / mpos hold their lengths and sources.  Requires sf_lz_index.
+#define SF_ABORTED 0x7fffffff
+template <int NMAX> __device__ inline int sf_lz_parse(SfCtx<NMAX> &c, int cutoff, bool staged)
+{
+    const int n = c.n;
+    int bound[4] = {0, n, n, n};
+    int nst = 1;
+    if (staged && n >= 1024) { nst = 3; bound[1] = (3 * n / 8) & ~31; bound[2] = (5 * n / 8) & ~31; }
+    int entry = 0, total = 0;
+    for (int st = 0; st < nst; st++) {
+        int bytes;
+        entry = sf_lz_parse_range<NMAX>(c, bound[st], bound[st + 1], entry, &bytes);
+        total += bytes;
+        if (st + 1 < nst) {
+            const int rest = n - entry;
+            const int lb = total + (rest > 0 ? 4 * (rest >> 5) + min(4, 2 * (rest & 31)) : 0);
+            if (lb >= cutoff) return SF_ABORTED;
+        }
+    }
+    return total;
+}
+
 
 // Dictionary payload -> c.pay (after sf_lz_parse; ord is dead by now)
 template <int NMAX> __device__ inline void sf_lz_emit(SfCtx<NMAX> &c)
@@ -999,7 +1140,9 @@ template <int NMAX> __device__ SfOut sf_select(SfCtx<NMAX> &c, uint32_t mask, in
             if (lz_min < cutoff) {
                 sf_lz_index(c);
                 SF_PH(4);
-                const int len = sf_lz_parse(c);
+                // many distinct trigrams and a Huffman payload in hand: the Dictionary payload usually loses clearly
+                const bool staged = hf_len != 0x7fffffff && 100 * st.distinct3 >= 34 * min(1000, n);
+                const int len = sf_lz_parse(c, cutoff, staged);
                 SF_PH(5);
                 if (len < cutoff) {
                     sf_lz_emit(c);

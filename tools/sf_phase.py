@@ -20,4 +20,4 @@ for k in kinds:
     v = list(buf)
     nch = n // 4096
     print(names[k], "sel %.2f ms |" % ms[0], " ".join("%s=%.0f" % (ph[i], v[i] / nch) for i in sorted(ph)),
-          "| per chunk: evals=%.0f batches=%.0f wordsteps=%.0f" % (v[30] / nch, v[31] / nch, v[32] / nch), flush=True)
+          "| per chunk: evals=%.0f batches=%.0f wordsteps=%.0f warp-iters spec=%.0f fix=%.0f chain-iters spec=%.0f fix=%.0f rounds=%.1f redos=%.1f" % tuple(v[i] / nch for i in (30, 31, 32, 33, 34, 35, 36, 37, 38)), flush=True)
