@@ -43,7 +43,11 @@ static_assert(SF_W == 4, "the per-bucket counter word holds four 16-bit fields, 
 __device__ unsigned long long g_sf[48];
 #define SF_PH_DECL long long sf_t = clock64();
 #define SF_PH(id) do { if (threadIdx.x == 0) { long long now_ = clock64(); atomicAdd(&g_sf[id], (unsigned long long)(now_ - sf_t)); sf_t = now_; } } while (0)
+#ifdef AMBC_PHASE_COUNT
 #define SF_COUNT(id, v) atomicAdd(&g_sf[id], (unsigned long long)(v))
+#else
+#define SF_COUNT(id, v)
+#endif
 #else
 #define SF_PH_DECL
 #define SF_PH(id)
@@ -55,7 +59,7 @@ template <int NMAX> struct SfCfg {
     static constexpr int NB = 1 << HB;                        // buckets
     static constexpr int NWORDS = NMAX / 32;                  // bitmap words
     static constexpr int A_BYTES = NB * 8;                    // region A: counters | trigram set | Huffman scratch | mlen + mpos
-    static_assert(A_BYTES >= NMAX * 3 + 64, "mlen + mpos overlay region A");
+    static_assert(A_BYTES >= NMAX * 3 + NB * 2, "mlen + mpos + fo16 overlay region A");
     static constexpr int OFF_SD = 0;
     static constexpr int OFF_A = OFF_SD + NMAX + SF_PAD;
     static constexpr int OFF_ORD = OFF_A + A_BYTES;           // ord (u16 per position) | payload buffer
@@ -64,7 +68,7 @@ template <int NMAX> struct SfCfg {
     static constexpr int OFF_HIST = OFF_BITS + 6 * NWORDS * 4;
     static constexpr int OFF_HCODE = OFF_HIST + 1024;
     static constexpr int OFF_MISC = OFF_HCODE + 1280;
-    static constexpr int SMEM = OFF_MISC + 128 + 16 * SF_NG;
+    static constexpr int SMEM = OFF_MISC + 128 + 16 * SF_NG + SF_W * 192;
 };
 
 template <int NMAX> struct SfCtx {
@@ -79,11 +83,14 @@ template <int NMAX> struct SfCtx {
     uint8_t *hlen;       // [256] Huffman code length by symbol
     int *red;            // 32 ints of reduction scratch
     int *gst;            // group state: 4 x SF_NG ints
+    uint32_t *wsc;       // per-warp scratch of the pooled match evaluation: SF_W x 48 words
+    uint32_t wscb;
     uint32_t sdb, ordb, bstb; // 32-bit shared-window addresses of sd / ord / bstart (ld.shared with 32-bit address math)
     int n;
     // views of region A
     __device__ __forceinline__ uint8_t *mlen() const { return A; }
     __device__ __forceinline__ uint16_t *mpos() const { return (uint16_t *)(A + NMAX); }
+    __device__ __forceinline__ uint16_t *fo16() const { return (uint16_t *)(A + 3 * NMAX); } // NB entries
 };
 
 template <int NMAX> __device__ __forceinline__ void sf_carve(SfCtx<NMAX> &c, uint8_t *base)
@@ -102,6 +109,8 @@ template <int NMAX> __device__ __forceinline__ void sf_carve(SfCtx<NMAX> &c, uin
     c.hlen = base + C::OFF_HCODE + 1024;
     c.red = (int *)(base + C::OFF_MISC);
     c.gst = c.red + 32;
+    c.wsc = (uint32_t *)(c.gst + 4 * SF_NG);
+    c.wscb = (uint32_t)__cvta_generic_to_shared(c.wsc);
     c.sdb = (uint32_t)__cvta_generic_to_shared(c.sd);
     c.ordb = (uint32_t)__cvta_generic_to_shared(c.ord);
     c.bstb = (uint32_t)__cvta_generic_to_shared(c.bstart);
@@ -650,21 +659,18 @@ template <int NMAX> __device__ inline void sf_lz_index(SfCtx<NMAX> &c)
     uint64_t *cnt64 = (uint64_t *)c.A;            // per bucket: four u16 fields, one per warp
     uint32_t *cnt32 = (uint32_t *)c.A;
     volatile uint16_t *cnt16 = (volatile uint16_t *)c.A;
-    uint32_t *fo = (uint32_t *)c.ord;             // first position per trigram hash (NB entries; ord is written later)
     SF_PH_DECL
     for (int i = tid; i < C::NB / 2; i += SF_T) ((uint4 *)c.A)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < C::NB / 4; i += SF_T) ((uint4 *)fo)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
     __syncthreads();
     const uint32_t inc = (w & 1) ? 0x10000u : 1u;
     const int fsel = w >> 1;
-    // pass 1: counts (order irrelevant) and first positions
+    // pass 1: counts (order irrelevant)
     for (int r = 0; r < Rw; r++) {
         const int p = 32 * (w * Rw + r) + lane;
         if (p < P) {
             uint32_t hp;
-            const uint32_t b = sf_bucket<NMAX>(lds_u32u(c.sd + p), &hp);
+            const uint32_t b = sf_bucket<NMAX>(sf_ldsu(c.sdb + p), &hp);
             atomicAdd(&cnt32[2 * b + fsel], inc);
-            atomicMin(&fo[hp >> (32 - C::HB)], (uint32_t)p);
         }
     }
     __syncthreads();
@@ -698,17 +704,6 @@ template <int NMAX> __device__ inline void sf_lz_index(SfCtx<NMAX> &c)
         }
         if (tid == 0) c.bstart[C::NB] = (uint16_t)P;
     }
-    // literal filter: bit p = the first position of p's trigram hash lies before p
-    for (int blk = w; blk < nblk; blk += SF_W) {
-        const int p = 32 * blk + lane;
-        bool has = false;
-        if (p < P) {
-            const uint32_t hp = (lds_u32u(c.sd + p) & 0xFFFFFFu) * 2654435761u;
-            has = fo[hp >> (32 - C::HB)] < (uint32_t)p;
-        }
-        const uint32_t hw = __ballot_sync(FULL_MASK, has);
-        if (lane == 0) c.has3[blk] = hw;
-    }
     __syncthreads();
     SF_PH(11);
     // pass 2: ordered scatter.  A warp walks its blocks in ascending order; inside a block the lanes that share a
@@ -721,7 +716,7 @@ template <int NMAX> __device__ inline void sf_lz_index(SfCtx<NMAX> &c)
         uint32_t b = 0, c0 = 0, w4 = 0;
         if (valid) {
             uint32_t hp;
-            w4 = lds_u32u(c.sd + p);
+            w4 = sf_ldsu(c.sdb + p);
             b = sf_bucket<NMAX>(w4, &hp);
             c0 = cnt16[4 * b + w];
         }
@@ -741,102 +736,158 @@ template <int NMAX> __device__ inline void sf_lz_index(SfCtx<NMAX> &c)
     }
     __syncthreads();
     SF_PH(12);
+    // first position per trigram hash (the counters are dead now): fo32 in A, then a u16 copy behind mlen / mpos
+    // for the parse (c.fo16) and the literal filter has3
+    uint32_t *fo = (uint32_t *)c.A;
+    for (int i = tid; i < C::NB / 4; i += SF_T) ((uint4 *)fo)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    __syncthreads();
+    for (int blk = w; blk < nblk; blk += SF_W) {
+        const int p = 32 * blk + lane;
+        if (p < P) atomicMin(&fo[((sf_ldsu(c.sdb + p) & 0xFFFFFFu) * 2654435761u) >> (32 - C::HB)], (uint32_t)p);
+    }
+    __syncthreads();
+    for (int blk = w; blk < nblk; blk += SF_W) {
+        const int p = 32 * blk + lane;
+        bool has = false;
+        if (p < P) has = fo[((sf_ldsu(c.sdb + p) & 0xFFFFFFu) * 2654435761u) >> (32 - C::HB)] < (uint32_t)p;
+        const uint32_t hw = __ballot_sync(FULL_MASK, has);
+        if (lane == 0) c.has3[blk] = hw;
+    }
+    uint16_t *fo16 = c.fo16();
+    for (int i = tid; i < C::NB; i += SF_T) fo16[i] = (uint16_t)min(fo[i], 0xFFFFu);
+    __syncthreads();
+    SF_PH(16);
 }
 
 // Longest match for the positions p of the groups with need == true (earliest among the longest, capped at
-// min(32, n - p): compression_methods.py:283-313), by the SF_G lanes of each group; warp-uniform.
-// Returns len << 16 | (0xFFFF - pos), or 0 when no match of >= 3 bytes exists.
+// min(32, n - p): compression_methods.py:283-313); warp-uniform.  The candidates of the (up to four) positions a
+// warp evaluates at once are pooled: item j of the warp = entry k of the bucket of owner o, 32 items per step with
+// every lane busy, the owner's maximum is kept by a shared atomicMax on len << 16 | (0xFFFF - pos) -- which is the
+// reference's "first strictly longer match".  (One group per bucket, 8 entries per step, cost the longest of the
+// four buckets for all of them: 365 warp instructions per call, ncu.)
+// Returns the key, or 0 when no match of >= 3 bytes exists.
 template <int NMAX> __device__ __forceinline__ uint32_t sf_evaluate(const SfCtx<NMAX> &c, int p, bool need)
 {
-    using C = SfCfg<NMAX>;
     const int n = c.n, lane = threadIdx.x & 31;
-    const int sub = lane & (SF_G - 1);
-    const int gsh = lane & ~(SF_G - 1);
+    const int sub = lane & (SF_G - 1), g = lane >> 3;
+    uint32_t *ws = c.wsc + (threadIdx.x >> 5) * 48;    // rec[4][8] | best[4] | first3[4]
+    const uint32_t wsb = c.wscb + (threadIdx.x >> 5) * 192;
     const uint32_t pa = c.sdb + (need ? p : 0);
-    const uint32_t pab = pa & ~3u, psh = (pa & 3u) * 8;
-    const uint32_t plo1 = sf_lds32(pab + 4);
-    const uint32_t wp0 = __funnelshift_r(sf_lds32(pab), plo1, psh);
-    const uint32_t fpp = SfOrd<NMAX>::fp(wp0 >> 24);
+    const uint32_t wp0 = sf_ldsu(pa);
     const int cap = min(32, n - p);
     uint32_t hp;
     const uint32_t own = sf_bucket<NMAX>(wp0, &hp);
-    int i = 0, i1 = 0;
-    if (need) {
-        i = (int)sf_lds16(c.bstb + 2 * own) + sub;
-        i1 = (int)sf_lds16(c.bstb + 2 * own + 2);
+    // (A) matches of >= 4 bytes: the entries of p's own bucket
+    int i0 = 0, cA = 0;
+    if (need) { // the entries before p (ascending: lower bound of p in its bucket)
+        i0 = (int)sf_lds16(c.bstb + 2 * own);
+        int lo = i0, hi = (int)sf_lds16(c.bstb + 2 * own + 2);
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((int)(sf_lds16(c.ordb + 2 * mid) & SfOrd<NMAX>::POSMASK) < p) lo = mid + 1; else hi = mid;
+        }
+        cA = lo - i0;
     }
-    // (A) matches of >= 4 bytes: the earlier entries of p's own bucket, SF_G per step, ascending
-    uint32_t best = 0;
-    uint32_t pbyte = 0; // byte of the look-ahead at offset len(best): a longer candidate has to match it
-    bool more = need;
-    if (sub == 0 && need) SF_COUNT(30, 1);
-    while (__any_sync(FULL_MASK, more)) {
-        uint32_t key = 0;
-        bool stop = true;
-        if (more) {
-            if (sub == 0) SF_COUNT(31, 1);
-            const uint32_t e = i < i1 ? sf_lds16(c.ordb + 2 * i) : 0xFFFFu;
-            const int q = (int)(e & SfOrd<NMAX>::POSMASK);
-            stop = q >= p;                                   // ascending: nothing behind it is earlier than p
-            bool cand = !stop && (e >> SfOrd<NMAX>::POSB) == fpp;
-            if (NMAX > 4096) cand = cand && (q + 4096 >= p); // window_size (compression_methods.py:294)
-            const int bl = (int)(best >> 16);
-            if (cand && bl >= 4) cand = sf_lds8(c.sdb + q + bl) == pbyte; // only a strictly longer match counts
-            if (cand) {
-                const uint32_t qa = c.sdb + q;
-                const uint32_t qab = qa & ~3u, qsh = (qa & 3u) * 8;
-                uint32_t qlo = sf_lds32(qab + 4);
-                uint32_t x = __funnelshift_r(sf_lds32(qab), qlo, qsh) ^ wp0;
-                if (x == 0) {
-                    int len = 32;
-                    uint32_t plo = plo1;
+    if (sub == 0) {
+        ws[8 * g + 0] = (uint32_t)p;
+        ws[8 * g + 1] = (uint32_t)i0;
+        ws[8 * g + 2] = wp0;
+        ws[8 * g + 3] = (uint32_t)cap | (SfOrd<NMAX>::fp(wp0 >> 24) << 8);
+        ws[32 + g] = 0;
+        ws[36 + g] = 0xFFFFu;
+        if (need) SF_COUNT(30, 1);
+    }
+    {
+        const int P1 = __shfl_sync(FULL_MASK, cA, 0);
+        const int P2 = P1 + __shfl_sync(FULL_MASK, cA, 8);
+        const int P3 = P2 + __shfl_sync(FULL_MASK, cA, 16);
+        const int M = P3 + __shfl_sync(FULL_MASK, cA, 24);
+        for (int base = 0; base < M; base += 32) {
+            const int j = base + lane;
+            const int o = (j >= P1) + (j >= P2) + (j >= P3);
+            const int k = j - (o == 0 ? 0 : o == 1 ? P1 : o == 2 ? P2 : P3);
+            __syncwarp();
+            const uint32_t cur = sf_lds32(wsb + 4 * (32 + o)); // best of the steps before this one
+            __syncwarp();
+            if (lane == 0) SF_COUNT(31, 1);
+            if (j < M) {
+                const int po = (int)ws[8 * o + 0];
+                const uint32_t capfp = ws[8 * o + 3];
+                const int capo = (int)(capfp & 0xFFu);
+                const int bl = (int)(cur >> 16);
+                if (bl < capo) {
+                    const uint32_t e = sf_lds16(c.ordb + 2 * ((int)ws[8 * o + 1] + k));
+                    const int q = (int)(e & SfOrd<NMAX>::POSMASK);
+                    bool cand = (e >> SfOrd<NMAX>::POSB) == (capfp >> 8);
+                    if (NMAX > 4096) cand = cand && (q + 4096 >= po); // window_size (compression_methods.py:294)
+                    // with a match in hand only a strictly longer one counts (later entries are later positions)
+                    if (cand && bl >= 4) cand = sf_lds8(c.sdb + q + bl) == sf_lds8(c.sdb + po + bl);
+                    if (cand) {
+                        const uint32_t qa = c.sdb + q, pao = c.sdb + po;
+                        const uint32_t qab = qa & ~3u, qsh = (qa & 3u) * 8, pab = pao & ~3u, psh = (pao & 3u) * 8;
+                        uint32_t qlo = sf_lds32(qab + 4);
+                        uint32_t x = __funnelshift_r(sf_lds32(qab), qlo, qsh) ^ ws[8 * o + 2];
+                        if (x == 0) {
+                            int len = 32;
+                            uint32_t plo = sf_lds32(pab + 4);
 #pragma unroll 1
-                    for (int k = 1; k < 8; k++) {
-                        if (4 * k >= cap) break; // (the rest lies beyond the look-ahead)
-                        const uint32_t qhi = sf_lds32(qab + 4 * k + 4), phi = sf_lds32(pab + 4 * k + 4);
-                        x = __funnelshift_r(qlo, qhi, qsh) ^ __funnelshift_r(plo, phi, psh);
-                        SF_COUNT(32, 1);
-                        if (x) { len = 4 * k + ((__ffs(x) - 1) >> 3); break; }
-                        qlo = qhi; plo = phi;
+                            for (int kk = 1; kk < 8; kk++) {
+                                if (4 * kk >= capo) break; // (the rest lies beyond the look-ahead)
+                                const uint32_t qhi = sf_lds32(qab + 4 * kk + 4), phi = sf_lds32(pab + 4 * kk + 4);
+                                x = __funnelshift_r(qlo, qhi, qsh) ^ __funnelshift_r(plo, phi, psh);
+                                SF_COUNT(32, 1);
+                                if (x) { len = 4 * kk + ((__ffs(x) - 1) >> 3); break; }
+                                qlo = qhi; plo = phi;
+                            }
+                            len = min(len, capo);
+                            atomicMax(&ws[32 + o], ((uint32_t)len << 16) | (uint32_t)(0xFFFF - q));
+                        }
                     }
-                    len = min(len, cap);
-                    key = ((uint32_t)len << 16) | (uint32_t)(0xFFFF - q);
                 }
             }
         }
-#pragma unroll
-        for (int d = 1; d < SF_G; d <<= 1) key = max(key, __shfl_xor_sync(FULL_MASK, key, d));
-        const bool gstop = ((__ballot_sync(FULL_MASK, stop) >> gsh) & ((1u << SF_G) - 1u)) != 0;
-        if (more) {
-            if (key > best) {
-                best = key;
-                pbyte = sf_lds8(pa + (best >> 16));
-            }
-            if (gstop || (int)(best >> 16) >= cap) more = false;
-            i += SF_G;
+    }
+    __syncwarp();
+    uint32_t best = ws[32 + g];
+    // (B) no match of >= 4 bytes: the earliest earlier position with the same 3 bytes; it lies in one of the 8
+    // buckets of the class, which are adjacent in ord
+    bool needB = need && (best >> 16) < 4;
+    if (needB) { // fast path: the first position with p's trigram hash carries p's trigram -> it is the answer
+        const uint32_t f = c.fo16()[hp >> (32 - SfCfg<NMAX>::HB)];
+        if ((NMAX <= 4096 || (int)f + 4096 >= p) && ((sf_ldsu(c.sdb + f) ^ wp0) & 0xFFFFFFu) == 0) {
+            best = (3u << 16) | (0xFFFFu - f); // (f < p: has3 was set)
+            needB = false;
         }
     }
-    // (B) no match of >= 4 bytes (possible only when fewer than 4 bytes remain... or none exists): the earliest
-    // earlier position with the same 3 bytes, one lane per bucket of the class
-    const bool needB = need && (best >> 16) < 4;
     if (__any_sync(FULL_MASK, needB)) {
-        uint32_t q3 = 0xFFFFu;
+        int j0 = 0, cB = 0;
         if (needB) {
-            const uint32_t b = (own & ~7u) | (uint32_t)sub;
-            int j = (int)sf_lds16(c.bstb + 2 * b);
-            const int j1 = (int)sf_lds16(c.bstb + 2 * b + 2);
-            for (; j < j1; j++) {
-                const uint32_t q = sf_lds16(c.ordb + 2 * j) & SfOrd<NMAX>::POSMASK;
-                if ((int)q >= p) break;
-                if (NMAX > 4096 && (int)q + 4096 < p) continue;
-                if (((sf_ldsu(c.sdb + q) ^ wp0) & 0xFFFFFFu) == 0) { q3 = q; break; }
+            j0 = (int)sf_lds16(c.bstb + 2 * (own & ~7u));
+            cB = (int)sf_lds16(c.bstb + 2 * (own & ~7u) + 16) - j0;
+        }
+        if (sub == 0) ws[8 * g + 4] = (uint32_t)j0;
+        const int P1 = __shfl_sync(FULL_MASK, cB, 0);
+        const int P2 = P1 + __shfl_sync(FULL_MASK, cB, 8);
+        const int P3 = P2 + __shfl_sync(FULL_MASK, cB, 16);
+        const int M = P3 + __shfl_sync(FULL_MASK, cB, 24);
+        __syncwarp();
+        for (int base = 0; base < M; base += 32) {
+            const int j = base + lane;
+            if (lane == 0) SF_COUNT(39, 1);
+            if (j < M) {
+                const int o = (j >= P1) + (j >= P2) + (j >= P3);
+                const int k = j - (o == 0 ? 0 : o == 1 ? P1 : o == 2 ? P2 : P3);
+                const int po = (int)ws[8 * o + 0];
+                const int q = (int)(sf_lds16(c.ordb + 2 * ((int)ws[8 * o + 4] + k)) & SfOrd<NMAX>::POSMASK);
+                bool cand = q < po;
+                if (NMAX > 4096) cand = cand && (q + 4096 >= po);
+                if (cand && ((sf_ldsu(c.sdb + q) ^ ws[8 * o + 2]) & 0xFFFFFFu) == 0) atomicMin(&ws[36 + o], (uint32_t)q);
             }
         }
-#pragma unroll
-        for (int d = 1; d < SF_G; d <<= 1) q3 = min(q3, __shfl_xor_sync(FULL_MASK, q3, d));
+        __syncwarp();
+        const uint32_t q3 = ws[36 + g];
         if (needB && q3 != 0xFFFFu) best = (3u << 16) | (0xFFFFu - q3);
     }
-    (void)C::NB;
     return best;
 }
 

@@ -6,7 +6,7 @@ lib = engine.require_cuda()
 n = 64 << 20
 names = ['csv', 'log', 'runs', 'lowcard', 'binrec', 'random', 'text']
 ph = {1: 'rle', 2: 'stats', 3: 'huff_build', 4: 'index', 5: 'parse', 6: 'lz_emit', 7: 'huff_emit',
-      10: 'ix.count', 11: 'ix.scan', 12: 'ix.scatter', 13: 'p.spec', 14: 'p.wait', 15: 'p.stitch'}
+      10: 'ix.count', 11: 'ix.scan', 12: 'ix.scatter', 13: 'p.spec', 14: 'p.wait', 15: 'p.stitch', 16: 'ix.fo'}
 buf = (C.c_ulonglong * 48)()
 lib.ambc_enable_timing(1)
 kinds = [int(x) for x in sys.argv[1].split(',')] if len(sys.argv) > 1 else (0, 1, 3, 4, 6)
