@@ -32,8 +32,11 @@
 
 #define SF_T 128                 // threads per CTA
 #define SF_W (SF_T / 32)         // warps
-#define SF_G 8                   // lanes per parse group = sub-buckets of a trigram class (see sf_lz_index)
+#ifndef SF_G
+#define SF_G 4                   // lanes per parse group (chain); measured: 8 -> 14.1, 4 -> 12.6, 2 -> 12.5 ms over the six corpus kinds
+#endif
 #define SF_NG (SF_T / SF_G)      // parse groups = speculative chains
+#define SF_WSW (11 * (32 / SF_G) + 5) // words of per-warp scratch of the pooled match evaluation
 #define SF_PAD 64                // zero bytes behind the chunk
 static_assert(SF_W == 4, "the per-bucket counter word holds four 16-bit fields, one per warp");
 
@@ -68,7 +71,7 @@ template <int NMAX> struct SfCfg {
     static constexpr int OFF_HIST = OFF_BITS + 6 * NWORDS * 4;
     static constexpr int OFF_HCODE = OFF_HIST + 1024;
     static constexpr int OFF_MISC = OFF_HCODE + 1280;
-    static constexpr int SMEM = OFF_MISC + 128 + 16 * SF_NG + SF_W * 192;
+    static constexpr int SMEM = OFF_MISC + 128 + 16 * SF_NG + ((SF_W * SF_WSW * 4 + 15) & ~15);
 };
 
 template <int NMAX> struct SfCtx {
@@ -83,8 +86,7 @@ template <int NMAX> struct SfCtx {
     uint8_t *hlen;       // [256] Huffman code length by symbol
     int *red;            // 32 ints of reduction scratch
     int *gst;            // group state: 4 x SF_NG ints
-    uint32_t *wsc;       // per-warp scratch of the pooled match evaluation: SF_W x 48 words
-    uint32_t wscb;
+    uint32_t *wsc;       // per-warp scratch of the pooled match evaluation: SF_W x SF_WSW words
     uint32_t sdb, ordb, bstb; // 32-bit shared-window addresses of sd / ord / bstart (ld.shared with 32-bit address math)
     int n;
     // views of region A
@@ -110,7 +112,6 @@ template <int NMAX> __device__ __forceinline__ void sf_carve(SfCtx<NMAX> &c, uin
     c.red = (int *)(base + C::OFF_MISC);
     c.gst = c.red + 32;
     c.wsc = (uint32_t *)(c.gst + 4 * SF_NG);
-    c.wscb = (uint32_t)__cvta_generic_to_shared(c.wsc);
     c.sdb = (uint32_t)__cvta_generic_to_shared(c.sd);
     c.ordb = (uint32_t)__cvta_generic_to_shared(c.ord);
     c.bstb = (uint32_t)__cvta_generic_to_shared(c.bstart);
@@ -632,7 +633,6 @@ template <int NMAX> struct SfOrd {
         return POSB == 12 ? ((b ^ (b >> 4)) & 0xFu) : ((b ^ (b >> 2) ^ (b >> 5)) & 0x7u);
     }
 };
-static_assert(SF_G == 8, "one lane per sub-bucket of a trigram class");
 // bucket of the position whose four bytes are w4: the top HB - 3 bits of the trigram hash (the class), then 3 bits
 // of the 4th byte.  The matches of >= 4 bytes of a position lie in its own bucket, those of exactly 3 bytes in the
 // 8 buckets of its class.  (With one bucket per trigram hash, zero-padded binary records put 200+ entries in front
@@ -768,10 +768,11 @@ template <int NMAX> __device__ inline void sf_lz_index(SfCtx<NMAX> &c)
 // Returns the key, or 0 when no match of >= 3 bytes exists.
 template <int NMAX> __device__ __forceinline__ uint32_t sf_evaluate(const SfCtx<NMAX> &c, int p, bool need)
 {
+    constexpr int NO = 32 / SF_G;                       // owners (chains) per warp
     const int n = c.n, lane = threadIdx.x & 31;
-    const int sub = lane & (SF_G - 1), g = lane >> 3;
-    uint32_t *ws = c.wsc + (threadIdx.x >> 5) * 48;    // rec[4][8] | best[4] | first3[4]
-    const uint32_t wsb = c.wscb + (threadIdx.x >> 5) * 192;
+    const int sub = lane & (SF_G - 1), g = lane / SF_G;
+    uint32_t *ws = c.wsc + (threadIdx.x >> 5) * SF_WSW; // rec[NO][8] | best[NO] | first3[NO] | prefix[NO + 1]
+    uint32_t *wbest = ws + 8 * NO, *wf3 = wbest + NO, *wpre = wf3 + NO;
     const uint32_t pa = c.sdb + (need ? p : 0);
     const uint32_t wp0 = sf_ldsu(pa);
     const int cap = min(32, n - p);
@@ -788,69 +789,73 @@ template <int NMAX> __device__ __forceinline__ uint32_t sf_evaluate(const SfCtx<
         }
         cA = lo - i0;
     }
-    if (sub == 0) {
-        ws[8 * g + 0] = (uint32_t)p;
-        ws[8 * g + 1] = (uint32_t)i0;
-        ws[8 * g + 2] = wp0;
-        ws[8 * g + 3] = (uint32_t)cap | (SfOrd<NMAX>::fp(wp0 >> 24) << 8);
-        ws[32 + g] = 0;
-        ws[36 + g] = 0xFFFFu;
-        if (need) SF_COUNT(30, 1);
+    int M;
+    {   // prefix of the owners' item counts (lane SF_G * o holds owner o's count)
+        int v = sub == 0 ? cA : 0;
+        const int inc = warp_incl_scan(v);
+        M = __shfl_sync(FULL_MASK, inc, 31);
+        if (sub == 0) {
+            ws[8 * g + 0] = (uint32_t)p;
+            ws[8 * g + 1] = (uint32_t)i0;
+            ws[8 * g + 2] = wp0;
+            ws[8 * g + 3] = (uint32_t)cap | (SfOrd<NMAX>::fp(wp0 >> 24) << 8);
+            wbest[g] = 0;
+            wf3[g] = 0xFFFFu;
+            wpre[g] = (uint32_t)(inc - v);
+            if (need) SF_COUNT(30, 1);
+        }
+        if (lane == 0) wpre[NO] = (uint32_t)M;
     }
-    {
-        const int P1 = __shfl_sync(FULL_MASK, cA, 0);
-        const int P2 = P1 + __shfl_sync(FULL_MASK, cA, 8);
-        const int P3 = P2 + __shfl_sync(FULL_MASK, cA, 16);
-        const int M = P3 + __shfl_sync(FULL_MASK, cA, 24);
-        for (int base = 0; base < M; base += 32) {
-            const int j = base + lane;
-            const int o = (j >= P1) + (j >= P2) + (j >= P3);
-            const int k = j - (o == 0 ? 0 : o == 1 ? P1 : o == 2 ? P2 : P3);
-            __syncwarp();
-            const uint32_t cur = sf_lds32(wsb + 4 * (32 + o)); // best of the steps before this one
-            __syncwarp();
-            if (lane == 0) SF_COUNT(31, 1);
-            if (j < M) {
-                const int po = (int)ws[8 * o + 0];
-                const uint32_t capfp = ws[8 * o + 3];
-                const int capo = (int)(capfp & 0xFFu);
-                const int bl = (int)(cur >> 16);
-                if (bl < capo) {
-                    const uint32_t e = sf_lds16(c.ordb + 2 * ((int)ws[8 * o + 1] + k));
-                    const int q = (int)(e & SfOrd<NMAX>::POSMASK);
-                    bool cand = (e >> SfOrd<NMAX>::POSB) == (capfp >> 8);
-                    if (NMAX > 4096) cand = cand && (q + 4096 >= po); // window_size (compression_methods.py:294)
-                    // with a match in hand only a strictly longer one counts (later entries are later positions)
-                    if (cand && bl >= 4) cand = sf_lds8(c.sdb + q + bl) == sf_lds8(c.sdb + po + bl);
-                    if (cand) {
-                        const uint32_t qa = c.sdb + q, pao = c.sdb + po;
-                        const uint32_t qab = qa & ~3u, qsh = (qa & 3u) * 8, pab = pao & ~3u, psh = (pao & 3u) * 8;
-                        uint32_t qlo = sf_lds32(qab + 4);
-                        uint32_t x = __funnelshift_r(sf_lds32(qab), qlo, qsh) ^ ws[8 * o + 2];
-                        if (x == 0) {
-                            int len = 32;
-                            uint32_t plo = sf_lds32(pab + 4);
+    __syncwarp();
+    for (int base = 0; base < M; base += 32) {
+        const int j = base + lane;
+        int o = 0;
+#pragma unroll
+        for (int t = 1; t < NO; t++) o += (j >= (int)wpre[t]);
+        const int k = j - (int)wpre[o];
+        __syncwarp();
+        const uint32_t cur = wbest[o]; // best of the steps before this one
+        __syncwarp();
+        if (lane == 0) SF_COUNT(31, 1);
+        if (j < M) {
+            const int po = (int)ws[8 * o + 0];
+            const uint32_t capfp = ws[8 * o + 3];
+            const int capo = (int)(capfp & 0xFFu);
+            const int bl = (int)(cur >> 16);
+            if (bl < capo) {
+                const uint32_t e = sf_lds16(c.ordb + 2 * ((int)ws[8 * o + 1] + k));
+                const int q = (int)(e & SfOrd<NMAX>::POSMASK);
+                bool cand = (e >> SfOrd<NMAX>::POSB) == (capfp >> 8);
+                if (NMAX > 4096) cand = cand && (q + 4096 >= po); // window_size (compression_methods.py:294)
+                // with a match in hand only a strictly longer one counts (later entries are later positions)
+                if (cand && bl >= 4) cand = sf_lds8(c.sdb + q + bl) == sf_lds8(c.sdb + po + bl);
+                if (cand) {
+                    const uint32_t qa = c.sdb + q, pao = c.sdb + po;
+                    const uint32_t qab = qa & ~3u, qsh = (qa & 3u) * 8, pab = pao & ~3u, psh = (pao & 3u) * 8;
+                    uint32_t qlo = sf_lds32(qab + 4);
+                    uint32_t x = __funnelshift_r(sf_lds32(qab), qlo, qsh) ^ ws[8 * o + 2];
+                    if (x == 0) {
+                        int len = 32;
+                        uint32_t plo = sf_lds32(pab + 4);
 #pragma unroll 1
-                            for (int kk = 1; kk < 8; kk++) {
-                                if (4 * kk >= capo) break; // (the rest lies beyond the look-ahead)
-                                const uint32_t qhi = sf_lds32(qab + 4 * kk + 4), phi = sf_lds32(pab + 4 * kk + 4);
-                                x = __funnelshift_r(qlo, qhi, qsh) ^ __funnelshift_r(plo, phi, psh);
-                                SF_COUNT(32, 1);
-                                if (x) { len = 4 * kk + ((__ffs(x) - 1) >> 3); break; }
-                                qlo = qhi; plo = phi;
-                            }
-                            len = min(len, capo);
-                            atomicMax(&ws[32 + o], ((uint32_t)len << 16) | (uint32_t)(0xFFFF - q));
+                        for (int kk = 1; kk < 8; kk++) {
+                            if (4 * kk >= capo) break; // (the rest lies beyond the look-ahead)
+                            const uint32_t qhi = sf_lds32(qab + 4 * kk + 4), phi = sf_lds32(pab + 4 * kk + 4);
+                            x = __funnelshift_r(qlo, qhi, qsh) ^ __funnelshift_r(plo, phi, psh);
+                            SF_COUNT(32, 1);
+                            if (x) { len = 4 * kk + ((__ffs(x) - 1) >> 3); break; }
+                            qlo = qhi; plo = phi;
                         }
+                        len = min(len, capo);
+                        atomicMax(&wbest[o], ((uint32_t)len << 16) | (uint32_t)(0xFFFF - q));
                     }
                 }
             }
         }
     }
     __syncwarp();
-    uint32_t best = ws[32 + g];
-    // (B) no match of >= 4 bytes: the earliest earlier position with the same 3 bytes; it lies in one of the 8
-    // buckets of the class, which are adjacent in ord
+    uint32_t best = wbest[g];
+    // (B) no match of >= 4 bytes: the earliest earlier position with the same 3 bytes
     bool needB = need && (best >> 16) < 4;
     if (needB) { // fast path: the first position with p's trigram hash carries p's trigram -> it is the answer
         const uint32_t f = c.fo16()[hp >> (32 - SfCfg<NMAX>::HB)];
@@ -860,32 +865,35 @@ template <int NMAX> __device__ __forceinline__ uint32_t sf_evaluate(const SfCtx<
         }
     }
     if (__any_sync(FULL_MASK, needB)) {
+        // it lies in one of the 8 buckets of the class, which are adjacent in ord
         int j0 = 0, cB = 0;
         if (needB) {
             j0 = (int)sf_lds16(c.bstb + 2 * (own & ~7u));
             cB = (int)sf_lds16(c.bstb + 2 * (own & ~7u) + 16) - j0;
         }
-        if (sub == 0) ws[8 * g + 4] = (uint32_t)j0;
-        const int P1 = __shfl_sync(FULL_MASK, cB, 0);
-        const int P2 = P1 + __shfl_sync(FULL_MASK, cB, 8);
-        const int P3 = P2 + __shfl_sync(FULL_MASK, cB, 16);
-        const int M = P3 + __shfl_sync(FULL_MASK, cB, 24);
         __syncwarp();
-        for (int base = 0; base < M; base += 32) {
+        const int v = sub == 0 ? cB : 0;
+        const int inc = warp_incl_scan(v);
+        const int MB = __shfl_sync(FULL_MASK, inc, 31);
+        if (sub == 0) { ws[8 * g + 4] = (uint32_t)j0; wpre[g] = (uint32_t)(inc - v); }
+        __syncwarp();
+        for (int base = 0; base < MB; base += 32) {
             const int j = base + lane;
             if (lane == 0) SF_COUNT(39, 1);
-            if (j < M) {
-                const int o = (j >= P1) + (j >= P2) + (j >= P3);
-                const int k = j - (o == 0 ? 0 : o == 1 ? P1 : o == 2 ? P2 : P3);
+            if (j < MB) {
+                int o = 0;
+#pragma unroll
+                for (int t = 1; t < NO; t++) o += (j >= (int)wpre[t]);
+                const int k = j - (int)wpre[o];
                 const int po = (int)ws[8 * o + 0];
                 const int q = (int)(sf_lds16(c.ordb + 2 * ((int)ws[8 * o + 4] + k)) & SfOrd<NMAX>::POSMASK);
                 bool cand = q < po;
                 if (NMAX > 4096) cand = cand && (q + 4096 >= po);
-                if (cand && ((sf_ldsu(c.sdb + q) ^ ws[8 * o + 2]) & 0xFFFFFFu) == 0) atomicMin(&ws[36 + o], (uint32_t)q);
+                if (cand && ((sf_ldsu(c.sdb + q) ^ ws[8 * o + 2]) & 0xFFFFFFu) == 0) atomicMin(&wf3[o], (uint32_t)q);
             }
         }
         __syncwarp();
-        const uint32_t q3 = ws[36 + g];
+        const uint32_t q3 = wf3[g];
         if (needB && q3 != 0xFFFFu) best = (3u << 16) | (0xFFFFu - q3);
     }
     return best;
@@ -1055,7 +1063,7 @@ template <int NMAX> __device__ inline int sf_lz_parse(SfCtx<NMAX> &c, int cutoff
     const int n = c.n;
     int bound[4] = {0, n, n, n};
     int nst = 1;
-    if (staged && n >= 1024) { nst = 3; bound[1] = (3 * n / 8) & ~31; bound[2] = (5 * n / 8) & ~31; }
+    if (staged && n >= 1024) { nst = 3; bound[1] = (11 * n / 32) & ~31; bound[2] = (9 * n / 16) & ~31; }
     int entry = 0, total = 0;
     for (int st = 0; st < nst; st++) {
         int bytes;
