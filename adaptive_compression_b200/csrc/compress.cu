@@ -194,7 +194,7 @@ k_select(const uint8_t *__restrict__ in, uint64_t total, uint32_t N, uint32_t ma
 
 // round-2 kernel (select_fast.cuh): 128 threads and ~38 KB of shared memory per chunk, five CTAs per SM
 template <int NMAX>
-__global__ void __launch_bounds__(SF_T, NMAX <= 4096 ? 5 : 2)
+__global__ void __launch_bounds__(SF_T, NMAX <= 4096 ? 5 : 3)
 k_select_fast(const uint8_t *__restrict__ in, uint64_t total, uint32_t N, uint32_t mask, uint32_t ovh,
               uint8_t *__restrict__ slots, uint64_t slot_stride, uint8_t *__restrict__ type,
               uint32_t *__restrict__ comp, unsigned long long *first_raw, uint64_t chunk_begin, uint64_t n_chunks)
@@ -226,7 +226,45 @@ static bool use_fast_select(uint32_t chunk)
 {
     static int mode = -1;
     if (mode < 0) { const char *e = getenv("AMBC_SELECT"); mode = (e && !strcmp(e, "old")) ? 0 : 1; }
-    return mode == 1 && chunk <= 4096;
+    return mode == 1 && chunk <= AMBC_NMAX;
+}
+
+// span mode (multi-candidate path, see k_select_span below) with the round-2 chunk code
+struct ChunkSpan;
+template <int NMAX>
+__global__ void __launch_bounds__(SF_T, NMAX <= 4096 ? 5 : 3)
+k_select_span_fast(const uint8_t *__restrict__ in, uint64_t total, uint32_t N, uint32_t mask, uint32_t ovh, uint32_t stride,
+                   const unsigned long long *__restrict__ list, uint8_t *__restrict__ slots, uint8_t *__restrict__ type,
+                   uint32_t *__restrict__ comp, uint64_t n_items)
+{
+    // list == nullptr: item i = [i * stride, i * stride + min(N, total - i * stride)), no payload kept;
+    // else item i = (pos, size) = (list[2 i], low half of list[2 i + 1]) and its payload goes to slots + pos
+    extern __shared__ uint4 smem4[];
+    SfCtx<NMAX> c;
+    sf_carve<NMAX>(c, (uint8_t *)smem4);
+    for (uint64_t i = blockIdx.x; i < n_items; i += gridDim.x) {
+        uint64_t off;
+        int n;
+        if (list) { off = list[2 * i]; n = (int)(uint32_t)list[2 * i + 1]; }
+        else { off = i * (uint64_t)stride; n = (int)min((uint64_t)N, total - off); }
+        sf_load<NMAX>(c, in + off, n);
+        const SfOut o = sf_select<NMAX>(c, mask, (int)ovh);
+        __syncthreads();
+        if (slots && o.type != 255) {
+            uint8_t *dst = slots + off;
+            if ((((uintptr_t)dst) & 15) == 0) {
+                const int nv = (o.len + 15) >> 4;
+                for (int k = threadIdx.x; k < nv; k += SF_T) ((uint4 *)dst)[k] = ((const uint4 *)c.pay)[k];
+            } else {
+                for (int k = threadIdx.x; k < o.len; k += SF_T) dst[k] = c.pay[k];
+            }
+        }
+        if (threadIdx.x == 0) {
+            type[i] = (uint8_t)o.type;
+            comp[i] = (uint32_t)o.len;
+        }
+        __syncthreads();
+    }
 }
 
 // ---- package-size scan ---------------------------------------------------------------------
@@ -491,7 +529,16 @@ static int launch_select_span(unsigned grid, size_t smem, cudaStream_t stream, c
                               uint32_t mask, uint32_t ovh, uint32_t stride, const ChunkSpan *list, uint8_t *slots,
                               uint8_t *type, uint32_t *comp, uint64_t n_items)
 {
-    if (N <= LZ2_NMAX) {
+    static_assert(sizeof(ChunkSpan) == 16, "k_select_span_fast reads spans as two 64-bit words");
+    if (use_fast_select(N) && N <= 4096) {
+        CUDA_TRY(cudaFuncSetAttribute(k_select_span_fast<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SfCfg<4096>::SMEM));
+        k_select_span_fast<4096><<<grid, SF_T, SfCfg<4096>::SMEM, stream>>>(in, total, N, mask, ovh, stride, (const unsigned long long *)list,
+                                                                            slots, type, comp, n_items);
+    } else if (use_fast_select(N)) {
+        CUDA_TRY(cudaFuncSetAttribute(k_select_span_fast<8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SfCfg<8192>::SMEM));
+        k_select_span_fast<8192><<<grid, SF_T, SfCfg<8192>::SMEM, stream>>>(in, total, N, mask, ovh, stride, (const unsigned long long *)list,
+                                                                            slots, type, comp, n_items);
+    } else if (N <= LZ2_NMAX) {
         CUDA_TRY(cudaFuncSetAttribute(k_select_span<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_select_span<2><<<grid, AMBC_BLOCK, smem, stream>>>(in, total, N, mask, ovh, stride, list, slots, type, comp, n_items);
     } else {
@@ -640,6 +687,7 @@ int ambc_compress_dev_impl(const void *in_dev, uint64_t n, uint32_t chunk, uint3
         CUDA_TRY(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute(k_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
         CUDA_TRY(cudaFuncSetAttribute(k_select_fast<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SfCfg<4096>::SMEM));
+        CUDA_TRY(cudaFuncSetAttribute(k_select_fast<8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SfCfg<8192>::SMEM));
         // piece-wise run (host-buffer path): select / scan / pack of piece k are queued behind the
         // upload of piece k; the finished body bytes of a piece go home while later pieces compute
         bool pieces = piece_ready && n_pieces > 1 && piece_start && piece_start[0] == 0 && piece_start[n_pieces] >= L.n_chunks;
@@ -659,8 +707,12 @@ int ambc_compress_dev_impl(const void *in_dev, uint64_t n, uint32_t chunk, uint3
             const unsigned gt = (unsigned)((c1 - c0 + SCAN_TILE - 1) / SCAN_TILE);
             if (pieces) CUDA_TRY(cudaStreamWaitEvent(stream, piece_ready[k], 0));
             if (k == 0) ambc_timing_mark(0, stream);
-            if (use_fast_select(chunk))
+            if (use_fast_select(chunk) && chunk <= 4096)
                 k_select_fast<4096><<<gch, SF_T, SfCfg<4096>::SMEM, stream>>>((const uint8_t *)in_dev, n, chunk, method_mask, ovh,
+                                                                             W + L.slots, L.slot_stride, type, comp,
+                                                                             &st->first_raw, c0, c1);
+            else if (use_fast_select(chunk))
+                k_select_fast<8192><<<gch, SF_T, SfCfg<8192>::SMEM, stream>>>((const uint8_t *)in_dev, n, chunk, method_mask, ovh,
                                                                              W + L.slots, L.slot_stride, type, comp,
                                                                              &st->first_raw, c0, c1);
             else
