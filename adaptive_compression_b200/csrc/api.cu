@@ -70,25 +70,25 @@ extern "C" int ambc_set_lz_force_buckets(int on)
 }
 
 // fold of the all-gathered placement records (see include/ambc.h; mirrors distributed.fold_placement)
-extern "C" int ambc_shard_place(const ambc_shard_rec *recs, uint32_t n_ranks, const uint64_t *first_chunk, uint32_t chunk,
+extern "C" int ambc_shard_place(const ambc_shard_rec *recs, uint32_t n_ranks, const uint64_t *first_byte, uint32_t chunk,
                                 uint32_t marker_bytes, ambc_shard_slot *out)
 {
-    if (!recs || !out || !first_chunk || n_ranks == 0 || chunk == 0 || marker_bytes < 1 || marker_bytes > 4)
+    if (!recs || !out || !first_byte || n_ranks == 0 || chunk == 0 || marker_bytes < 1 || marker_bytes > 4)
         return ambc_fail(AMBC_E_ARG, "ambc_shard_place: bad argument");
     uint64_t offset = 0, raw_chunk = 0, raw_payload_off = 0;
     bool raw_seen = false;
     for (uint32_t r = 0; r < n_ranks; r++) {
         out[r].reserved = 0;
         if (raw_seen) { // inside the one raw package: input bytes land behind its header
-            if (first_chunk[r] < raw_chunk) return ambc_fail(AMBC_E_ARG, "ambc_shard_place: shards out of order");
+            if (first_byte[r] < raw_chunk * (uint64_t)chunk) return ambc_fail(AMBC_E_ARG, "ambc_shard_place: shards out of order");
             out[r].state = AMBC_SHARD_IN_RAW_TAIL;
-            out[r].offset = raw_payload_off + (first_chunk[r] - raw_chunk) * (uint64_t)chunk;
+            out[r].offset = raw_payload_off + (first_byte[r] - raw_chunk * (uint64_t)chunk);
             continue;
         }
         out[r].offset = offset;
         offset += recs[r].packed_bytes;
         if (recs[r].first_raw >= 0) {
-            if ((uint64_t)recs[r].first_raw < first_chunk[r]) return ambc_fail(AMBC_E_ARG, "ambc_shard_place: first_raw before the shard");
+            if ((uint64_t)recs[r].first_raw * (uint64_t)chunk < first_byte[r]) return ambc_fail(AMBC_E_ARG, "ambc_shard_place: first_raw before the shard");
             out[r].state = AMBC_SHARD_RAW_STARTS;
             raw_seen = true;
             raw_chunk = (uint64_t)recs[r].first_raw;

@@ -49,14 +49,16 @@ def fold_placement(records):
     return out
 
 
-def fold_placement_native(records, first_chunks, chunk, marker_bytes=4):
+def fold_placement_native(records, first_bytes, chunk, marker_bytes=4):
     """the same fold through the C-ABI (ambc_shard_place): -> list of (offset, state); for ranks inside
-    the raw tail the offset is the place of their input bytes in the global body"""
+    the raw tail the offset is the place of their input bytes in the global body.  first_bytes[r] = input
+    byte offset of rank r's shard (shard_range()[1]: clamped to the input length, so an empty trailing
+    rank behind a partial last chunk still lands at the end of the raw data)"""
     import ctypes as C
     from . import _lib as L
     n = len(records)
     recs = (L.ShardRec * n)(*[L.ShardRec(int(b), int(fr)) for b, fr in records])
-    fc = (C.c_uint64 * n)(*[int(x) for x in first_chunks])
+    fc = (C.c_uint64 * n)(*[int(x) for x in first_bytes])
     out = (L.ShardSlot * n)()
     L.check(L.lib().ambc_shard_place(recs, n, fc, chunk, marker_bytes, out))
     names = ("packed", "raw_starts_here", "in_raw_tail")
@@ -86,14 +88,42 @@ def packed_bytes(body_len, n_local, first_raw_local, chunk, marker_bytes=4):
     return body_len - end - (marker_bytes + 14) - (n_local - first_raw_local * chunk)
 
 
+def fragment_plan(records, total_bytes, chunk, marker_bytes=4):
+    """-> ([(offset, length, state)] per rank, body length): where every rank's contribution lands in the
+    global body and how long it is, from the all-gathered records alone (every rank computes the same plan;
+    the shards are shard_range(total_bytes, chunk, r, world)).  The last rank's length includes the END
+    package.  Rule sharded: adaptive_compressor.py:586-590."""
+    world = len(records)
+    ovh, end = marker_bytes + 14, marker_bytes + 12
+    states = fold_placement(records)
+    g = next((fr for _, fr in records if fr >= 0), NO_RAW)  # global first raw chunk
+    packed_total = 0
+    if g >= 0:
+        packed_total = sum(nb for nb, _ in records[:next(i for i, (_, fr) in enumerate(records) if fr >= 0) + 1])
+    plan = []
+    for r, ((off, state), (nbytes, _)) in enumerate(zip(states, records)):
+        _, b0, b1 = shard_range(total_bytes, chunk, r, world)
+        if state == "packed":
+            length = nbytes
+        elif state == "raw_starts_here":
+            length = nbytes + ovh + (b1 - g * chunk)
+        else:  # input bytes, verbatim, inside the raw package (b0 is clamped to the input length)
+            off = packed_total + ovh + (b0 - g * chunk)
+            length = b1 - b0
+        if r == world - 1:
+            length += end
+        plan.append((off, length, state))
+    last_off, last_len, _ = plan[-1]
+    return plan, last_off + last_len
+
+
 def shard_fragment(local_body, local_input, first_raw_local, first_chunk_global, chunk, total_bytes, records, rank,
                    marker=b"\xff\xff\x00\x00"):
     """-> (global byte offset, 1-D uint8 tensor) this rank contributes to the global body (the END
     package is appended by the last rank).  local_body / local_input are tensors on any device."""
     mb = len(marker)
-    ovh = mb + 14
-    plan = fold_placement(records)
-    offset, state = plan[rank]
+    plan, _ = fragment_plan(records, total_bytes, chunk, mb)
+    offset, length, state = plan[rank]
     n_local = local_input.numel()
     pk = packed_bytes(local_body.numel(), n_local, first_raw_local, chunk, mb)
     last = rank == len(records) - 1
@@ -109,12 +139,33 @@ def shard_fragment(local_body, local_input, first_raw_local, first_chunk_global,
         hdr_t = torch.tensor(list(hdr), dtype=torch.uint8, device=local_body.device)
         frag = torch.cat([local_body[:pk], hdr_t, local_input[first_raw_local * chunk:]])
     else:
-        packed_total = sum(nb for nb, _ in records[:next(i for i, (_, fr) in enumerate(records) if fr >= 0) + 1])
-        offset = packed_total + ovh + (first_chunk_global * chunk - g * chunk)
         frag = local_input
     if last:
         frag = torch.cat([frag, end_pkg])
+    assert frag.numel() == length, (frag.numel(), length, state)
     return offset, frag
+
+
+def assemble_body(frag, records, total_bytes, chunk, marker_bytes=4, dst=0, out=None):
+    """Gather every rank's fragment into ONE body on rank `dst` (NCCL send / recv straight into the placed
+    slice of the destination buffer -- NVLink peer copies; gloo on CPU).  Returns the body tensor on `dst`
+    (None elsewhere).  `out`: optional preallocated destination on `dst` (>= body length)."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    plan, body_len = fragment_plan(records, total_bytes, chunk, marker_bytes)
+    if rank != dst:
+        if frag.numel():
+            dist.send(frag.contiguous(), dst)
+        return None
+    body = out[:body_len] if out is not None else torch.empty(body_len, dtype=torch.uint8, device=frag.device)
+    reqs = []
+    for r, (off, length, _) in enumerate(plan):
+        if r == dst:
+            body[off:off + length].copy_(frag)
+        elif length:
+            reqs.append(dist.irecv(body[off:off + length], r))
+    for q in reqs:
+        q.wait()
+    return body
 
 
 def merge_marker_flags(flags):

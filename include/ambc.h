@@ -261,14 +261,16 @@ int ambc_last_timing(float *ms4);
  * across shards: out[r].offset = byte offset of rank r's contribution in the global body and
  * out[r].state = AMBC_SHARD_PACKED (its packed fragment), AMBC_SHARD_RAW_STARTS (packed part, then the
  * header of the one global raw package and its input from the raw chunk on) or AMBC_SHARD_IN_RAW_TAIL
- * (its input bytes, verbatim, inside that package).  first_chunk[r] = global index of rank r's first
- * chunk.  Pure host arithmetic; needs no device. */
+ * (its input bytes, verbatim, inside that package).  first_byte[r] = input byte offset of rank r's shard
+ * (a multiple of the chunk size, or the input length for an empty trailing rank -- byte offsets rather than
+ * chunk indices so that such a rank lands at the end of the raw data when the last chunk is partial).
+ * Pure host arithmetic; needs no device. */
 typedef struct { uint64_t packed_bytes; int64_t first_raw; } ambc_shard_rec;
 typedef struct { uint64_t offset; uint32_t state; uint32_t reserved; } ambc_shard_slot;
 #define AMBC_SHARD_PACKED 0
 #define AMBC_SHARD_RAW_STARTS 1
 #define AMBC_SHARD_IN_RAW_TAIL 2
-int ambc_shard_place(const ambc_shard_rec *recs, uint32_t n_ranks, const uint64_t *first_chunk, uint32_t chunk,
+int ambc_shard_place(const ambc_shard_rec *recs, uint32_t n_ranks, const uint64_t *first_byte, uint32_t chunk,
                      uint32_t marker_bytes, ambc_shard_slot *out);
 
 /* pinned host memory helpers for callers without their own allocator */

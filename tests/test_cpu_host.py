@@ -227,7 +227,7 @@ def test_shard_place_c_abi_matches_python_fold():
             fr = -1 if r.rand() < 0.7 else first_chunks[k] + int(r.randint(0, per))
             recs.append((int(r.randint(0, per * chunk)), fr))
         want = D.fold_placement(recs)
-        got = D.fold_placement_native(recs, first_chunks, chunk)
+        got = D.fold_placement_native(recs, [c * chunk for c in first_chunks], chunk)
         assert [s for _, s in got] == [s for _, s in want]
         g = next((fr for _, fr in recs if fr >= 0), None)
         for k, ((off, state), (woff, _)) in enumerate(zip(got, want)):

@@ -38,6 +38,10 @@ def _worker(rank, world, port, data, chunk, q):
         pk = D.packed_bytes(len(body), len(local), first_raw, chunk)
         (off, state), recs = D.place_shards(pk, first_raw, c0, world)
         goff, frag = D.shard_fragment(t_body, t_in, first_raw, c0, chunk, len(data), recs, rank)
+        # the assembled body on rank 0 (send / recv straight into the placed slices)
+        whole = D.assemble_body(frag, recs, len(data), chunk)
+        if rank == 0:
+            q.put((-1, 0, whole.numpy().tobytes(), "assembled", b""))
         # marker flags: each rank marks some values, the merge must be the union
         flags = torch.zeros(64, dtype=torch.uint8)
         flags[rank::world] = 1
@@ -55,7 +59,7 @@ def _run(world, data, chunk):
     procs = [ctx.Process(target=_worker, args=(r, world, port, data, chunk, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=120) for _ in range(world))
+    res = sorted(q.get(timeout=120) for _ in range(world + 1))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -76,6 +80,8 @@ def test_sharded_body_equals_single_shot(world, case):
     data = b"".join(parts) + inputs.text(300, 9)
     want, _ = O.compress_body(data, chunk)
     res = _run(world, data, chunk)
+    assert res[0][3] == "assembled" and res[0][2] == want, case
+    res = res[1:]
     out = bytearray(len(want))
     covered = 0
     for rank, off, frag, state, flags in res:
@@ -89,3 +95,24 @@ def test_sharded_body_equals_single_shot(world, case):
     assert covered == len(want)
     assert bytes(out) == want, case
     assert O.decompress_body(bytes(out), len(data)) == data
+
+
+@pytest.mark.parametrize("world,n_chunks,tail,raw_at", [(4, 3, 500, 0), (4, 3, 500, 1), (3, 2, 1, 0), (4, 2, 0, 1), (2, 5, 77, 4),
+                                                     (4, 3, 500, None), (3, 1, 300, 0)])
+def test_more_ranks_than_chunks_and_partial_last_chunk(world, n_chunks, tail, raw_at):
+    """empty trailing ranks behind a partial last chunk, with the raw chunk in an early rank --
+    the END package has to land right behind the raw data"""
+    chunk = 1024
+    data = bytearray(inputs.mixed_file(n_chunks, chunk, 900 + n_chunks, ("text", "log", "runs", "lowcard")))
+    if tail:
+        data = data[:(n_chunks - 1) * chunk + tail]
+    if raw_at is not None:
+        a = raw_at * chunk
+        b = min(len(data), a + chunk)
+        data[a:b] = inputs.rand(b - a, 5)
+    data = bytes(data)
+    want, _ = O.compress_body(data, chunk)
+    res = _run(world, data, chunk)
+    assert res[0][3] == "assembled"
+    assert res[0][2] == want, (world, n_chunks, tail, raw_at, len(res[0][2]), len(want))
+    assert O.decompress_body(res[0][2], len(data)) == data
