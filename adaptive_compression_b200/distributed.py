@@ -130,6 +130,9 @@ def shard_fragment(local_body, local_input, first_raw_local, first_chunk_global,
     end_pkg = torch.tensor(list(marker + bytes(12)), dtype=torch.uint8, device=local_body.device)
     g = next((fr for _, fr in records if fr >= 0), NO_RAW)  # global first raw chunk
     if state == "packed":
+        if last and first_raw_local < 0:  # the local body ends with the same END package: no copy
+            assert local_body.numel() == pk + mb + 12
+            return offset, local_body
         frag = local_body[:pk]
     elif state == "raw_starts_here":
         rawlen = total_bytes - g * chunk

@@ -5,9 +5,11 @@ methods only.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--size-mib M]
 
-N = 1 : configs[1], 1 GiB on one B200.  N > 1 (torchrun): every rank takes a contiguous 1 GiB
-chunk-range shard of an N GiB corpus (weak scaling); the only exchange on the path is the
-all-gather of 16-byte shard placement records.
+N = 1 : configs[1], 1 GiB on one B200.  N > 1 (torchrun): configs[3] -- every rank takes a contiguous
+4 GiB chunk-range shard of a 4 N GiB corpus (weak scaling; 32 GiB at 8 GPUs), compresses it, the 16-byte
+shard placement records are all-gathered and every rank's fragment is sent into its placed
+slice of ONE body on rank 0 (NCCL send / recv over NVLink) -- placement and assembly are inside the timed
+compress.
 
 One step = compress the resident shard (device input -> device .ambc body) then decompress it
 (device body -> package index built on the GPU -> device output).  `value` = bytes / (t_compress + t_decompress),
@@ -39,9 +41,10 @@ CHUNK = 4096
 
 
 def workload_config(size_mib, n_gpus):
-    return {"workload": "configs[1]: %d MiB/GPU synthetic mixed CSV/log/runs/lowcard/binary/text corpus, chunk 4096, "
+    name = "configs[1]" if n_gpus == 1 else "configs[3] (%d GiB corpus sharded by chunk range, one body assembled on rank 0)" % (size_mib * n_gpus >> 10)
+    return {"workload": "%s: %d MiB/GPU synthetic mixed CSV/log/runs/lowcard/binary/text corpus, chunk 4096, "
                         "methods RLE+Dictionary+Huffman+Delta (third-party disabled), strict reference semantics, "
-                        "compress + decompress round trip" % size_mib,
+                        "compress + decompress round trip" % (name, size_mib),
             "bytes_per_gpu": size_mib << 20, "chunk": CHUNK, "seed": "0xA3BC0001", "sharding": "contiguous chunk ranges, %d shard(s)" % n_gpus,
             "cache": "inputs larger than L2 (no flush needed)"}
 
@@ -99,6 +102,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if not args.size_mib:
+        args.size_mib = 1024 if int(os.environ.get("WORLD_SIZE", "1")) == 1 else 4096
     threads = os.cpu_count() or 1
     sample = cpu_sample_bytes(args, threads)
     args.cpu_sample_mib = sample >> 20
@@ -207,6 +212,97 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------
+def per_kind_table(engine, lib, L, peak, mib=64):
+    """k_select / decoders on 64 MiB of every corpus kind: ms, input GB/s and (N + C) / t against the HBM roof --
+    the mixed corpus hides a 20 x spread between kinds"""
+    import torch
+    names = ["csv", "log", "runs", "lowcard", "binrec", "random", "text"]
+    out = {}
+    n = mib << 20
+    lib.ambc_enable_timing(1)
+    for k in (0, 1, 2, 3, 4, 6):
+        t = engine.synth(n, 0, kind_mask=1 << k)
+        sel, dec = [], []
+        o = None
+        for _ in range(3):
+            o = engine.compress_device(t, CHUNK)
+            ms = (C.c_float * 4)()
+            lib.ambc_last_timing(ms)
+            sel.append(ms[0])
+        for _ in range(3):
+            back, st = engine.decompress_device(o.body, n)
+            ms = (C.c_float * 4)()
+            lib.ambc_last_timing(ms)
+            dec.append(ms[3])
+        assert torch.equal(back, t) and st == [0, 0]
+        s_ms, d_ms = min(sel), min(dec)
+        c = int(o.body_len)
+        out[names[k]] = {"k_select_ms": s_ms, "compress_gbps": n / (s_ms * 1e-3) / 1e9, "compress_frac": (n + c) / (s_ms * 1e-3) / 1e9 / peak,
+                         "decode_ms": d_ms, "decode_gbps": n / (d_ms * 1e-3) / 1e9, "decode_frac": (n + c) / (d_ms * 1e-3) / 1e9 / peak,
+                         "ratio": c / n, "usage_raw_rle_dict_huff_delta": [int(x) for x in o.usage]}
+    lib.ambc_enable_timing(0)
+    return {"bytes_per_kind": n, "note": "best of 3; k_select only / decode kernels only (device timers of the library)", "kinds": out}
+
+
+def full_size_parity(args, engine, t_in, n, threads):
+    """same-run parity at the full size: the CUDA body of the whole shard against the CPU port with its indexed match
+    search (proven equal to the naive scan on the golden vectors and on the baseline sample above)"""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    lib = O.lib()
+    data = t_in.cpu().numpy()
+    meth = np.array([1, 2, 3, 4], dtype=np.int32)
+    per = (n // CHUNK + threads - 1) // threads * CHUNK
+    outs = [np.empty(per + (per // CHUNK + 2) * 18 + 64, dtype=np.uint8) for _ in range(threads)]
+    out_ptrs = (C.c_void_p * threads)(*[o.ctypes.data for o in outs])
+    lens = np.zeros(threads, dtype=np.int64)
+    O.set_lz_fast(True)
+    t0 = time.perf_counter()
+    lib.orc_mt_compress(data.ctypes.data, n, CHUNK, meth.ctypes.data, 4, threads, out_ptrs, lens.ctypes.data)
+    dt = time.perf_counter() - t0
+    O.set_lz_fast(False)
+    body = np.concatenate([outs[t][:max(0, lens[t] - 16)] for t in range(threads)] + [outs[0][lens[0] - 16:lens[0]]])
+    chk = engine.compress_device(t_in, CHUNK)
+    same = int(chk.body_len) == body.size and bool(torch.equal(chk.body[:chk.body_len].cpu(), torch.from_numpy(body)))
+    assert same, "parity: CUDA body of the whole shard differs from the CPU port's body"
+    return {"bytes": n, "body_bytes": int(body.size), "equal": True, "cpu_seconds": dt,
+            "oracle": "C port, indexed match search (lz_fast), %d threads" % threads}
+
+
+def bind_to_gpu_numa_node(index):
+    """Pin this rank (and with it the first-touch placement of its pinned host buffers and the helper
+    threads of the host package walk) to the CPUs of its GPU's NUMA node: with 8 ranks on one host the
+    host-buffer path otherwise crosses sockets for half of its copies.  Returns a description or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = index
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if index < len(ids) and ids[index].isdigit():
+                phys = int(ids[index])
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dev = "/sys/bus/pci/devices/" + bus.lower()[-12:]
+        node = int(open(dev + "/numa_node").read())
+        cpulist = open(dev + "/local_cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node < 0 or not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception:  # noqa: BLE001
+        return None
+
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -219,6 +315,7 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     # stdout carries exactly one JSON line: anything libraries print meanwhile (the NCCL version banner
     # at the first collective, for one) goes to stderr
     sys.stdout.flush()
@@ -227,6 +324,8 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = engine.require_cuda()
+    if not args.size_mib:
+        args.size_mib = 1024 if world == 1 else 4096
     n = args.size_mib << 20
     mask = L.NATIVE_MASK
     marker = engine.FIXED_MARKER
@@ -245,12 +344,23 @@ def run_b200(args):
         L.check(lib.ambc_compress_dev(C.c_void_p(t_in.data_ptr()), n, CHUNK, mask, 0, marker, 4,
                                       C.c_void_p(t_out.data_ptr()), bound, C.c_void_p(t_work.data_ptr()),
                                       t_work.numel(), C.byref(res), stream))
-        if world > 1:  # shard placement: all-gather of (bytes before first raw, first raw chunk)
-            return D.place_shards(D.packed_bytes(res.body_len, n, res.first_raw, CHUNK), res.first_raw,
-                                  rank * (n // CHUNK), world)
+        if world > 1:
+            # shard placement: all-gather of (bytes before first raw, first raw chunk), then every fragment goes
+            # into its placed slice of the one body on rank 0
+            c0 = rank * (n // CHUNK)
+            _, recs = D.place_shards(D.packed_bytes(res.body_len, n, res.first_raw, CHUNK), res.first_raw, c0, world)
+            _, frag = D.shard_fragment(t_out[:res.body_len], t_in, res.first_raw, c0, CHUNK, n * world, recs, rank)
+            return D.assemble_body(frag, recs, n * world, CHUNK, out=t_global)
         return None
 
-    compress()
+    # destination of the assembled body (rank 0): the bound of the whole corpus
+    t_global = torch.empty(lib.ambc_compress_bound(n * world, CHUNK, 4), dtype=torch.uint8, device="cuda") \
+        if world > 1 and rank == 0 else None
+    g_body = compress()
+    if world > 1 and rank == 0:
+        # the assembled body is the body of the whole corpus: its first shard-worth decodes to this rank's input
+        # (full check against a single-GPU run: tests/test_gpu_multirank.py)
+        assert g_body is not None and int(g_body.numel()) > 16 and bytes(g_body[-16:].cpu().tolist()) == marker + bytes(12)
     body_len = int(res.body_len)
     assert res.first_raw == -1, "bench corpus must have a native winner in every chunk"
     # package index: built on the GPU inside the timed decompress (ambc_index_dev); the host walk that the
@@ -313,7 +423,7 @@ def run_b200(args):
     tc_m, td_m, tstep = tt.cpu().tolist()
 
     # e2e through the C-ABI host calls (pinned buffers)
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, args.steps)
     h_in = torch.empty(n, dtype=torch.uint8, pin_memory=True)
     h_in.copy_(t_in)
     h_body = torch.empty(bound, dtype=torch.uint8, pin_memory=True)
@@ -359,8 +469,13 @@ def run_b200(args):
             mk, mk_bits = D.find_marker_sharded(t_in, 32)
             mev[1].record()
             torch.cuda.synchronize()
-            marker_info = {"marker_hex": mk.hex(), "bits": mk_bits, "ms": mev[0].elapsed_time(mev[1]),
-                           "collective": "1 x all_gather(40 B/rank) + 1 x all_reduce(MAX, 2^16 B flags) over NCCL"}
+            mk_ms = mev[0].elapsed_time(mev[1])
+            marker_info = {"marker_hex": mk.hex(), "bits": mk_bits, "ms": mk_ms,
+                           "collective": "1 x all_gather(40 B/rank), then per level tried (16 bits: 2^16 B of flags; "
+                                         "24 bits: 2^24 B) 1 x all_reduce(MAX) over NCCL; %d-bit result: %s" %
+                                         (mk_bits, "16-bit level only" if mk_bits <= 16 else "both levels ran"),
+                           "roofline": {"bound": "hbm", "achieved": n / (mk_ms * 1e-3) / 1e9, "unit": "GB/s",
+                                        "note": "shard bytes / time of the whole sharded search (flags kernels + collectives + pick)"}}
         except Exception as e:  # noqa: BLE001
             marker_info = {"error": str(e)[:200]}
 
@@ -371,12 +486,15 @@ def run_b200(args):
         if os.path.exists(pk_path):
             peaks = json.load(open(pk_path))
             peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-        traffic = args.traffic
-        tr_path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if traffic is None and os.path.exists(tr_path):
-            tr = json.load(open(tr_path))
-            if tr.get("bytes_per_gpu") == n and tr.get("chunk") == CHUNK:  # same launch shape as the capture
-                traffic = tr["traffic_bytes_per_launch"]
+        traffic, traffic_source = args.traffic, "--traffic" if args.traffic is not None else None
+        for tr_name in ("r02_traffic.json", "r01_traffic.json"):
+            tr_path = os.path.join(ROOT, "profiles", tr_name)
+            if traffic is None and os.path.exists(tr_path):
+                tr = json.load(open(tr_path))
+                if tr.get("bytes_per_gpu") == n and tr.get("chunk") == CHUNK:  # same launch shape as the capture
+                    traffic = tr["traffic_bytes_per_launch"]
+                    traffic_source = "profiles/%s (%s): a committed ncu capture of this launch shape, not a measurement of this run" % (
+                        tr_name, tr.get("capture", "ncu --set full"))
         payload = int(res.payload_bytes)
         sel_ms = statistics.mean(ksel)
         algo_bytes = n + payload  # k_select reads the shard once and writes every winning payload once
@@ -393,7 +511,7 @@ def run_b200(args):
                           "k_decode": statistics.mean(kdec), "gpu_index": statistics.mean(kidx),
                           "host_index_walk_ms": t_index * 1e3},
             "roofline": {"bound": "hbm", "kernel": "k_select", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes,
                          "decode": {"kernel": "k_decode", "achieved": (body_len + n) / (statistics.mean(kdec) * 1e-3) / 1e9,
                                     "frac": (body_len + n) / (statistics.mean(kdec) * 1e-3) / 1e9 / peak}},
@@ -407,6 +525,10 @@ def run_b200(args):
         }
         if marker_info is not None:
             line["marker_search"] = marker_info
+        if numa is not None:
+            line["config"]["numa_binding"] = numa
+        if world == 1 and not args.no_kinds:
+            line["roofline"]["per_kind"] = per_kind_table(engine, lib, L, peak)
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
             args.cpu_sample_mib = cpu_sample_bytes(args, threads) >> 20
@@ -417,7 +539,18 @@ def run_b200(args):
             same = chk.body_len == r["body"].size and bool(
                 torch.equal(chk.body[:chk.body_len].cpu(), torch.from_numpy(r["body"])))
             assert same, "parity: CUDA body differs from the CPU port's body on the baseline sample"
+            pyref = None
+            pr_path = os.path.join(ROOT, "profiles", "r02_python_reference_timing.json")
+            if os.path.exists(pr_path):
+                pr = json.load(open(pr_path))
+                pyref = {"source": "profiles/r02_python_reference_timing.json (build container, oracle/time_python_reference.py; "
+                                   "the reference cannot travel to the GPU box)",
+                         "one_core_roundtrip_kb_s": pr["one_core"]["roundtrip_kb_s"],
+                         "eight_processes_roundtrip_kb_s": pr["eight_processes"]["roundtrip_kb_s"],
+                         "host": pr.get("host"), "cpus": pr.get("cpus")}
+            full = full_size_parity(args, engine, t_in, n, threads) if not args.no_full_parity else None
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "python_reference": pyref, "full_size_parity": full,
                                     "compress_gbps": (args.cpu_sample_mib << 20) / r["compress_s"] / 1e9,
                                     "decompress_gbps": (args.cpu_sample_mib << 20) / r["decompress_s"] / 1e9,
                                     "parity": "CUDA body == CPU port body on the sample (%d bytes), bit-exact" % r["body"].size,
@@ -438,10 +571,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--size-mib", type=int, default=1024)
+    ap.add_argument("--size-mib", type=int, default=0, help="MiB per GPU (0: 1024 at N = 1 = configs[1], 4096 at N > 1 = configs[3])")
+    ap.add_argument("--no-kinds", action="store_true", help="skip the per-kind table (roofline.per_kind)")
     ap.add_argument("--cpu-sample-mib", type=int, default=0,
                     help="MiB of the corpus the CPU legs process per pass (0 = calibrate to ~10 s per pass)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-full-parity", action="store_true", help="skip the CPU body of the whole shard (indexed oracle)")
     ap.add_argument("--traffic", type=float, default=None,
                     help="dram bytes per k_select launch from the committed ncu capture (profiles/)")
     args = ap.parse_args()
