@@ -7,10 +7,11 @@ END package (:595-607), "rest of the file is one raw package" when a chunk has n
 (:586-590), verbatim copy when header+body is larger than the input (:241-247).
 
 What differs, on purpose:
-  * CHUNK_SIZE_CANDIDATES defaults to ONE size (4096, the documented --chunk-size default,
-    README.md:79) -- the benchmarked fixed-grid path.  Several candidates (chunk_size=[...] or
-    chunk_size="dynamic" for the reference's own list 131072..1024, :61-62) run the reference's
-    dynamic multi-size search (:548-584): every size is tried at every position on the GPU.
+  * CHUNK_SIZE_CANDIDATES defaults to the reference's own list 131072..1024 (:61-62), so a caller without
+    arguments writes the files the reference writes (dynamic multi-size search, :548-584: every size is
+    tried at every position on the GPU).  chunk_size=N selects ONE size -- the fixed grid of the benchmarked
+    path (--chunk-size 4096 in BASELINE.json's configs), an order of magnitude faster.  Candidate lists are
+    searched largest first (the reference honours the list order on ratio ties; its own list is descending).
   * only the repo-native methods 1-4 (+255) are loaded; third-party codecs 5-11 are out of scope.
   * per_chunk_raw=True and use_marker_search=True are labelled extensions (files stay readable by
     the reference decoder)."""
@@ -42,7 +43,7 @@ REFERENCE_CANDIDATES = (131072, 65536, 32768, 16384, 8192, 4096, 2048, 1024)  # 
 class AdaptiveCompressor:
     MAGIC_NUMBER = b"AMBC"
     FORMAT_VERSION = 2
-    CHUNK_SIZE_CANDIDATES = [4096]
+    CHUNK_SIZE_CANDIDATES = list(REFERENCE_CANDIDATES)
 
     def __init__(self, marker_max_length=32, sample_size=10000, chunk_size=None, methods=None,
                  disable_methods=None, per_chunk_raw=False, use_marker_search=False):
@@ -80,6 +81,7 @@ class AdaptiveCompressor:
         self.method_chunk_prefs = dict(METHOD_CHUNK_PREFS)
         self.chunk_stats = {}
         self.last_timing = {}
+        self.last_status = [0, 0]  # decompress: [packages whose codec raised, packages with a length mismatch]
 
     # ---- no-op knobs kept for API compatibility (adaptive_compressor.py:179-194) ----
     def set_progress_callback(self, callback):
@@ -152,52 +154,96 @@ class AdaptiveCompressor:
         return engine.method_mask(ids)
 
     # ---- compress (adaptive_compressor.py:221-255) ----
+    @staticmethod
+    def _read_with_md5(path, slot):
+        """file -> (pinned uint8 array, join() -> md5 digest): the file is read in pieces into page-locked memory
+        while a thread hashes the pieces already there (MD5 is a serial chain at ~0.6 GB/s, the floor of this API;
+        hashlib releases the GIL)"""
+        n = os.path.getsize(path)
+        buf = engine.pinned(slot, max(n, 1))
+        h = hashlib.md5()
+        done = [0]
+        cv = threading.Condition()
+
+        def hasher():
+            pos = 0
+            while pos < n:
+                with cv:
+                    while done[0] <= pos:
+                        cv.wait()
+                    upto = done[0]
+                h.update(memoryview(buf)[pos:upto])
+                pos = upto
+
+        th = threading.Thread(target=hasher)
+        th.start()
+        piece = 32 << 20
+        with open(path, "rb", buffering=0) as f:
+            pos = 0
+            while pos < n:
+                got = f.readinto(memoryview(buf)[pos:min(n, pos + piece)])
+                if not got:
+                    raise IOError("short read of %s" % path)
+                pos += got
+                with cv:
+                    done[0] = pos
+                    cv.notify()
+
+        def join():
+            th.join()
+            return h.digest()
+        return buf[:n], join
+
     def compress(self, input_file, output_file):
         start_t = time.time()
         engine.require_cuda()
         chunk = self._fixed_chunk()
         mask = self._method_mask()
-        file_data = np.fromfile(input_file, dtype=np.uint8)
+        file_data, md5_join = self._read_with_md5(input_file, "in")
         n = int(file_data.size)
         t_read = time.time()
-        md5 = {}
-        th = threading.Thread(target=lambda: md5.setdefault("d", hashlib.md5(file_data).digest()))
-        th.start()  # MD5 is a serial chain; hashlib releases the GIL, so it overlaps the GPU work
 
         marker_bytes, marker_len = self._find_marker(file_data, self.sample_size)
         self._init_marker(marker_bytes, marker_len)
-        t_in = torch.from_numpy(file_data).to("cuda") if n else torch.empty(0, dtype=torch.uint8, device="cuda")
         flags = L.F_PER_CHUNK_RAW if self.per_chunk_raw else 0
         if chunk is None:  # several candidate sizes: the reference's dynamic mode (:548-584)
+            t_in = torch.from_numpy(file_data).to("cuda") if n else torch.empty(0, dtype=torch.uint8, device="cuda")
             out = engine.compress_dynamic_device(t_in, self.CHUNK_SIZE_CANDIDATES, mask, flags, self.marker_bytes_aligned)
             self._fill_chunk_stats_packages(out.packages, n)
+            body, body_len = None, int(out.body_len)
         else:
-            out = engine.compress_device(t_in, chunk, mask, flags, self.marker_bytes_aligned)
-            if out.first_raw >= 0 and not self.per_chunk_raw and n - out.first_raw * chunk > 0xFFFFFFFF:
+            # fixed grid: the pipelined host-buffer path of the C-ABI (ambc_compress_host)
+            body, res, types, comps = engine.compress_host(file_data, n, chunk, mask, flags, self.marker_bytes_aligned)
+            if res.first_raw >= 0 and not self.per_chunk_raw and n - res.first_raw * chunk > 0xFFFFFFFF:
                 raise struct.error("'I' format requires 0 <= number <= 4294967295")  # as struct.pack at :617-619
-            self._fill_chunk_stats(out, n, chunk)
+            self._fill_chunk_stats(res, types, comps, n, chunk)
+            body_len = int(res.body_len)
         t_gpu = time.time()
-        th.join()
-        header = self._build_header(marker_bytes[:self.marker_byte_length], marker_len, md5["d"], n, out.body_len)
-        final_size = len(header) + out.body_len
+        header = self._build_header(marker_bytes[:self.marker_byte_length], marker_len, b"\0" * 16, n, body_len)
+        final_size = len(header) + body_len
         if final_size > n:
             print("Compression bigger than original => store raw.")
             file_data.tofile(output_file)
+            md5_join()
             stats = self._build_stats_raw(n, time.time() - start_t)
         else:
-            body = out.body.cpu().numpy()
-            with open(output_file, "wb") as f:
+            if body is None:
+                body = out.body.cpu().numpy()
+            with open(output_file, "wb") as f:  # body first (the checksum is still being computed), header patched in
                 f.write(header)
                 body.tofile(f)
+                header = self._build_header(marker_bytes[:self.marker_byte_length], marker_len, md5_join(), n, body_len)
+                f.seek(0)
+                f.write(header)
             stats = self._calculate_compression_stats(n, final_size, time.time() - start_t)
         self.last_timing = {"read_s": t_read - start_t, "gpu_s": t_gpu - t_read, "total_s": time.time() - start_t}
         return stats
 
-    def _fill_chunk_stats(self, out, n, chunk):
-        """same numbers as _init_stats/_update_stats (:457-480) + the END overhead (:393)"""
+    def _fill_chunk_stats(self, out, types, comps, n, chunk):
+        """same numbers as _init_stats/_update_stats (:457-480) + the END overhead (:393); out = CompressResult,
+        types / comps = the per-chunk method map"""
         ovh = self.marker_byte_length + 14
-        types = out.types.cpu().numpy()
-        comps = out.comp_lens.cpu().numpy().astype(np.int64)
+        comps = comps.astype(np.int64)
         limit = int(out.n_chunks)
         if out.first_raw >= 0 and not self.per_chunk_raw:
             limit = int(out.first_raw)
@@ -274,16 +320,22 @@ class AdaptiveCompressor:
     def decompress(self, input_file, output_file):
         start_t = time.time()
         engine.require_cuda()
-        cdata = np.fromfile(input_file, dtype=np.uint8)
-        hdr = self._parse_header(cdata.tobytes()[:64] if cdata.size >= 64 else cdata.tobytes())
+        size = os.path.getsize(input_file)
+        cdata = engine.pinned("cin", max(size, 1))[:size]
+        with open(input_file, "rb", buffering=0) as f:
+            pos = 0
+            while pos < size:
+                got = f.readinto(memoryview(cdata)[pos:])
+                if not got:
+                    raise IOError("short read of %s" % input_file)
+                pos += got
+        hdr = self._parse_header(cdata[:64].tobytes())
         self._init_marker(hdr["marker_bytes"], hdr["marker_length"])
         body = cdata[hdr["header_size"]:]
         known = engine.method_mask([m.type_id for m in self.compression_methods if m.type_id != 255])
-        t_body = torch.from_numpy(body).to("cuda") if body.size else torch.empty(0, dtype=torch.uint8, device="cuda")
-        # package index on the GPU (ambc_index_dev); the host walk (engine.index_host) gives the same table
-        out, status = engine.decompress_device(t_body, hdr["original_size"], self.marker_bytes_aligned, known,
-                                               gpu_index=True)
-        decompressed = out.cpu().numpy()
+        # the pipelined host-buffer path of the C-ABI (ambc_decompress_host): the package walk on the host runs
+        # ahead of the upload, decode and download overlap
+        decompressed, status = engine.decompress_host(body, hdr["original_size"], self.marker_bytes_aligned, known)
         md5 = {}
         th = threading.Thread(target=lambda: md5.setdefault("d", hashlib.md5(decompressed).digest()))
         th.start()  # the checksum (a serial chain, GIL released) runs while the file is written
@@ -292,6 +344,8 @@ class AdaptiveCompressor:
         self.last_status = status
         if md5["d"] != hdr["checksum"]:  # (the output file stays, as in the reference: written at :294, checked at :297-299)
             raise ValueError("Checksum mismatch => possibly corrupted file.")
+        if status != [0, 0]:  # cannot happen with a matching checksum unless the damage cancels out; say so anyway
+            print("Warning: %d package(s) failed to decode, %d with a length mismatch" % (status[0], status[1]))
         elapsed = time.time() - start_t
         dsize = int(decompressed.size)
         return {"compressed_size": int(cdata.size), "decompressed_size": dsize, "elapsed_time": elapsed,

@@ -806,6 +806,10 @@ int ambc_compress_dev_impl(const void *in_dev, uint64_t n, uint32_t chunk, uint3
         h_st.usage[0] = 1;
     }
     if (h_st.body_len > out_cap) return ambc_fail(AMBC_E_CAPACITY, "ambc_compress_dev: out_cap too small");
+    // the rest-of-file raw package carries its length in u32 fields (adaptive_compressor.py:617-619)
+    if (native && !(flags & AMBC_F_PER_CHUNK_RAW) && h_st.first_raw != ~0ull &&
+        n - h_st.first_raw * (uint64_t)chunk > 0xFFFFFFFFull)
+        return ambc_fail(AMBC_E_ARG, "raw package over 4 GiB cannot be framed (u32 fields)");
     res->body_len = h_st.body_len;
     res->first_raw = h_st.first_raw == ~0ull ? -1 : (int64_t)h_st.first_raw;
     res->n_packages = h_st.n_packages;

@@ -367,8 +367,12 @@ int ambc_decode_launch(const void *body_dev, const ambc_pkg *table_dev, uint64_t
     if (n_entries == 0) return AMBC_OK;
     const int in_cap = DEC_OUT_CAP; // payloads the reference's encoder emits are < orig_len <= 8192
     size_t smem = decctx_smem_bytes(in_cap);
-    static bool attr_done = false;
+    static bool attr_done_dev[16] = {}; // (function attributes are per device)
     size_t lsmem = (size_t)DLZ_WARPS * DLZ_OUT, lsmem_big = (size_t)DLZ_WARPS * DLZ_OUT_BIG;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) return ambc_fail(AMBC_E_ARG, "device index out of range");
+    bool &attr_done = attr_done_dev[dev];
     if (!attr_done) {
         CUDA_TRY(cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute(k_decode_lz<DLZ_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
@@ -379,9 +383,6 @@ int ambc_decode_launch(const void *body_dev, const ambc_pkg *table_dev, uint64_t
     // joined back into the caller's stream
     static cudaStream_t side[16] = {};
     static cudaEvent_t ev_fork[16] = {}, ev_join[16] = {};
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 16) return ambc_fail(AMBC_E_ARG, "device index out of range");
     if (!side[dev]) {
         CUDA_TRY(cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming));

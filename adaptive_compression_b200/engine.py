@@ -290,3 +290,50 @@ def synth(n, offset=0, seed=0xA3BC0001, kind_mask=0b1011111, out=None):
         out = torch.empty(n, dtype=torch.uint8, device="cuda")
     L.check(lib.ambc_synth_dev(C.c_void_p(out.data_ptr() if n else 0), offset, n, seed, kind_mask, _stream_ptr()))
     return out[:n]
+
+
+# ---- pinned host buffers for the file API (grow-only cache: pinning a GiB costs a few 100 ms) ----------
+_PINNED = {}
+
+
+def pinned(slot, nbytes):
+    """numpy uint8 view of at least `nbytes` bytes of page-locked host memory (one buffer per slot name)"""
+    lib = require_cuda()
+    cur = _PINNED.get(slot)
+    if cur is None or cur[1] < nbytes:
+        if cur is not None:
+            lib.ambc_host_free(C.c_void_p(cur[0]))
+            _PINNED.pop(slot)
+        cap = max(int(nbytes), 1 << 20)
+        cap += cap >> 3
+        ptr = lib.ambc_host_alloc(cap)
+        if not ptr:
+            raise L.AmbcError(L.E_CUDA, lib.ambc_last_error().decode("utf-8", "replace"))
+        _PINNED[slot] = cur = (int(ptr), cap)
+    return np.ctypeslib.as_array((C.c_uint8 * cur[1]).from_address(cur[0]))
+
+
+def compress_host(h_in, n, chunk, mask=L.NATIVE_MASK, flags=0, marker=FIXED_MARKER):
+    """host buffer -> (body view in the pinned 'body' slot, CompressResult, types u8[], comp_lens u32[]) through
+    ambc_compress_host (piece-wise upload overlapping the chunk kernels, body downloaded piece by piece)"""
+    lib = require_cuda()
+    bound = int(lib.ambc_compress_bound(n, chunk, len(marker)))
+    n_chunks = (n + chunk - 1) // chunk
+    body = pinned("body", bound)
+    types = np.empty(max(n_chunks, 1), dtype=np.uint8)
+    comps = np.empty(max(n_chunks, 1), dtype=np.uint32)
+    res = L.CompressResult()
+    L.check(lib.ambc_compress_host(C.c_void_p(h_in.ctypes.data if n else 0), n, chunk, mask, flags, marker, len(marker),
+                                   C.c_void_p(body.ctypes.data), bound, C.c_void_p(types.ctypes.data),
+                                   C.c_void_p(comps.ctypes.data), C.byref(res)))
+    return body[:res.body_len], res, types[:n_chunks], comps[:n_chunks]
+
+
+def decompress_host(h_body, orig_size, marker=FIXED_MARKER, known_mask=L.NATIVE_MASK):
+    """host body -> (output view in the pinned 'out' slot, status) through ambc_decompress_host"""
+    lib = require_cuda()
+    out = pinned("out", max(int(orig_size), 1))
+    st = (C.c_uint32 * 2)()
+    L.check(lib.ambc_decompress_host(C.c_void_p(h_body.ctypes.data if h_body.size else 0), int(h_body.size), marker,
+                                     len(marker), known_mask, C.c_void_p(out.ctypes.data), int(orig_size), st))
+    return out[:orig_size], [int(st[0]), int(st[1])]

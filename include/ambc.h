@@ -273,6 +273,23 @@ typedef struct { uint64_t offset; uint32_t state; uint32_t reserved; } ambc_shar
 int ambc_shard_place(const ambc_shard_rec *recs, uint32_t n_ranks, const uint64_t *first_byte, uint32_t chunk,
                      uint32_t marker_bytes, ambc_shard_slot *out);
 
+/* ---- threading ----------------------------------------------------------------------------------------
+ * The *_host calls serialise on a library mutex.  The *_dev calls keep per-DEVICE scratch (side stream and
+ * events of the decoders, index scratch, kernel timers): call them from ONE host thread per device at a
+ * time (different devices may be driven concurrently, one thread each). */
+
+/* ---- test and experiment hooks (exported, not part of the reference-facing surface) -------------------
+ * ambc_set_lz_levels / ambc_set_lz_coop_threshold / ambc_set_lz_force_buckets steer the round-1 bucket search
+ * (kept behind AMBC_SELECT=old and for the plug-in codec kernels); ambc_set_walk_threads lets small bodies
+ * exercise the helper threads of ambc_index_host (min_bytes = body size from which helpers start, threads =
+ * 0 for the host cores divided by LOCAL_WORLD_SIZE, at most 8); ambc_scan_state_bytes = size of the per-piece
+ * state record ambc_compress_host downloads.  None of them changes any result. */
+int ambc_set_lz_levels(const int *levels, int n);
+int ambc_set_lz_coop_threshold(int t);
+int ambc_set_lz_force_buckets(int on);
+void ambc_set_walk_threads(uint64_t min_bytes, unsigned threads);
+uint64_t ambc_scan_state_bytes(void);
+
 /* pinned host memory helpers for callers without their own allocator */
 void *ambc_host_alloc(uint64_t bytes);
 void ambc_host_free(void *p);

@@ -29,33 +29,57 @@ def parse_methods(text):
     return ids
 
 
-def _append_history(input_path, stats):
-    """same record the reference appends (main.py:184-194, compression_analyzer.py:30-72), json only"""
-    results_dir = "compression_results"
+def _format_file_size(size_bytes):
+    """compression_analyzer.py:857-876"""
+    if size_bytes == 0:
+        return "0 B"
+    names = ["B", "KB", "MB", "GB", "TB"]
+    i = 0
+    while size_bytes >= 1024 and i < len(names) - 1:
+        size_bytes /= 1024.0
+        i += 1
+    return f"{size_bytes:.1f} {names[i]}"
+
+
+def _append_history(input_path, stats, results_dir="compression_results"):
+    """the record the reference appends (main.py:184-194 -> CompressionAnalyzer.load_results / add_result /
+    save_results, compression_analyzer.py:30-72, 74-138), json only: the history is loaded keeping the most
+    recent record per file name (in first-occurrence order), a record with the same file name is replaced in
+    place, a new one is appended"""
     os.makedirs(results_dir, exist_ok=True)
     path = os.path.join(results_dir, "compression_history.json")
     results = []
     if os.path.exists(path):
         try:
             with open(path) as f:
-                results = json.load(f)
-        except Exception as e:  # noqa: BLE001
+                loaded = json.load(f)
+            latest = {}
+            for r in loaded:  # (:95-101)
+                name = r.get("filename", "unknown")
+                if name not in latest or r.get("timestamp", 0) > latest[name].get("timestamp", 0):
+                    latest[name] = r
+            results = list(latest.values())
+        except Exception as e:  # noqa: BLE001 (main.py:189-192)
             print(f"Error loading results: {e}")
     base = os.path.basename(input_path)
     rec = dict(stats)
     rec["chunk_stats"] = dict(stats["chunk_stats"])
+    # (json.dump turns the reference's int method ids into strings as well)
     rec["chunk_stats"]["method_usage"] = {str(k): v for k, v in stats["chunk_stats"].get("method_usage", {}).items()}
-    size = float(stats.get("original_size", 0))
-    label = "%d B" % size
-    for unit in ("KB", "MB", "GB"):
-        if size >= 1024:
-            size /= 1024.0
-            label = "%.2f %s" % (size, unit)
     rec.update(filename=base, extension=os.path.splitext(base)[1].lower() or "unknown",
-               filename_no_ext=os.path.splitext(base)[0], timestamp=time.time(), size_label=label)
-    results = [r for r in results if r.get("filename") != base] + [rec]
+               filename_no_ext=os.path.splitext(base)[0], timestamp=time.time(),
+               size_label=_format_file_size(stats.get("original_size", 0)))
+    for i, r in enumerate(results):
+        if r.get("filename") == base:
+            if rec["timestamp"] > r.get("timestamp", 0):
+                print(f"Replacing previous result for '{base}'")
+                results[i] = rec
+            break
+    else:
+        results.append(rec)
     with open(path, "w") as f:
         json.dump(results, f, indent=2)
+    return path
 
 
 def compress_file(args):
@@ -122,9 +146,10 @@ def main(argv=None):
     c = sub.add_parser("compress", help="Compress a file")
     c.add_argument("input")
     c.add_argument("output")
-    c.add_argument("--chunk-size", type=parse_chunk_size, default=4096,
-                   help="Size of data chunks in bytes (default: 4096); 'dynamic' = the reference's candidate list "
-                        "131072..1024 (adaptive_compressor.py:61-62), or a comma-separated candidate list")
+    c.add_argument("--chunk-size", type=parse_chunk_size, default="dynamic",
+                   help="'dynamic' (default) = the reference's candidate list 131072..1024 (adaptive_compressor.py:61-62: "
+                        "what the reference's own CLI always does); N = one chunk size, the fast fixed grid (4096 in the "
+                        "benchmarked configurations); or a comma-separated candidate list")
     c.add_argument("--methods", default=None, help="Comma-separated list of compression methods to use")
     c.add_argument("--disable-methods", default=None, help="Comma-separated list of compression methods to disable")
     c.add_argument("--show-progress", action="store_true", help="accepted for compatibility; the GPU path has no per-chunk progress")

@@ -236,3 +236,41 @@ def test_shard_place_c_abi_matches_python_fold():
             else:
                 packed_total = sum(nb for nb, _ in recs[:next(i for i, (_, fr) in enumerate(recs) if fr >= 0) + 1])
                 assert off == packed_total + 18 + (first_chunks[k] * chunk - g * chunk)
+
+
+def test_history_record_matches_the_analyzer_schema(tmp_path, golden):
+    """main.py appends the record the reference's analyzer writes (main.py:184-194,
+    compression_analyzer.py:30-72): same keys, same size labels, replace-by-filename in place.  The schema and the
+    (size, label) pairs come from the reference's own compression_results/compression_history.json."""
+    import json
+    import main as M
+    fx = golden["history_schema"]
+    for size, label in fx["size_labels"]:
+        assert M._format_file_size(size) == label
+    assert M._format_file_size(0) == "0 B" and M._format_file_size(512) == "512.0 B"
+    stats = {"original_size": 40044, "compressed_size": 30000, "ratio": 0.7492, "percent_reduction": 25.08,
+             "elapsed_time": 0.01, "throughput_mb_per_sec": 3.8, "overhead_bytes": 52, "compression_efficiency": 0.9,
+             "chunk_stats": {"total_chunks": 3, "compressed_chunks": 2, "raw_chunks": 1, "method_usage": {1: 0, 2: 1, 3: 1, 4: 0, 255: 0},
+                             "bytes_saved": 10000, "original_size": 40044, "compressed_size_without_overhead": 29948,
+                             "overhead_bytes": 52}}
+    d = str(tmp_path / "compression_results")
+    path = M._append_history("/some/dir/a.log", stats, d)
+    M._append_history("/x/b.bin", stats, d)
+    recs = json.load(open(path))
+    assert [r["filename"] for r in recs] == ["a.log", "b.bin"]
+    assert sorted(recs[0].keys()) == fx["record_keys"]
+    assert sorted(recs[0]["chunk_stats"].keys()) == fx["chunk_stats_keys"]
+    assert all(isinstance(k, str) for k in recs[0]["chunk_stats"]["method_usage"])
+    assert recs[0]["extension"] == ".log" and recs[0]["filename_no_ext"] == "a" and recs[0]["size_label"] == "39.1 KB"
+    # the same file again: replaced in place (index 0), not appended
+    stats2 = dict(stats, compressed_size=111)
+    M._append_history("/other/a.log", stats2, d)
+    recs = json.load(open(path))
+    assert [r["filename"] for r in recs] == ["a.log", "b.bin"] and recs[0]["compressed_size"] == 111
+    # a history with duplicates (older files of the reference have them) is reduced to the latest record per name
+    dup = recs + [dict(recs[1], timestamp=recs[1]["timestamp"] - 100, compressed_size=5)]
+    json.dump(dup, open(path, "w"))
+    M._append_history("/x/c", stats, d)
+    recs = json.load(open(path))
+    assert [r["filename"] for r in recs] == ["a.log", "b.bin", "c"] and recs[1]["compressed_size"] == 30000
+    assert recs[2]["extension"] == "unknown"
