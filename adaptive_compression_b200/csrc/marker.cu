@@ -4,7 +4,11 @@
 //
 //   k_marker_flags   presence of every L-bit window.  L <= 16: per-CTA bitmap in shared memory
 //                    (test-before-set shared atomics over coalesced 16-byte loads), flushed to
-//                    byte flags in global memory; L > 16: byte flags in global memory (L2).
+//                    byte flags in global memory; L > 16: byte flags in global memory (L2), behind a per-CTA
+//                    direct-mapped table of the values this CTA looked up last (48 KB of shared memory): a
+//                    window value found there costs one shared load; anything else goes to the test-before-set
+//                    on the global flag (round 1 went there for every window: 8 L2 sectors per input byte, the
+//                    bound of that level.  Blind stores instead of test-before-set were measured slower).
 //   k_marker_level   presence at length l-1 from length l (prefix OR + the stream's last window)
 //                    and the smallest absent value per length.
 // Byte flags (not packed bits) so that shards on several GPUs merge with one NCCL
@@ -16,14 +20,18 @@
 
 __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
 
+#define MK_CACHE 12288 // entries of the per-CTA "flagged lately" table (L > 16)
 template <bool SMEM>
 __global__ void __launch_bounds__(MK_THREADS)
 k_marker_flags(const uint8_t *__restrict__ in, uint64_t n, uint32_t L, uint8_t *__restrict__ flags)
 {
-    extern __shared__ uint32_t bm[]; // SMEM: 2^L bits
+    extern __shared__ uint32_t bm[]; // SMEM: 2^L bits; else MK_CACHE values
     const uint32_t nwords = SMEM ? max(1u, (1u << L) >> 5) : 0;
     if (SMEM) {
         for (uint32_t i = threadIdx.x; i < nwords; i += MK_THREADS) bm[i] = 0;
+        __syncthreads();
+    } else {
+        for (uint32_t i = threadIdx.x; i < MK_CACHE; i += MK_THREADS) bm[i] = 0xFFFFFFFFu; // (no L-bit value, L <= 31... see below)
         __syncthreads();
     }
     const uint64_t nbits = n * 8;
@@ -60,7 +68,11 @@ k_marker_flags(const uint8_t *__restrict__ in, uint64_t n, uint32_t L, uint8_t *
                         uint32_t bit = 1u << (v & 31);
                         if (!(bm[v >> 5] & bit)) atomicOr(&bm[v >> 5], bit);
                     } else {
-                        if (!flags[v]) flags[v] = 1;
+                        // (racy on purpose: a lost update of the table only costs a redundant global store;
+                        // for L == 32 the value 0xFFFFFFFF is never "found" in a fresh table either way, it is stored)
+                        const uint32_t slot = (v * 2654435761u) >> 18; // 14 bits
+                        const uint32_t sl = slot < MK_CACHE ? slot : slot - MK_CACHE / 2;
+                        if (bm[sl] != v || v == 0xFFFFFFFFu) { bm[sl] = v; if (!flags[v]) flags[v] = 1; }
                     }
                 }
             }
@@ -114,7 +126,8 @@ extern "C" int ambc_marker_flags_dev(const void *in_dev, uint64_t n, uint32_t L,
         size_t smem = max<size_t>(4, ((size_t)1 << L) / 8);
         k_marker_flags<true><<<grid, MK_THREADS, smem, stream>>>((const uint8_t *)in_dev, n, L, flags_dev);
     } else {
-        k_marker_flags<false><<<grid, MK_THREADS, 0, stream>>>((const uint8_t *)in_dev, n, L, flags_dev);
+        cudaFuncSetAttribute(k_marker_flags<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MK_CACHE * 4);
+        k_marker_flags<false><<<grid, MK_THREADS, MK_CACHE * 4, stream>>>((const uint8_t *)in_dev, n, L, flags_dev);
     }
     ambc_count_launch();
     if (carry_bits) {
