@@ -194,7 +194,7 @@ k_select(const uint8_t *__restrict__ in, uint64_t total, uint32_t N, uint32_t ma
 
 // round-2 kernel (select_fast.cuh): 128 threads and ~38 KB of shared memory per chunk, five CTAs per SM
 template <int NMAX>
-__global__ void __launch_bounds__(SF_T, NMAX <= 4096 ? 5 : 3)
+__global__ void __launch_bounds__(SF_T, NMAX <= 4096 ? 6 : 3)
 k_select_fast(const uint8_t *__restrict__ in, uint64_t total, uint32_t N, uint32_t mask, uint32_t ovh,
               uint8_t *__restrict__ slots, uint64_t slot_stride, uint8_t *__restrict__ type,
               uint32_t *__restrict__ comp, unsigned long long *first_raw, uint64_t chunk_begin, uint64_t n_chunks)
@@ -232,7 +232,7 @@ static bool use_fast_select(uint32_t chunk)
 // span mode (multi-candidate path, see k_select_span below) with the round-2 chunk code
 struct ChunkSpan;
 template <int NMAX>
-__global__ void __launch_bounds__(SF_T, NMAX <= 4096 ? 5 : 3)
+__global__ void __launch_bounds__(SF_T, NMAX <= 4096 ? 6 : 3)
 k_select_span_fast(const uint8_t *__restrict__ in, uint64_t total, uint32_t N, uint32_t mask, uint32_t ovh, uint32_t stride,
                    const unsigned long long *__restrict__ list, uint8_t *__restrict__ slots, uint8_t *__restrict__ type,
                    uint32_t *__restrict__ comp, uint64_t n_items)

@@ -62,16 +62,20 @@ template <int NMAX> struct SfCfg {
     static constexpr int NB = 1 << HB;                        // buckets
     static constexpr int NWORDS = NMAX / 32;                  // bitmap words
     static constexpr int A_BYTES = NB * 8;                    // region A: counters | trigram set | Huffman scratch | mlen + mpos
-    static_assert(A_BYTES >= NMAX * 3 + NB * 2, "mlen + mpos + fo16 overlay region A");
+    // region A during the parse: mm16 (packed match per position) | five bitmaps + lenhi | ... | fo16 at the end
+    static_assert(A_BYTES >= NMAX * 2 + 6 * NWORDS * 4 + NB * 2, "match table + bitmaps + fo16 overlay region A");
     static constexpr int OFF_SD = 0;
     static constexpr int OFF_A = OFF_SD + NMAX + SF_PAD;
     static constexpr int OFF_ORD = OFF_A + A_BYTES;           // ord (u16 per position) | payload buffer
     static constexpr int OFF_BSTART = OFF_ORD + NMAX * 2;
     static constexpr int OFF_BITS = OFF_BSTART + (((NB + 1) * 2 + 15) & ~15);
-    static constexpr int OFF_HIST = OFF_BITS + 6 * NWORDS * 4;
+    static constexpr int OFF_HIST = OFF_BITS + NWORDS * 4; // (only the run-boundary bitmap lives outside region A)
     static constexpr int OFF_HCODE = OFF_HIST + 1024;
     static constexpr int OFF_MISC = OFF_HCODE + 1280;
-    static constexpr int SMEM = OFF_MISC + 128 + 16 * SF_NG + ((SF_W * SF_WSW * 4 + 15) & ~15);
+    #ifndef SF_EXTRA_SMEM
+#define SF_EXTRA_SMEM 0 // dev knob: pad the CTA's shared memory to lower the occupancy (latency-sensitivity experiments)
+#endif
+    static constexpr int SMEM = OFF_MISC + 128 + 16 * SF_NG + ((SF_W * SF_WSW * 4 + 15) & ~15) + SF_EXTRA_SMEM;
 };
 
 template <int NMAX> struct SfCtx {
@@ -80,7 +84,8 @@ template <int NMAX> struct SfCtx {
     uint16_t *ord;       // bucket-sorted positions
     uint8_t *pay;        // winner's payload (overlays ord)
     uint16_t *bstart;    // NB + 1 bucket starts
-    uint32_t *bmask, *has3, *eval, *vis, *vis2, *ism; // bitmaps, NWORDS words each
+    uint32_t *bmask;     // run-boundary bitmap, NWORDS words
+    uint32_t *has3, *eval, *vis, *vis2, *ism, *lenhi; // bitmaps of the Dictionary trial, NWORDS words each, inside region A
     uint32_t *hist;      // 256 byte counts
     uint32_t *hcode;     // [256] Huffman code by symbol
     uint8_t *hlen;       // [256] Huffman code length by symbol
@@ -90,9 +95,15 @@ template <int NMAX> struct SfCtx {
     uint32_t sdb, ordb, bstb; // 32-bit shared-window addresses of sd / ord / bstart (ld.shared with 32-bit address math)
     int n;
     // views of region A
-    __device__ __forceinline__ uint8_t *mlen() const { return A; }
-    __device__ __forceinline__ uint16_t *mpos() const { return (uint16_t *)(A + NMAX); }
-    __device__ __forceinline__ uint16_t *fo16() const { return (uint16_t *)(A + 3 * NMAX); } // NB entries
+    // match of an evaluated position: (distance - 1) | (length - 3) & 15 << 12, bit 4 of length - 3 in lenhi
+    __device__ __forceinline__ uint16_t *mm16() const { return (uint16_t *)A; }
+    __device__ __forceinline__ uint16_t *fo16() const { return (uint16_t *)(A + SfCfg<NMAX>::A_BYTES - 2 * SfCfg<NMAX>::NB); } // NB entries
+    __device__ __forceinline__ int match_len(int p) const
+    {
+        const uint32_t bit = 1u << (p & 31);
+        if (!(ism[p >> 5] & bit)) return 0;
+        return 3 + (int)(mm16()[p] >> 12) + ((lenhi[p >> 5] & bit) ? 16 : 0);
+    }
 };
 
 template <int NMAX> __device__ __forceinline__ void sf_carve(SfCtx<NMAX> &c, uint8_t *base)
@@ -103,9 +114,10 @@ template <int NMAX> __device__ __forceinline__ void sf_carve(SfCtx<NMAX> &c, uin
     c.ord = (uint16_t *)(base + C::OFF_ORD);
     c.pay = base + C::OFF_ORD;
     c.bstart = (uint16_t *)(base + C::OFF_BSTART);
-    uint32_t *b = (uint32_t *)(base + C::OFF_BITS);
-    c.bmask = b; c.has3 = b + C::NWORDS; c.eval = b + 2 * C::NWORDS; c.vis = b + 3 * C::NWORDS;
-    c.vis2 = b + 4 * C::NWORDS; c.ism = b + 5 * C::NWORDS;
+    c.bmask = (uint32_t *)(base + C::OFF_BITS);
+    uint32_t *b = (uint32_t *)(c.A + 2 * NMAX);
+    c.has3 = b; c.eval = b + C::NWORDS; c.vis = b + 2 * C::NWORDS; c.vis2 = b + 3 * C::NWORDS;
+    c.ism = b + 4 * C::NWORDS; c.lenhi = b + 5 * C::NWORDS;
     c.hist = (uint32_t *)(base + C::OFF_HIST);
     c.hcode = (uint32_t *)(base + C::OFF_HCODE);
     c.hlen = base + C::OFF_HCODE + 1024;
@@ -183,8 +195,6 @@ template <int NMAX> __device__ inline void sf_load(SfCtx<NMAX> &c, const uint8_t
     }
     const int padend = ((n + 15) & ~15) + SF_PAD;
     for (int i = n + tid; i < padend; i += SF_T) c.sd[i] = 0;
-    // all six bitmaps start empty
-    for (int i = tid; i < 6 * SfCfg<NMAX>::NWORDS; i += SF_T) c.bmask[i] = 0;
     __syncthreads();
 }
 
@@ -739,7 +749,9 @@ template <int NMAX> __device__ inline void sf_lz_index(SfCtx<NMAX> &c)
     // first position per trigram hash (the counters are dead now): fo32 in A, then a u16 copy behind mlen / mpos
     // for the parse (c.fo16) and the literal filter has3
     uint32_t *fo = (uint32_t *)c.A;
+    static_assert(C::NB * 4 <= 2 * NMAX, "fo32 must end before the bitmaps");
     for (int i = tid; i < C::NB / 4; i += SF_T) ((uint4 *)fo)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    for (int i = tid; i < 6 * C::NWORDS; i += SF_T) c.has3[i] = 0; // has3 | eval | vis | vis2 | ism | lenhi
     __syncthreads();
     for (int blk = w; blk < nblk; blk += SF_W) {
         const int p = 32 * blk + lane;
@@ -772,7 +784,7 @@ template <int NMAX> __device__ __forceinline__ uint32_t sf_evaluate(const SfCtx<
     const int n = c.n, lane = threadIdx.x & 31;
     const int sub = lane & (SF_G - 1), g = lane / SF_G;
     uint32_t *ws = c.wsc + (threadIdx.x >> 5) * SF_WSW; // rec[NO][8] | best[NO] | first3[NO] | prefix[NO + 1]
-    uint32_t *wbest = ws + 8 * NO, *wf3 = wbest + NO, *wpre = wf3 + NO;
+    uint32_t *wbest = ws + 8 * NO, *wf3 = wbest + NO;
     const uint32_t pa = c.sdb + (need ? p : 0);
     const uint32_t wp0 = sf_ldsu(pa);
     const int cap = min(32, n - p);
@@ -790,10 +802,13 @@ template <int NMAX> __device__ __forceinline__ uint32_t sf_evaluate(const SfCtx<
         cA = lo - i0;
     }
     int M;
-    {   // prefix of the owners' item counts (lane SF_G * o holds owner o's count)
+    int pre[NO]; // exclusive prefix of the owners' item counts, in registers (it was 7 shared loads per item)
+    {   // (lane SF_G * o holds owner o's count)
         int v = sub == 0 ? cA : 0;
         const int inc = warp_incl_scan(v);
         M = __shfl_sync(FULL_MASK, inc, 31);
+#pragma unroll
+        for (int t = 0; t < NO; t++) pre[t] = __shfl_sync(FULL_MASK, inc - v, t * SF_G);
         if (sub == 0) {
             ws[8 * g + 0] = (uint32_t)p;
             ws[8 * g + 1] = (uint32_t)i0;
@@ -801,18 +816,16 @@ template <int NMAX> __device__ __forceinline__ uint32_t sf_evaluate(const SfCtx<
             ws[8 * g + 3] = (uint32_t)cap | (SfOrd<NMAX>::fp(wp0 >> 24) << 8);
             wbest[g] = 0;
             wf3[g] = 0xFFFFu;
-            wpre[g] = (uint32_t)(inc - v);
             if (need) SF_COUNT(30, 1);
         }
-        if (lane == 0) wpre[NO] = (uint32_t)M;
     }
     __syncwarp();
     for (int base = 0; base < M; base += 32) {
         const int j = base + lane;
-        int o = 0;
+        int o = 0, pb = 0;
 #pragma unroll
-        for (int t = 1; t < NO; t++) o += (j >= (int)wpre[t]);
-        const int k = j - (int)wpre[o];
+        for (int t = 1; t < NO; t++) { const bool ge = j >= pre[t]; o += ge; pb = ge ? pre[t] : pb; }
+        const int k = j - pb;
         __syncwarp();
         const uint32_t cur = wbest[o]; // best of the steps before this one
         __syncwarp();
@@ -875,16 +888,18 @@ template <int NMAX> __device__ __forceinline__ uint32_t sf_evaluate(const SfCtx<
         const int v = sub == 0 ? cB : 0;
         const int inc = warp_incl_scan(v);
         const int MB = __shfl_sync(FULL_MASK, inc, 31);
-        if (sub == 0) { ws[8 * g + 4] = (uint32_t)j0; wpre[g] = (uint32_t)(inc - v); }
+#pragma unroll
+        for (int t = 0; t < NO; t++) pre[t] = __shfl_sync(FULL_MASK, inc - v, t * SF_G);
+        if (sub == 0) ws[8 * g + 4] = (uint32_t)j0;
         __syncwarp();
         for (int base = 0; base < MB; base += 32) {
             const int j = base + lane;
             if (lane == 0) SF_COUNT(39, 1);
             if (j < MB) {
-                int o = 0;
+                int o = 0, pb = 0;
 #pragma unroll
-                for (int t = 1; t < NO; t++) o += (j >= (int)wpre[t]);
-                const int k = j - (int)wpre[o];
+                for (int t = 1; t < NO; t++) { const bool ge = j >= pre[t]; o += ge; pb = ge ? pre[t] : pb; }
+                const int k = j - pb;
                 const int po = (int)ws[8 * o + 0];
                 const int q = (int)(sf_lds16(c.ordb + 2 * ((int)ws[8 * o + 4] + k)) & SfOrd<NMAX>::POSMASK);
                 bool cand = q < po;
@@ -914,8 +929,7 @@ __device__ __forceinline__ int sf_chains(SfCtx<NMAX> &c, int p, int s1, bool act
     const int lane = threadIdx.x & 31;
     const int sub = lane & (SF_G - 1);
     uint32_t *mark = FIX ? c.vis2 : c.vis;
-    uint8_t *mlen = c.mlen();
-    uint16_t *mpos = c.mpos();
+    uint16_t *mm16 = c.mm16();
     int result = p;
     act = act && p < s1;
     while (__any_sync(FULL_MASK, act)) {
@@ -966,7 +980,7 @@ __device__ __forceinline__ int sf_chains(SfCtx<NMAX> &c, int p, int s1, bool act
         bool need = false;
         if (act) {
             if (FIX && (c.vis[wd] & bit)) { result = -1 - p; act = false; }
-            else if (c.eval[wd] & bit) L = mlen[p];
+            else if (c.eval[wd] & bit) L = c.match_len(p);
             else need = true;
         }
         if (__any_sync(FULL_MASK, need)) {
@@ -974,10 +988,13 @@ __device__ __forceinline__ int sf_chains(SfCtx<NMAX> &c, int p, int s1, bool act
             if (need) {
                 L = (int)(best >> 16);
                 if (sub == 0) {
-                    mlen[p] = (uint8_t)L;
-                    mpos[p] = (uint16_t)(0xFFFF - (best & 0xFFFFu));
                     c.eval[wd] |= bit;
-                    if (L >= 3) c.ism[wd] |= bit;
+                    if (L >= 3) {
+                        const int q = (int)(0xFFFFu - (best & 0xFFFFu));
+                        mm16[p] = (uint16_t)((uint32_t)(p - q - 1) | ((uint32_t)((L - 3) & 15) << 12));
+                        c.ism[wd] |= bit;
+                        if (L >= 19) c.lenhi[wd] |= bit;
+                    }
                 }
             }
         }
@@ -1094,8 +1111,7 @@ template <int NMAX> __device__ inline void sf_lz_emit(SfCtx<NMAX> &c)
     int total;
     int off = sf_block_excl_scan(bytes, c.red, &total);
     uint16_t *pay16 = (uint16_t *)c.pay; // token offsets are even
-    const uint8_t *mlen = c.mlen();
-    const uint16_t *mpos = c.mpos();
+    const uint16_t *mm16 = c.mm16();
     for (int wd = tid * wpt; wd < min(nw, (tid + 1) * wpt); wd++) {
         uint32_t reach = c.vis2[wd];
         const uint32_t mm = c.ism[wd];
@@ -1105,9 +1121,11 @@ template <int NMAX> __device__ inline void sf_lz_emit(SfCtx<NMAX> &c)
             const int p = 32 * wd + bit;
             if ((mm >> bit) & 1u) {
                 if (off + 4 <= NMAX) {
-                    const int d = p - (int)mpos[p];
+                    const uint32_t v = mm16[p];
+                    const int d = (int)(v & 0xFFFu) + 1;
+                    const int L = 3 + (int)(v >> 12) + (((c.lenhi[wd] >> bit) & 1u) ? 16 : 0);
                     pay16[off >> 1] = (uint16_t)(1u | ((uint32_t)(d & 0xFF) << 8));
-                    pay16[(off >> 1) + 1] = (uint16_t)((uint32_t)(d >> 8) | ((uint32_t)mlen[p] << 8));
+                    pay16[(off >> 1) + 1] = (uint16_t)((uint32_t)(d >> 8) | ((uint32_t)L << 8));
                 }
                 off += 4;
             } else {

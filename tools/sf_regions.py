@@ -15,10 +15,14 @@ for r in rows:
         d[0] += int(r[4] or 0); d[1] += int(float(r[idx['Instructions Executed']] or 0)); d[2] += int(float(r[idx['Thread Instructions Executed']] or 0))
     except Exception: pass
 # function starts from the embedded source
+# function starts from the source file itself (the report only lists lines that carry instructions)
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 starts = []
-for ln in sorted(src):
-    m = re.search(r'\b(sf_[a-z_0-9]+)\s*\(', src[ln])
-    if m and ('__device__' in src[ln] or 'template' in src.get(ln - 1, '') and '__device__' in src[ln]): starts.append((ln, m.group(1)))
+for i, line in enumerate(open(os.path.join(root, 'adaptive_compression_b200/csrc/select_fast.cuh')), 1):
+    m = re.match(r'^(?:template <[^>]*>\s*)?(?:__host__ )?__device__ .*?\b(sf_[a-z_0-9]+)\s*\(', line)
+    if m: starts.append((i, m.group(1)))
+    m2 = re.match(r'^__device__ .*?\b(sf_[a-z_0-9]+)\s*\(', line)
+    if m2 and (not starts or starts[-1][0] != i): starts.append((i, m2.group(1)))
 starts.append((10 ** 9, 'end'))
 agg = {}
 for ln, (s, i, t) in lines.items():
