@@ -842,9 +842,100 @@ extern "C" int ambc_phase_read(unsigned long long *out32, int reset)
 // serial walk over <= n / g table entries), and the chosen chunks are encoded and framed in span mode.
 static uint64_t gcd64(uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; }
 
+// ---- the chain of the multi-candidate mode on the GPU ---------------------------------------------------------
+// The reference walks the file once: at every position it tries every candidate size and moves on by the winner's
+// size (adaptive_compressor.py:363-394, 537-590).  Only the positions on that chain matter, about one in six of
+// the multiples of g -- round 1 tried every size at EVERY multiple of g and walked the tables on the host.  Here
+// the file is cut into segments of DYN_SEGU * g bytes; one CTA walks the chain of a segment from its first byte,
+// evaluating the candidates at the positions it actually visits (speculative: the true chain may enter the segment
+// elsewhere).  Chains that enter a segment at different positions meet after a few packages (the winner at a
+// position is a function of the position), so the host stitches the true chain from the speculative ones and
+// re-enters (a second launch, same kernel) only the segments whose true entry differs, each until it meets the
+// segment's speculative chain.
+#define DYN_SEGU 64
+struct WalkRec { unsigned long long pos; uint32_t size; uint32_t type_len; };   // type << 24 | payload length
+struct WalkSeg { unsigned long long exit; unsigned long long stop; uint32_t count; uint32_t merged; uint32_t pad[2]; };
+struct WalkCands { uint32_t n; uint32_t c[32]; };
+__global__ void __launch_bounds__(SF_T, 3)
+k_dynamic_walk(const uint8_t *__restrict__ in, uint64_t total, WalkCands cands, uint32_t mask, uint32_t ovh, uint32_t pcr,
+               uint32_t g, const unsigned long long *__restrict__ list, uint64_t n_items,
+               const WalkRec *__restrict__ spec_recs, const WalkSeg *__restrict__ spec_segs,
+               WalkRec *__restrict__ recs, WalkSeg *__restrict__ segs)
+{
+    // list == nullptr: item i = segment i entered at its first byte; else item i = (segment, entry position) and the
+    // walk stops where it meets the segment's speculative chain (spec_recs / spec_segs)
+    extern __shared__ uint4 smem4[];
+    SfCtx<8192> c;
+    sf_carve<8192>(c, (uint8_t *)smem4);
+    __shared__ uint32_t visited[DYN_SEGU / 32];
+    const uint64_t seglen = (uint64_t)DYN_SEGU * g;
+    for (uint64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const uint64_t sg = list ? list[2 * it] : it;
+        const uint64_t s0 = sg * seglen, s1 = min(total, s0 + seglen);
+        uint64_t pos = list ? list[2 * it + 1] : s0;
+        if (list) { // positions the speculative chain of this segment visits
+            if (threadIdx.x < DYN_SEGU / 32) visited[threadIdx.x] = 0;
+            __syncthreads();
+            const uint32_t cnt = spec_segs[sg].count;
+            for (uint32_t k = threadIdx.x; k < cnt; k += SF_T) {
+                const uint32_t u = (uint32_t)((spec_recs[sg * DYN_SEGU + k].pos - s0) / g);
+                atomicOr(&visited[u >> 5], 1u << (u & 31));
+            }
+            __syncthreads();
+        }
+        uint32_t count = 0, merged = 0;
+        unsigned long long stop = ~0ull;
+        while (pos < s1) {
+            if (list) {
+                const uint32_t u = (uint32_t)((pos - s0) / g);
+                if ((visited[u >> 5] >> (u & 31)) & 1u) { merged = 1; break; }
+            }
+            const uint64_t remain = total - pos;
+            // (adaptive_compressor.py:548-584) every candidate, clamped to the rest of the file, in list order; the
+            // smallest (len + overhead) / size wins as a double, the first of equals stays
+            double best_ratio = 1.0;
+            uint32_t best_c = 0, best_t = 255, best_len = 0, last_c = 0, last_t = 255, last_len = 0;
+            for (uint32_t ci = 0; ci < cands.n; ci++) {
+                const uint32_t cs = (uint64_t)cands.c[ci] < remain ? cands.c[ci] : (uint32_t)remain;
+                if (cs > AMBC_NMAX) continue; // no native method is eligible (:114-127)
+                uint32_t t, len;
+                if (cs == last_c) { t = last_t; len = last_len; } // (clamped candidates repeat near the end of the file)
+                else {
+                    sf_load<8192>(c, in + pos, (int)cs);
+                    const SfOut o = sf_select<8192>(c, mask, (int)ovh);
+                    __syncthreads();
+                    t = (uint32_t)o.type; len = (uint32_t)o.len;
+                    last_c = cs; last_t = t; last_len = len;
+                }
+                if (t == 255) continue;
+                const double ratio = (double)((uint64_t)len + ovh) / (double)cs;
+                if (ratio < best_ratio) { best_ratio = ratio; best_c = cs; best_t = t; best_len = len; }
+            }
+            if (best_t == 255) {
+                if (!pcr) { stop = pos; break; } // rest of the file raw (:586-590)
+                best_c = (uint64_t)cands.c[cands.n - 1] < remain ? cands.c[cands.n - 1] : (uint32_t)remain; // labelled extension
+                best_len = best_c;
+            }
+            if (threadIdx.x == 0) {
+                WalkRec r;
+                r.pos = pos; r.size = best_c; r.type_len = (best_t << 24) | best_len;
+                recs[sg * DYN_SEGU + count] = r;
+            }
+            count++;
+            pos += best_c;
+        }
+        if (threadIdx.x == 0) {
+            WalkSeg w;
+            w.exit = pos; w.stop = stop; w.count = count; w.merged = merged; w.pad[0] = w.pad[1] = 0;
+            segs[list ? it : sg] = w;
+        }
+        __syncthreads();
+    }
+}
+
 struct DynLayout {
-    uint64_t slots, spans, type, comp, offs, tiles, state, trial_type, trial_len, total;
-    uint64_t n_pos, n_tiles, n_pass, g;
+    uint64_t slots, spans, type, comp, offs, tiles, state, trial_type, trial_len, walk_recs, walk_segs, walk_list, total;
+    uint64_t n_pos, n_tiles, n_pass, g, n_seg;
     uint32_t pass_size[16];
     int cand_pass[32];
 };
@@ -880,6 +971,10 @@ static int dyn_layout(uint64_t n, const uint32_t *cands, uint32_t n_cands, DynLa
     L.state = take(sizeof(ScanState));
     L.trial_type = take(L.n_pass * (L.n_pos + 16));
     L.trial_len = take(L.n_pass * (L.n_pos * 4 + 16));
+    L.n_seg = (L.n_pos + DYN_SEGU - 1) / DYN_SEGU;
+    L.walk_recs = take(2 * L.n_pos * sizeof(WalkRec) + 64);   // speculative chains | re-entered chains
+    L.walk_segs = take(2 * L.n_seg * sizeof(WalkSeg) + 64);
+    L.walk_list = take(L.n_seg * 16 + 64);
     L.total = o;
     return AMBC_OK;
 }
@@ -915,54 +1010,149 @@ extern "C" int ambc_compress_dynamic_dev(const void *in_dev, uint64_t n, const u
     uint8_t *W = (uint8_t *)work_dev;
     const bool pcr = flags & AMBC_F_PER_CHUNK_RAW;
 
-    // ---- trial passes: sizes only, every multiple of g, one pass per distinct size ----------------
-    std::vector<uint8_t> h_type(L.n_pass * L.n_pos);
-    std::vector<uint32_t> h_len(L.n_pass * L.n_pos);
     const bool native = (method_mask & AMBC_NATIVE_MASK) != 0;
-    if (n && native) {
-        for (uint64_t j = 0; j < L.n_pass; j++) {
-            const uint32_t S = L.pass_size[j];
-            size_t smem = S <= LZ2_NMAX ? chunkctx_fast_smem_bytes((int)S) : chunkctx_smem_bytes((int)S, (int)S);
-            uint8_t *tt = W + L.trial_type + j * (L.n_pos + 16);
-            uint32_t *tl = (uint32_t *)(W + L.trial_len + j * (L.n_pos * 4 + 16));
-            unsigned grid = (unsigned)min<uint64_t>(L.n_pos, 0x7fffffffull);
-            if ((rc = launch_select_span(grid, smem, stream, (const uint8_t *)in_dev, n, S, method_mask, ovh, (uint32_t)L.g,
-                                         nullptr, nullptr, tt, tl, L.n_pos))) return rc;
-            CUDA_TRY(cudaMemcpyAsync(h_type.data() + j * L.n_pos, tt, L.n_pos, cudaMemcpyDeviceToHost, stream));
-            CUDA_TRY(cudaMemcpyAsync(h_len.data() + j * L.n_pos, tl, L.n_pos * 4, cudaMemcpyDeviceToHost, stream));
-        }
-        CUDA_TRY(cudaStreamSynchronize(stream));
-    }
-
-    // ---- the chain (adaptive_compressor.py:363-394 + 537-590) -------------------------------------
     std::vector<ChunkSpan> spans;
     std::vector<uint8_t> s_type;
     std::vector<uint32_t> s_len;
-    uint64_t pos = 0, raw_from = n; // raw_from < n: one raw package [raw_from, n)
-    while (pos < n) {
-        const uint64_t remain = n - pos, i = pos / L.g;
-        double best_ratio = 1.0;
-        uint64_t best_c = remain;
-        int best_t = 255;
-        uint32_t best_len = 0;
-        for (uint32_t ci = 0; ci < n_cands && native; ci++) {
-            const uint64_t c = cands[ci] < remain ? cands[ci] : remain;
-            if (c > AMBC_NMAX) continue; // no native method is eligible (:114-127)
-            const uint64_t j = (uint64_t)L.cand_pass[ci];
-            const int t = h_type[j * L.n_pos + i];
-            if (t == 255) continue;
-            const uint32_t len = h_len[j * L.n_pos + i];
-            const double ratio = (double)((uint64_t)len + ovh) / (double)c; // (:573-574)
-            if (ratio < best_ratio) { best_ratio = ratio; best_c = c; best_t = t; best_len = len; }
+    uint64_t raw_from = n; // raw_from < n: one raw package [raw_from, n)
+    static int dyn_mode = -1; // dev knob: AMBC_DYNAMIC=trial keeps the round-1 path (every size at every multiple of g)
+    if (dyn_mode < 0) { const char *e = getenv("AMBC_DYNAMIC"); dyn_mode = (e && !strcmp(e, "trial")) ? 0 : 1; }
+    if (n && native && dyn_mode == 1) {
+        // ---- the chain, walked on the GPU segment by segment (k_dynamic_walk) ------------------------------------
+        WalkCands wc;
+        wc.n = n_cands;
+        for (uint32_t i = 0; i < n_cands; i++) wc.c[i] = cands[i];
+        const uint64_t seglen = (uint64_t)DYN_SEGU * L.g, n_seg = L.n_seg;
+        WalkRec *d_spec = (WalkRec *)(W + L.walk_recs), *d_fix = d_spec + L.n_pos;
+        WalkSeg *d_sseg = (WalkSeg *)(W + L.walk_segs), *d_fseg = d_sseg + n_seg;
+        unsigned long long *d_list = (unsigned long long *)(W + L.walk_list);
+        const size_t wsmem = SfCfg<8192>::SMEM;
+        CUDA_TRY(cudaFuncSetAttribute(k_dynamic_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+        k_dynamic_walk<<<(unsigned)min<uint64_t>(n_seg, 0x7fffffffull), SF_T, wsmem, stream>>>(
+            (const uint8_t *)in_dev, n, wc, method_mask, ovh, pcr ? 1u : 0u, (uint32_t)L.g, nullptr, n_seg, nullptr, nullptr, d_spec, d_sseg);
+        ambc_count_launch();
+        CUDA_TRY(cudaGetLastError());
+        std::vector<WalkRec> h_spec(L.n_pos), h_fix(L.n_pos);
+        std::vector<WalkSeg> h_sseg(n_seg), h_fseg(n_seg), fixseg(n_seg);
+        std::vector<uint64_t> fix_entry(n_seg, ~0ull); // entry position the stored re-entered chain of a segment belongs to
+        CUDA_TRY(cudaMemcpyAsync(h_spec.data(), d_spec, L.n_pos * sizeof(WalkRec), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(h_sseg.data(), d_sseg, n_seg * sizeof(WalkSeg), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        std::vector<unsigned long long> list;
+        for (int round = 0;; round++) {
+            // follow the true chain through the segments with what is known; collect the (segment, entry) pairs that
+            // still have to be walked (unknown ones are assumed to meet their speculative chain)
+            list.clear();
+            uint64_t e = 0;
+            for (uint64_t sg = 0; sg < n_seg && e < n; sg++) {
+                const uint64_t s0 = sg * seglen, s1 = min<uint64_t>(n, s0 + seglen);
+                if (e >= s1) continue;
+                if (e == s0) { if (h_sseg[sg].stop != ~0ull) break; e = h_sseg[sg].exit; continue; }
+                if (fix_entry[sg] == e) {
+                    const WalkSeg &f = fixseg[sg];
+                    if (f.merged) { if (h_sseg[sg].stop != ~0ull) break; e = h_sseg[sg].exit; }
+                    else { if (f.stop != ~0ull) break; e = f.exit; }
+                    continue;
+                }
+                list.push_back(sg); list.push_back(e);
+                if (h_sseg[sg].stop != ~0ull) break;
+                e = h_sseg[sg].exit;
+            }
+            if (list.empty()) break;
+            if (round > (int)n_seg + 2) return ambc_fail(AMBC_E_CUDA, "internal: the chain stitch does not settle");
+            const uint64_t ni = list.size() / 2;
+            CUDA_TRY(cudaMemcpyAsync(d_list, list.data(), list.size() * 8, cudaMemcpyHostToDevice, stream));
+            k_dynamic_walk<<<(unsigned)min<uint64_t>(ni, 0x7fffffffull), SF_T, wsmem, stream>>>(
+                (const uint8_t *)in_dev, n, wc, method_mask, ovh, pcr ? 1u : 0u, (uint32_t)L.g, d_list, ni, d_spec, d_sseg, d_fix, d_fseg);
+            ambc_count_launch();
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(h_fseg.data(), d_fseg, ni * sizeof(WalkSeg), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            // (one copy of the whole record buffer: thousands of short copies cost more than the 16 bytes per g bytes)
+            const uint64_t lo = list[0] * DYN_SEGU, hi = min<uint64_t>(L.n_pos, (list[2 * (ni - 1)] + 1) * DYN_SEGU);
+            CUDA_TRY(cudaMemcpyAsync(h_fix.data() + lo, d_fix + lo, (hi - lo) * sizeof(WalkRec), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            for (uint64_t k = 0; k < ni; k++) {
+                const uint64_t sg = list[2 * k];
+                fixseg[sg] = h_fseg[k];
+                fix_entry[sg] = list[2 * k + 1];
+            }
         }
-        if (best_t == 255) {
-            if (!pcr) { raw_from = pos; break; }                       // rest of the file raw (:586-590)
-            best_c = cands[n_cands - 1] < remain ? cands[n_cands - 1] : remain; // labelled extension
-            best_len = (uint32_t)best_c;
+        // the chain itself
+        auto push = [&](const WalkRec &r) {
+            ChunkSpan sp; sp.pos = r.pos; sp.size = r.size; sp.pad = 0;
+            spans.push_back(sp); s_type.push_back((uint8_t)(r.type_len >> 24)); s_len.push_back(r.type_len & 0xFFFFFFu);
+        };
+        uint64_t e = 0;
+        for (uint64_t sg = 0; sg < n_seg && e < n; sg++) {
+            const uint64_t s0 = sg * seglen, s1 = min<uint64_t>(n, s0 + seglen);
+            if (e >= s1) continue;
+            uint32_t from = 0; // first speculative record that belongs to the true chain
+            bool use_spec = true;
+            if (e != s0) {
+                const WalkSeg &f = fixseg[sg];
+                for (uint32_t k = 0; k < f.count; k++) push(h_fix[sg * DYN_SEGU + k]);
+                if (f.merged) {
+                    while (from < h_sseg[sg].count && h_spec[sg * DYN_SEGU + from].pos != f.exit) from++;
+                    if (from == h_sseg[sg].count) return ambc_fail(AMBC_E_CUDA, "internal: meeting point not on the speculative chain");
+                } else {
+                    use_spec = false;
+                    if (f.stop != ~0ull) { raw_from = f.stop; break; }
+                    e = f.exit;
+                }
+            }
+            if (use_spec) {
+                for (uint32_t k = from; k < h_sseg[sg].count; k++) push(h_spec[sg * DYN_SEGU + k]);
+                if (h_sseg[sg].stop != ~0ull) { raw_from = h_sseg[sg].stop; break; }
+                e = h_sseg[sg].exit;
+            }
         }
-        ChunkSpan sp; sp.pos = pos; sp.size = (uint32_t)best_c; sp.pad = 0;
-        spans.push_back(sp); s_type.push_back((uint8_t)best_t); s_len.push_back(best_len);
-        pos += best_c;
+    } else {
+        // ---- trial passes: sizes only, every multiple of g, one pass per distinct size ----------------
+        std::vector<uint8_t> h_type(L.n_pass * L.n_pos);
+        std::vector<uint32_t> h_len(L.n_pass * L.n_pos);
+        if (n && native) {
+            for (uint64_t j = 0; j < L.n_pass; j++) {
+                const uint32_t S = L.pass_size[j];
+                size_t smem = S <= LZ2_NMAX ? chunkctx_fast_smem_bytes((int)S) : chunkctx_smem_bytes((int)S, (int)S);
+                uint8_t *tt = W + L.trial_type + j * (L.n_pos + 16);
+                uint32_t *tl = (uint32_t *)(W + L.trial_len + j * (L.n_pos * 4 + 16));
+                unsigned grid = (unsigned)min<uint64_t>(L.n_pos, 0x7fffffffull);
+                if ((rc = launch_select_span(grid, smem, stream, (const uint8_t *)in_dev, n, S, method_mask, ovh, (uint32_t)L.g,
+                                             nullptr, nullptr, tt, tl, L.n_pos))) return rc;
+                CUDA_TRY(cudaMemcpyAsync(h_type.data() + j * L.n_pos, tt, L.n_pos, cudaMemcpyDeviceToHost, stream));
+                CUDA_TRY(cudaMemcpyAsync(h_len.data() + j * L.n_pos, tl, L.n_pos * 4, cudaMemcpyDeviceToHost, stream));
+            }
+            CUDA_TRY(cudaStreamSynchronize(stream));
+        }
+
+        // ---- the chain (adaptive_compressor.py:363-394 + 537-590) -------------------------------------
+        uint64_t pos = 0;
+        while (pos < n) {
+            const uint64_t remain = n - pos, i = pos / L.g;
+            double best_ratio = 1.0;
+            uint64_t best_c = remain;
+            int best_t = 255;
+            uint32_t best_len = 0;
+            for (uint32_t ci = 0; ci < n_cands && native; ci++) {
+                const uint64_t c = cands[ci] < remain ? cands[ci] : remain;
+                if (c > AMBC_NMAX) continue; // no native method is eligible (:114-127)
+                const uint64_t j = (uint64_t)L.cand_pass[ci];
+                const int t = h_type[j * L.n_pos + i];
+                if (t == 255) continue;
+                const uint32_t len = h_len[j * L.n_pos + i];
+                const double ratio = (double)((uint64_t)len + ovh) / (double)c; // (:573-574)
+                if (ratio < best_ratio) { best_ratio = ratio; best_c = c; best_t = t; best_len = len; }
+            }
+            if (best_t == 255) {
+                if (!pcr) { raw_from = pos; break; }                       // rest of the file raw (:586-590)
+                best_c = cands[n_cands - 1] < remain ? cands[n_cands - 1] : remain; // labelled extension
+                best_len = (uint32_t)best_c;
+            }
+            ChunkSpan sp; sp.pos = pos; sp.size = (uint32_t)best_c; sp.pad = 0;
+            spans.push_back(sp); s_type.push_back((uint8_t)best_t); s_len.push_back(best_len);
+            pos += best_c;
+        }
     }
     const uint64_t n_list = spans.size();
     if (n_list > L.n_pos) return ambc_fail(AMBC_E_ARG, "internal: chain longer than the position table");
