@@ -197,7 +197,8 @@ template <int NMAX>
 __global__ void __launch_bounds__(SF_T, NMAX <= 4096 ? 6 : 3)
 k_select_fast(const uint8_t *__restrict__ in, uint64_t total, uint32_t N, uint32_t mask, uint32_t ovh,
               uint8_t *__restrict__ slots, uint64_t slot_stride, uint8_t *__restrict__ type,
-              uint32_t *__restrict__ comp, unsigned long long *first_raw, uint64_t chunk_begin, uint64_t n_chunks)
+              uint32_t *__restrict__ comp, unsigned long long *first_raw, uint64_t chunk_begin, uint64_t n_chunks,
+              uint32_t strict)
 {
     extern __shared__ uint4 smem4[];
     SfCtx<NMAX> c;
@@ -205,6 +206,13 @@ k_select_fast(const uint8_t *__restrict__ in, uint64_t total, uint32_t N, uint32
     for (uint64_t i = chunk_begin + blockIdx.x; i < n_chunks; i += gridDim.x) {
         const uint64_t off = i * (uint64_t)N;
         const int n = (int)min((uint64_t)N, total - off);
+        // strict mode: a chunk behind a chunk without a winner lies inside the one raw package that ends the file
+        // (adaptive_compressor.py:586-590), whatever its own trial would say.  first_raw only ever decreases, so a
+        // value below i seen now is final enough: the scan and pack kernels ignore the map from first_raw on.
+        if (strict && *(volatile unsigned long long *)first_raw < i) {
+            if (threadIdx.x == 0) { type[i] = 255; comp[i] = (uint32_t)n; }
+            continue;
+        }
         sf_load<NMAX>(c, in + off, n);
         const SfOut o = sf_select<NMAX>(c, mask, (int)ovh);
         __syncthreads();
@@ -710,11 +718,11 @@ int ambc_compress_dev_impl(const void *in_dev, uint64_t n, uint32_t chunk, uint3
             if (use_fast_select(chunk) && chunk <= 4096)
                 k_select_fast<4096><<<gch, SF_T, SfCfg<4096>::SMEM, stream>>>((const uint8_t *)in_dev, n, chunk, method_mask, ovh,
                                                                              W + L.slots, L.slot_stride, type, comp,
-                                                                             &st->first_raw, c0, c1);
+                                                                             &st->first_raw, c0, c1, (flags & AMBC_F_PER_CHUNK_RAW) ? 0u : 1u);
             else if (use_fast_select(chunk))
                 k_select_fast<8192><<<gch, SF_T, SfCfg<8192>::SMEM, stream>>>((const uint8_t *)in_dev, n, chunk, method_mask, ovh,
                                                                              W + L.slots, L.slot_stride, type, comp,
-                                                                             &st->first_raw, c0, c1);
+                                                                             &st->first_raw, c0, c1, (flags & AMBC_F_PER_CHUNK_RAW) ? 0u : 1u);
             else
                 k_select<<<gch, AMBC_BLOCK, smem, stream>>>((const uint8_t *)in_dev, n, chunk, method_mask, ovh, W + L.slots,
                                                             L.slot_stride, type, comp, &st->first_raw, c0, c1, st->trial);

@@ -196,7 +196,7 @@ def _bits_of(window, before_bytes, want_bits):
     return (v & ((1 << have) - 1)) if have else 0, have
 
 
-def find_marker_sharded(t_shard, max_len=32, levels=(16, 24)):
+def find_marker_sharded(t_shard, max_len=32, levels=(16, 24, 32)):
     """MarkerFinder.find_marker (marker_finder.py:22-123) over a stream sharded across the ranks in rank
     order: every rank flags the L-bit windows that start in its shard (with the <= L-1 bits that precede
     it as carry), one byte-wise MAX all-reduce merges the flags (NCCL has no bitwise OR), every rank

@@ -499,6 +499,40 @@ def run_b200(args):
         dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
     te = te_t.item()
 
+    # fabric floor of the host-buffer round trip: the same bytes over PCIe (upload of the input and download of the
+    # body, then upload of the body and download of the output, both directions at once) with no kernel at all, on
+    # every rank at the same time -- what the shared host side of this box can move for N ranks
+    floor_info = None
+    if world > 1:
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+        d_a = torch.empty(n, dtype=torch.uint8, device="cuda")
+        d_b = torch.empty(body_len, dtype=torch.uint8, device="cuda")
+
+        def floor_once():
+            with torch.cuda.stream(s_up):
+                d_a.copy_(h_in, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                h_body[:body_len].copy_(d_b, non_blocking=True)
+            torch.cuda.synchronize()
+            with torch.cuda.stream(s_up):
+                d_b.copy_(h_body[:body_len], non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                h_out.copy_(d_a, non_blocking=True)
+            torch.cuda.synchronize()
+
+        floor_once()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            floor_once()
+        barrier()
+        tf = torch.tensor([(time.perf_counter() - t0) / 2], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        floor_info = {"ms_per_step": tf.item() * 1e3, "value": n * world / tf.item() / 1e9, "unit": UNIT,
+                      "note": "copies only (H2D input || D2H body, then H2D body || D2H output), all ranks at once: the "
+                              "host side of the box (one NUMA node exposed, no topology to bind to) bounds the e2e number"}
+        del d_a, d_b
+
     # sharded marker search (MarkerFinder.find_marker over the whole N-shard stream): per-shard flags,
     # one NCCL MAX all-reduce, same pick on every rank.  Not part of `value` (a separate API).
     marker_info = None
@@ -567,6 +601,9 @@ def run_b200(args):
         }
         if marker_info is not None:
             line["marker_search"] = marker_info
+        if floor_info is not None:
+            line["e2e"]["fabric_floor"] = floor_info
+            line["e2e"]["frac_of_fabric_floor"] = (total_bytes / te / 1e9) / floor_info["value"]
         if numa is not None:
             line["config"]["numa_binding"] = numa
         if world == 1 and not args.no_kinds:
