@@ -82,20 +82,39 @@ __device__ __forceinline__ double block_sum_f64(double v, volatile double *red)
     return tot;
 }
 
-// Copy `len` bytes global -> shared.  dst is 16-byte aligned shared memory.  Uses 16-byte
-// vector loads when src is 16-byte aligned, byte loads otherwise (odd chunk sizes).
+// 16 bytes starting Q words + r bits into the eight words of two consecutive aligned 16-byte loads
+template <int Q>
+__device__ __forceinline__ uint4 shift16(const uint4 lo, const uint4 hi, uint32_t r)
+{
+    const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    return make_uint4(__funnelshift_r(w[Q], w[Q + 1], r), __funnelshift_r(w[Q + 1], w[Q + 2], r),
+                      __funnelshift_r(w[Q + 2], w[Q + 3], r), __funnelshift_r(w[Q + 3], w[Q + 4], r));
+}
+
+// Copy `len` bytes global -> shared.  dst is 16-byte aligned shared memory.  16-byte loads: directly when src
+// is 16-byte aligned, else two aligned loads per 16 bytes, byte-shifted (package payloads start 18 bytes behind
+// a package start, so this is the common case for raw pieces).  Never touches a 16-byte granule that holds no
+// byte of the source range.
 template <int BS = AMBC_BLOCK>
 __device__ __forceinline__ void copy_g2s(uint8_t *dst, const uint8_t *__restrict__ src, int len)
 {
-    if ((((uintptr_t)src) & 15) == 0) {
-        int nv = len >> 4;
+    const int nv = len >> 4;
+    uint4 *d4 = (uint4 *)dst;
+    const uint32_t sh = (uint32_t)((uintptr_t)src & 15);
+    if (sh == 0) {
         const uint4 *s4 = (const uint4 *)src;
-        uint4 *d4 = (uint4 *)dst;
         for (int i = threadIdx.x; i < nv; i += BS) d4[i] = __ldg(s4 + i);
-        for (int i = (nv << 4) + threadIdx.x; i < len; i += BS) dst[i] = __ldg(src + i);
     } else {
-        for (int i = threadIdx.x; i < len; i += BS) dst[i] = __ldg(src + i);
+        const uint4 *s4 = (const uint4 *)(src - sh);
+        const uint32_t r = (sh & 3) * 8;
+        switch (sh >> 2) {
+        case 0: for (int i = threadIdx.x; i < nv; i += BS) d4[i] = shift16<0>(__ldg(s4 + i), __ldg(s4 + i + 1), r); break;
+        case 1: for (int i = threadIdx.x; i < nv; i += BS) d4[i] = shift16<1>(__ldg(s4 + i), __ldg(s4 + i + 1), r); break;
+        case 2: for (int i = threadIdx.x; i < nv; i += BS) d4[i] = shift16<2>(__ldg(s4 + i), __ldg(s4 + i + 1), r); break;
+        default: for (int i = threadIdx.x; i < nv; i += BS) d4[i] = shift16<3>(__ldg(s4 + i), __ldg(s4 + i + 1), r); break;
+        }
     }
+    for (int i = (nv << 4) + threadIdx.x; i < len; i += BS) dst[i] = __ldg(src + i);
 }
 
 // Copy `len` bytes shared (any alignment) -> global (any alignment): byte stores up to the

@@ -2,6 +2,7 @@
 // Replaces AdaptiveCompressor._adaptive_decompress (adaptive_compressor.py:396-454).
 #include "ambc_internal.h"
 #include "decode_codec.cuh"
+#include "decode_warp.cuh"
 #include <thread>
 #include <cstdlib>
 #include <vector>
@@ -289,30 +290,52 @@ __device__ int decode_package(DecCtx &d, uint32_t type, const uint8_t *__restric
 #ifndef KDEC_MINB
 #define KDEC_MINB 6
 #endif
+// The packages no warp kernel takes (raw pieces, Delta, oversized or foreign packages): one CTA per package.
+// Most bodies hold none, so a CTA first looks at AMBC_BLOCK table entries at once (one per thread) and then
+// decodes the few that are its business, in order.
 __global__ void __launch_bounds__(AMBC_BLOCK, KDEC_MINB)
 k_decode(const uint8_t *__restrict__ body, const ambc_pkg *__restrict__ table, uint64_t n_entries,
          uint8_t *__restrict__ out, int in_cap, uint32_t *status)
 {
     extern __shared__ uint4 smem4[];
+    __shared__ uint32_t s_mask[AMBC_WARPS];
     DecCtx d;
     decctx_carve(d, (uint8_t *)smem4, in_cap);
-    for (uint64_t i = blockIdx.x; i < n_entries; i += gridDim.x) {
-        const ambc_pkg e = table[i];
-        if (dlz_eligible(e)) continue; // decoded by k_decode_lz, one warp per package
-        uint8_t *dst = out + e.dst_off;
-        int produced = decode_package(d, e.type, body + e.src_off, e.comp_len, e.orig_len, dst, e.out_len);
-        // nominal length the index assumed for this package (see nominal_out)
-        uint32_t nominal = e.type == 255 ? e.orig_len
-                         : e.type == 4 ? (e.comp_len == 0 ? 0 : min(e.comp_len, e.orig_len))
-                                       : (e.comp_len == 0 ? 0 : e.orig_len);
-        if (produced < 0) { // codec raised: orig_len zero bytes (:440-442)
-            for (uint32_t k = threadIdx.x; k < e.out_len; k += AMBC_BLOCK) dst[k] = 0;
-            if (threadIdx.x == 0 && status) atomicAdd(&status[0], 1u);
-        } else if ((uint32_t)produced != nominal) {
-            // malformed stream: the reference would shift everything after it; we keep the
-            // grid and zero the gap, and report it
-            for (uint32_t k = (uint32_t)produced + threadIdx.x; k < e.out_len; k += AMBC_BLOCK) dst[k] = 0;
-            if (threadIdx.x == 0 && status) atomicAdd(&status[1], 1u);
+    // entry (blockIdx.x + k * gridDim.x) is thread k's to look at, AMBC_BLOCK entries per round
+    for (uint64_t k0 = 0; blockIdx.x + k0 * gridDim.x < n_entries; k0 += AMBC_BLOCK) {
+        const uint64_t mine = blockIdx.x + (k0 + threadIdx.x) * (uint64_t)gridDim.x;
+        bool want = false;
+        if (mine < n_entries) {
+            const ambc_pkg e = table[mine];
+            want = !dlz_eligible(e) && !dw_eligible(e, 8192);
+        }
+        const uint32_t bal = __ballot_sync(FULL_MASK, want);
+        if ((threadIdx.x & 31) == 0) s_mask[threadIdx.x >> 5] = bal;
+        __syncthreads();
+        for (int w = 0; w < AMBC_WARPS; w++) {
+            uint32_t m = s_mask[w];
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                const uint64_t i = blockIdx.x + (k0 + 32 * w + b) * (uint64_t)gridDim.x;
+                const ambc_pkg e = table[i];
+                uint8_t *dst = out + e.dst_off;
+                int produced = decode_package(d, e.type, body + e.src_off, e.comp_len, e.orig_len, dst, e.out_len);
+                // nominal length the index assumed for this package (see nominal_out)
+                uint32_t nominal = e.type == 255 ? e.orig_len
+                                 : e.type == 4 ? (e.comp_len == 0 ? 0 : min(e.comp_len, e.orig_len))
+                                               : (e.comp_len == 0 ? 0 : e.orig_len);
+                if (produced < 0) { // codec raised: orig_len zero bytes (:440-442)
+                    for (uint32_t k = threadIdx.x; k < e.out_len; k += AMBC_BLOCK) dst[k] = 0;
+                    if (threadIdx.x == 0 && status) atomicAdd(&status[0], 1u);
+                } else if ((uint32_t)produced != nominal) {
+                    // malformed stream: the reference would shift everything after it; we keep the
+                    // grid and zero the gap, and report it
+                    for (uint32_t k = (uint32_t)produced + threadIdx.x; k < e.out_len; k += AMBC_BLOCK) dst[k] = 0;
+                    if (threadIdx.x == 0 && status) atomicAdd(&status[1], 1u);
+                }
+                __syncthreads();
+            }
         }
         __syncthreads();
     }
@@ -398,7 +421,16 @@ int ambc_decode_launch(const void *body_dev, const ambc_pkg *table_dev, uint64_t
     ambc_count_launch();
     ambc_count_launch();
     CUDA_TRY(cudaEventRecord(ev_join[dev], side[dev]));
-    unsigned grid = (unsigned)min<uint64_t>(n_entries, 0x7fffffffull);
+    // Huffman and RLE packages: one warp each
+    const unsigned wgrid = (unsigned)min<uint64_t>((n_entries + DW_WARPS - 1) / DW_WARPS, 148ull * 64);
+    k_decode_warp<4096><<<wgrid, DW_WARPS * 32, DW_WARPS * DwCfg<4096>::PER_WARP, stream>>>(
+        (const uint8_t *)body_dev, table_dev, n_entries, (uint8_t *)out_dev, status_dev);
+    k_decode_warp<8192><<<wgrid, DW_WARPS * 32, DW_WARPS * DwCfg<8192>::PER_WARP, stream>>>(
+        (const uint8_t *)body_dev, table_dev, n_entries, (uint8_t *)out_dev, status_dev);
+    ambc_count_launch();
+    ambc_count_launch();
+    // everything else: one CTA each
+    unsigned grid = (unsigned)min<uint64_t>(n_entries, 148ull * KDEC_MINB);
     k_decode<<<grid, AMBC_BLOCK, smem, stream>>>((const uint8_t *)body_dev, table_dev, n_entries, (uint8_t *)out_dev,
                                                  in_cap, status_dev);
     ambc_count_launch();
@@ -430,6 +462,33 @@ extern "C" int ambc_decompress_dev(const void *body_dev, uint64_t body_len, cons
 }
 
 // ---- codec plug-in batch kernels (CompressionMethod API parity) -------------------------------
+// items the warp decoders take (the same code as the container path, so the codec-level fixtures hold it too)
+__device__ __forceinline__ bool codec_item_warp(int method, uint32_t comp, uint32_t orig)
+{
+    return (method == 1 || method == 3) && comp <= 8192u && orig <= 8192u;
+}
+
+__global__ void __launch_bounds__(DW_WARPS * 32)
+k_codec_decode_warp(int method, const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
+                    const uint32_t *__restrict__ orig_len, uint32_t n_items, uint8_t *__restrict__ out,
+                    uint64_t out_stride, int32_t *__restrict__ out_len)
+{
+    extern __shared__ uint4 smem4[];
+    const int w = threadIdx.x >> 5;
+    DwCtx d;
+    dw_carve<8192>(d, (uint8_t *)smem4 + (size_t)w * DwCfg<8192>::PER_WARP);
+    for (uint32_t i = blockIdx.x * DW_WARPS + w; i < n_items; i += gridDim.x * DW_WARPS) {
+        const uint64_t a = in_off[i], b = in_off[i + 1];
+        const uint32_t comp = (uint32_t)(b - a), orig = orig_len[i];
+        if (b - a > 8192u || !codec_item_warp(method, comp, orig)) continue;
+        const uint32_t cap = out_stride > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)out_stride;
+        const int produced = method == 3 ? dw_huff<8192>(d, in + a, (int)comp, (int)orig) : dw_rle<8192>(d, in + a, (int)comp, (int)orig);
+        if (produced > 0) dw_store(out + (uint64_t)i * out_stride, d.out, min((uint32_t)produced, cap));
+        if ((threadIdx.x & 31) == 0) out_len[i] = produced;
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(AMBC_BLOCK)
 k_codec_decode(int method, const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                const uint32_t *__restrict__ orig_len, uint32_t n_items, uint8_t *__restrict__ out,
@@ -441,6 +500,7 @@ k_codec_decode(int method, const uint8_t *__restrict__ in, const uint64_t *__res
     for (uint32_t i = blockIdx.x; i < n_items; i += gridDim.x) {
         uint64_t a = in_off[i], b = in_off[i + 1];
         uint32_t comp = (uint32_t)(b - a), orig = orig_len[i];
+        if (b - a <= 8192u && codec_item_warp(method, comp, orig)) continue; // k_codec_decode_warp
         uint32_t cap = out_stride > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)out_stride;
         int produced;
         if (method == 255) {
@@ -472,6 +532,11 @@ extern "C" int ambc_codec_decode_batch(int method, const void *in_dev, const uin
     const int in_cap = 2 * AMBC_NMAX + 2048; // any payload the encoders can emit for <= 8192 bytes
     size_t smem = decctx_smem_bytes(in_cap);
     CUDA_TRY(cudaFuncSetAttribute(k_codec_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (method == 1 || method == 3) {
+        k_codec_decode_warp<<<(n_items + DW_WARPS - 1) / DW_WARPS, DW_WARPS * 32, DW_WARPS * DwCfg<8192>::PER_WARP, stream>>>(
+            method, (const uint8_t *)in_dev, in_off_dev, orig_len_dev, n_items, (uint8_t *)out_dev, out_stride, out_len_dev);
+        ambc_count_launch();
+    }
     k_codec_decode<<<n_items, AMBC_BLOCK, smem, stream>>>(method, (const uint8_t *)in_dev, in_off_dev, orig_len_dev,
                                                           n_items, (uint8_t *)out_dev, out_stride, out_len_dev, in_cap);
     ambc_count_launch();
