@@ -421,11 +421,11 @@ int ambc_decode_launch(const void *body_dev, const ambc_pkg *table_dev, uint64_t
     ambc_count_launch();
     ambc_count_launch();
     CUDA_TRY(cudaEventRecord(ev_join[dev], side[dev]));
-    // Huffman and RLE packages: one warp each
-    const unsigned wgrid = (unsigned)min<uint64_t>((n_entries + DW_WARPS - 1) / DW_WARPS, 148ull * 64);
-    k_decode_warp<4096><<<wgrid, DW_WARPS * 32, DW_WARPS * DwCfg<4096>::PER_WARP, stream>>>(
+    // Huffman and RLE packages: 64 lanes each
+    const unsigned wgrid = (unsigned)min<uint64_t>(n_entries, 148ull * 16 * 8);
+    k_decode_warp<4096><<<wgrid, DW_T, DwCfg<4096>::PER_PKG, stream>>>(
         (const uint8_t *)body_dev, table_dev, n_entries, (uint8_t *)out_dev, status_dev);
-    k_decode_warp<8192><<<wgrid, DW_WARPS * 32, DW_WARPS * DwCfg<8192>::PER_WARP, stream>>>(
+    k_decode_warp<8192><<<wgrid, DW_T, DwCfg<8192>::PER_PKG, stream>>>(
         (const uint8_t *)body_dev, table_dev, n_entries, (uint8_t *)out_dev, status_dev);
     ambc_count_launch();
     ambc_count_launch();
@@ -468,24 +468,23 @@ __device__ __forceinline__ bool codec_item_warp(int method, uint32_t comp, uint3
     return (method == 1 || method == 3) && comp <= 8192u && orig <= 8192u;
 }
 
-__global__ void __launch_bounds__(DW_WARPS * 32)
+__global__ void __launch_bounds__(DW_T)
 k_codec_decode_warp(int method, const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                     const uint32_t *__restrict__ orig_len, uint32_t n_items, uint8_t *__restrict__ out,
                     uint64_t out_stride, int32_t *__restrict__ out_len)
 {
     extern __shared__ uint4 smem4[];
-    const int w = threadIdx.x >> 5;
     DwCtx d;
-    dw_carve<8192>(d, (uint8_t *)smem4 + (size_t)w * DwCfg<8192>::PER_WARP);
-    for (uint32_t i = blockIdx.x * DW_WARPS + w; i < n_items; i += gridDim.x * DW_WARPS) {
+    dw_carve<8192>(d, (uint8_t *)smem4);
+    for (uint32_t i = blockIdx.x; i < n_items; i += gridDim.x) {
         const uint64_t a = in_off[i], b = in_off[i + 1];
         const uint32_t comp = (uint32_t)(b - a), orig = orig_len[i];
         if (b - a > 8192u || !codec_item_warp(method, comp, orig)) continue;
         const uint32_t cap = out_stride > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)out_stride;
         const int produced = method == 3 ? dw_huff<8192>(d, in + a, (int)comp, (int)orig) : dw_rle<8192>(d, in + a, (int)comp, (int)orig);
         if (produced > 0) dw_store(out + (uint64_t)i * out_stride, d.out, min((uint32_t)produced, cap));
-        if ((threadIdx.x & 31) == 0) out_len[i] = produced;
-        __syncwarp();
+        if (threadIdx.x == 0) out_len[i] = produced;
+        __syncthreads();
     }
 }
 
@@ -533,7 +532,7 @@ extern "C" int ambc_codec_decode_batch(int method, const void *in_dev, const uin
     size_t smem = decctx_smem_bytes(in_cap);
     CUDA_TRY(cudaFuncSetAttribute(k_codec_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (method == 1 || method == 3) {
-        k_codec_decode_warp<<<(n_items + DW_WARPS - 1) / DW_WARPS, DW_WARPS * 32, DW_WARPS * DwCfg<8192>::PER_WARP, stream>>>(
+        k_codec_decode_warp<<<n_items, DW_T, DwCfg<8192>::PER_PKG, stream>>>(
             method, (const uint8_t *)in_dev, in_off_dev, orig_len_dev, n_items, (uint8_t *)out_dev, out_stride, out_len_dev);
         ambc_count_launch();
     }

@@ -1,14 +1,14 @@
-// decode_warp.cuh -- one WARP per package for the two kinds that carry most of a decode: Huffman (type 3) and
-// RLE (type 1) packages whose payload and output are at most CAP bytes (round 2; the round-1 decoders ran one
-// 256-thread CTA per package and re-decoded every Huffman bit range about four times, 18 k warp instructions per
-// 4 KiB package, ncu).
+// decode_warp.cuh -- two warps (64 lanes) per package for the two kinds that carry most of a decode: Huffman
+// (type 3) and RLE (type 1) packages whose payload and output are at most CAP bytes (round 2; the round-1 decoders
+// ran one 256-thread CTA per package and re-decoded every Huffman bit range about four times, 18 k warp
+// instructions per 4 KiB package, ncu).
 //
 // Reference behaviour restated (file:line relative to the reference repo):
 //   Huffman  compression_methods.py:407-470   (tree rebuilt from the table exactly as the encoder builds it,
 //                                              :472-500; bit walk; stops after the append that reaches orig_len)
 //   RLE      compression_methods.py:116-152   (pairs, odd tail ignored, truncate / zero pad)
 //
-// Huffman: the 32 lanes decode 32 bit ranges of the stream.  Only lane 0 knows where its first code starts, so
+// Huffman: the 64 lanes decode 64 bit ranges of the stream.  Only lane 0 knows where its first code starts, so
 //   pass 1     every lane decodes its range from the range start and remembers, at NCP checkpoints (bit boundaries
 //              inside the range), the first code start at or behind the boundary and how many symbols came before;
 //   re-sync    a lane whose predecessor ended somewhere else restarts there and decodes only until it stands on a
@@ -17,25 +17,30 @@
 //              re-synchronise within a few codes, so this costs a fraction of a pass; fixed-length codes never do,
 //              which is why ranges are made a multiple of the code length when the tree is flat;
 //   output     one more pass from the true starts writes the symbols at scanned offsets.
-// A code is decoded with one look-up in a 2^LB-entry table built per package; longer codes (rare: a symbol seen
-// once or twice in the chunk) continue bit by bit through the tree.
+// A step is one look-up in a 2^LB-entry table built per package that holds up to two codes; longer codes (rare:
+// a symbol seen once or twice in the chunk) continue bit by bit through the tree.
+// One package occupies 13.6 KB of shared memory; with one warp per package an SM held 16 warps and half of the
+// issue slots stayed empty behind the dependent look-ups of a chain (ncu: IPC 1.98), hence 64 lanes per package.
 #pragma once
 #include "common.cuh"
 
-#ifndef DW_WARPS
-#define DW_WARPS 2
-#endif
+#define DW_T 64       // lanes per package = threads per CTA
 #define DW_LB 10
-#define DW_NCP 8
+#ifndef DW_NCP
+#define DW_NCP 4
+#endif
+#ifndef DW_CASCADE
+#define DW_CASCADE 2  // re-synchronisation rounds before a code is treated as one that does not re-synchronise
+#endif
 
 template <int CAP> struct DwCfg {
     static constexpr int W_BYTES = CAP + 32;            // staged bit words (big-endian), or the RLE tables
     static constexpr int OUT_BYTES = CAP + 32;          // decoded bytes before they go to global memory
     static constexpr int LUT_BYTES = 4 << DW_LB;        // two-symbol table
     static constexpr int TREE_BYTES = 512 + 512 + 256;  // child0[256], child1[256] (u16, internal nodes), leafsym[256]
-    static constexpr int PER_WARP = W_BYTES + OUT_BYTES + LUT_BYTES + TREE_BYTES;
+    static constexpr int PER_PKG = W_BYTES + OUT_BYTES + LUT_BYTES + TREE_BYTES;
     static_assert(W_BYTES + OUT_BYTES >= 513 * 8 + 1024 + 1024 + (2 << DW_LB), "tree-build scratch overlays W + out");
-    static_assert(OUT_BYTES >= 4 * 32 * DW_NCP, "checkpoints overlay out");
+    static_assert(OUT_BYTES >= 4 * (DW_T * (DW_NCP + 1) + 2 + DW_LB * DW_T + DW_T + 1), "checkpoints, range ends and the entry table overlay out");
 };
 
 struct DwCtx {
@@ -57,33 +62,33 @@ template <int CAP> __device__ __forceinline__ void dw_carve(DwCtx &d, uint8_t *b
     d.K = 0;
 }
 
-__device__ __forceinline__ uint32_t dw_lane() { return threadIdx.x & 31; }
+__device__ __forceinline__ uint32_t dw_lane() { return threadIdx.x; } // 0 .. DW_T - 1
 
 // byte i of a payload of `len` bytes, 0 behind its end (the guards of the round-1 parser)
 __device__ __forceinline__ uint32_t dw_byte(const uint8_t *__restrict__ in, int i, int len) { return i < len ? (uint32_t)__ldg(in + i) : 0u; }
 
-// out[0 .. n) (shared, 16-byte aligned) -> dst (global, any alignment); one warp
+// out[0 .. n) (shared, 16-byte aligned) -> dst (global, any alignment); DW_T lanes
 __device__ __forceinline__ void dw_store(uint8_t *__restrict__ dst, const uint8_t *out, uint32_t n)
 {
     const uint32_t lane = dw_lane();
     uint32_t head = (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15);
     if (head > n) head = n;
-    for (uint32_t i = lane; i < head; i += 32) dst[i] = out[i];
+    for (uint32_t i = lane; i < head; i += DW_T) dst[i] = out[i];
     const uint32_t body = (n - head) >> 4;
     uint4 *d4 = (uint4 *)(dst + head);
     if (head == 0) {
         const uint4 *s4 = (const uint4 *)out;
-        for (uint32_t i = lane; i < body; i += 32) d4[i] = s4[i];
+        for (uint32_t i = lane; i < body; i += DW_T) d4[i] = s4[i];
     } else {
         const uint8_t *s = out + head;
-        for (uint32_t i = lane; i < body; i += 32) {
+        for (uint32_t i = lane; i < body; i += DW_T) {
             const uint8_t *p = s + (i << 4);
             uint4 v;
             v.x = lds_u32u(p); v.y = lds_u32u(p + 4); v.z = lds_u32u(p + 8); v.w = lds_u32u(p + 12);
             d4[i] = v;
         }
     }
-    for (uint32_t i = head + (body << 4) + lane; i < n; i += 32) dst[i] = out[i];
+    for (uint32_t i = head + (body << 4) + lane; i < n; i += DW_T) dst[i] = out[i];
 }
 
 // ---- Huffman: table -> tree -> look-up table ----------------------------------------------------------------
@@ -116,12 +121,11 @@ __device__ __forceinline__ void dw_merge(const T *keyL, T *keyM, int K, uint16_t
 }
 
 // Returns 0 or -1 where the reference raises; *boff = offset of the bit stream, *nbits = stream bits to decode,
-// *flat = the common code length when every code has the same length (else 0), *deep = some code is longer than
-// LB bits.  One warp.
+// *flat = the common code length when every code has the same length (else 0), *maxlen = the longest code.  Collective for the DW_T lanes of the package.
 template <int CAP>
-__device__ inline int dw_huff_build(DwCtx &d, const uint8_t *__restrict__ in, int len, int *boff, uint32_t *nbits, int *flat, bool *deep)
+__device__ inline int dw_huff_build(DwCtx &d, const uint8_t *__restrict__ in, int len, int *boff, uint32_t *nbits, int *flat, int *maxlen)
 {
-    const uint32_t lane = dw_lane();
+    const uint32_t tid = dw_lane(), lane = tid & 31, wid = tid >> 5;
     const int ne = (int)dw_byte(in, 0, len);
     if (ne > 0 && 1 + 5 * (ne - 1) >= len) return -1; // IndexError: a table entry's symbol byte lies past the payload (:430)
     // scratch (dead before the stream is staged)
@@ -130,37 +134,41 @@ __device__ inline int dw_huff_build(DwCtx &d, const uint8_t *__restrict__ in, in
     uint16_t *parent = (uint16_t *)(keyM + 256);                    // [512] parent | bit << 15
     uint32_t *lastidx = (uint32_t *)(parent + 512);                 // [256] 1 + last table entry of the symbol
     uint16_t *lut1 = (uint16_t *)(lastidx + 256);                   // [1 << LB] one-symbol table: 0x8000 | len << 8 | sym, else node
-    for (int b = lane; b < 256; b += 32) lastidx[b] = 0;
-    __syncwarp();
+    int *sh = (int *)d.child0;                                      // K, wmax, dmin[2], dmax[2] (child0 is written by the merge, later)
+    for (int b = tid; b < 256; b += DW_T) lastidx[b] = 0;
+    __syncthreads();
     // dict semantics: the last entry of a symbol wins (:436)
-    for (int e = lane; e < ne; e += 32) atomicMax(&lastidx[dw_byte(in, 1 + 5 * e, len)], (uint32_t)(e + 1));
-    __syncwarp();
-    // compact the present symbols: key = weight << 8 | symbol
-    int K = 0;
-    uint32_t wmax = 0;
-    for (int b0 = 0; b0 < 256; b0 += 32) {
-        const int b = b0 + (int)lane;
-        const uint32_t li = lastidx[b];
-        const uint32_t m = __ballot_sync(FULL_MASK, li != 0);
-        if (li) {
-            const int o = 2 + 5 * ((int)li - 1);
-            const uint32_t wgt = dw_byte(in, o, len) | (dw_byte(in, o + 1, len) << 8) | (dw_byte(in, o + 2, len) << 16) | (dw_byte(in, o + 3, len) << 24);
-            keyM[K + __popc(m & ((1u << lane) - 1))] = ((unsigned long long)wgt << 8) | (unsigned long long)b;
-            wmax = max(wmax, wgt);
+    for (int e = tid; e < ne; e += DW_T) atomicMax(&lastidx[dw_byte(in, 1 + 5 * e, len)], (uint32_t)(e + 1));
+    __syncthreads();
+    if (wid == 0) { // compact the present symbols: key = weight << 8 | symbol
+        int K = 0;
+        uint32_t wmax = 0;
+        for (int b0 = 0; b0 < 256; b0 += 32) {
+            const int b = b0 + (int)lane;
+            const uint32_t li = lastidx[b];
+            const uint32_t m = __ballot_sync(FULL_MASK, li != 0);
+            if (li) {
+                const int o = 2 + 5 * ((int)li - 1);
+                const uint32_t wgt = dw_byte(in, o, len) | (dw_byte(in, o + 1, len) << 8) | (dw_byte(in, o + 2, len) << 16) | (dw_byte(in, o + 3, len) << 24);
+                keyM[K + __popc(m & ((1u << lane) - 1))] = ((unsigned long long)wgt << 8) | (unsigned long long)b;
+                wmax = max(wmax, wgt);
+            }
+            K += __popc(m);
         }
-        K += __popc(m);
+        wmax = __reduce_max_sync(FULL_MASK, wmax);
+        if (lane == 0) { sh[0] = K; sh[1] = (int)(wmax < (1u << 15)); }
     }
+    __syncthreads();
+    const int K = sh[0];
+    const bool small = sh[1] != 0; // sums stay below 2^23: 32-bit keys
     d.K = K;
     if (K <= 1) return -1; // heappop on an empty heap / code[-1] of an empty code (:497, :527)
-    wmax = __reduce_max_sync(FULL_MASK, wmax);
-    const bool small = wmax < (1u << 15); // sums stay below 2^23: 32-bit keys
-    __syncwarp();
-    {   // rank sort (keys are distinct); up to 8 keys per lane
-        unsigned long long mine[8];
-        int rk[8];
+    {   // rank sort (keys are distinct); up to 4 keys per lane
+        unsigned long long mine[4];
+        int rk[4];
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const int j = (int)lane + 32 * q;
+        for (int q = 0; q < 4; q++) {
+            const int j = (int)tid + DW_T * q;
             mine[q] = ~0ull; rk[q] = 0;
             if (j < K) {
                 mine[q] = keyM[j];
@@ -169,35 +177,35 @@ __device__ inline int dw_huff_build(DwCtx &d, const uint8_t *__restrict__ in, in
                 rk[q] = r;
             }
         }
-        __syncwarp(); // every rank is known before keyM is given to the merge
+        __syncthreads(); // every rank is known before keyM is given to the merge
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const int j = (int)lane + 32 * q;
+        for (int q = 0; q < 4; q++) {
+            const int j = (int)tid + DW_T * q;
             if (j < K) {
                 if (small) ((uint32_t *)keyL)[rk[q]] = (uint32_t)mine[q]; else keyL[rk[q]] = mine[q];
                 d.leafsym[rk[q]] = (uint8_t)(mine[q] & 0xFFull);
             }
         }
         if (small) {
-            for (int j = lane; j < 256; j += 32) ((uint32_t *)keyM)[j] = 0xFFFFFFFFu;
-            if (lane == 0) ((uint32_t *)keyL)[K] = 0xFFFFFFFFu;
+            for (int j = tid; j < 256; j += DW_T) ((uint32_t *)keyM)[j] = 0xFFFFFFFFu;
+            if (tid == 0) ((uint32_t *)keyL)[K] = 0xFFFFFFFFu;
         } else {
-            for (int j = lane; j < 256; j += 32) keyM[j] = ~0ull;
-            if (lane == 0) keyL[K] = ~0ull;
+            for (int j = tid; j < 256; j += DW_T) keyM[j] = ~0ull;
+            if (tid == 0) keyL[K] = ~0ull;
         }
     }
-    __syncwarp();
-    if (lane == 0) {
+    for (int i = tid; i < (1 << DW_LB) / 2; i += DW_T) ((uint32_t *)lut1)[i] = 0;
+    __syncthreads();
+    if (tid == 0) {
         if (small) dw_merge<uint32_t>((const uint32_t *)keyL, (uint32_t *)keyM, K, parent, d.child0, d.child1);
         else dw_merge<unsigned long long>(keyL, keyM, K, parent, d.child0, d.child1);
     }
-    for (int i = lane; i < (1 << DW_LB) / 2; i += 32) ((uint32_t *)lut1)[i] = 0;
-    __syncwarp();
+    __syncthreads();
     // every node walks up to the root: depth and the root-side bits of its code.  Leaves of depth <= LB and the
     // internal nodes of depth LB mark the first table entry they own.
     const int root = 2 * K - 2;
     int dmin = 1 << 20, dmax = 0;
-    for (int n = lane; n < root; n += 32) {
+    for (int n = tid; n < root; n += DW_T) {
         uint32_t code = 0;
         int dep = 0, x = n;
         while (x != root) {
@@ -213,12 +221,17 @@ __device__ inline int dw_huff_build(DwCtx &d, const uint8_t *__restrict__ in, in
     }
     dmin = __reduce_min_sync(FULL_MASK, dmin);
     dmax = __reduce_max_sync(FULL_MASK, dmax);
+    int *shd = (int *)lastidx; // (dead)
+    if (lane == 0) { shd[wid] = dmin; shd[2 + wid] = dmax; }
+    __syncthreads();
+    dmin = min(shd[0], shd[1]);
+    dmax = max(shd[2], shd[3]);
     *flat = dmin == dmax ? dmin : 0;
-    *deep = dmax > DW_LB;
-    __syncwarp();
-    // an entry without a mark belongs to the nearest mark before it
+    *maxlen = dmax;
+    // an entry without a mark belongs to the nearest mark before it.  Each warp fills its half of the table: entry
+    // 2^(LB-1) (the code "1" followed by zeros) starts the right subtree of the root and always carries a mark.
     uint32_t carry = 0;
-    for (int r = 0; r < (1 << DW_LB); r += 32) {
+    for (int r = (int)wid << (DW_LB - 1); r < (int)(wid + 1) << (DW_LB - 1); r += 32) {
         const uint32_t e = lut1[r + lane];
         const uint32_t m = __ballot_sync(FULL_MASK, e != 0);
         const uint32_t below = m & (0xFFFFFFFFu >> (31 - lane));
@@ -227,9 +240,9 @@ __device__ inline int dw_huff_build(DwCtx &d, const uint8_t *__restrict__ in, in
         if (!e) lut1[r + lane] = (uint16_t)mine;
         carry = __shfl_sync(FULL_MASK, mine, 31);
     }
-    __syncwarp();
+    __syncthreads();
     // two-symbol table: the second code counts when it lies completely inside the LB bits
-    for (int i = lane; i < (1 << DW_LB); i += 32) {
+    for (int i = tid; i < (1 << DW_LB); i += DW_T) {
         const uint32_t e1 = lut1[i];
         uint32_t e;
         if (e1 & 0x8000u) {
@@ -247,26 +260,26 @@ __device__ inline int dw_huff_build(DwCtx &d, const uint8_t *__restrict__ in, in
     const uint32_t avail = off < len ? (uint32_t)(len - off) * 8u : 0u;
     *boff = off;
     *nbits = nb < avail ? nb : avail;
-    __syncwarp();
+    __syncthreads();
     return 0;
 }
 
 // stream bytes in[boff ..) -> W as big-endian 32-bit words (two words of slack behind the stream)
 __device__ inline void dw_stage_bits(DwCtx &d, const uint8_t *__restrict__ in, int len, int boff, uint32_t nbits)
 {
-    const uint32_t lane = dw_lane();
+    const uint32_t tid = dw_lane();
     const uint32_t nw = (nbits + 31) >> 5;
     const uintptr_t a = (uintptr_t)(in + boff);
     const uint32_t *g = (const uint32_t *)(a & ~(uintptr_t)3);
     const uint32_t sh = (uint32_t)(a & 3) * 8;
     // aligned words that hold at least one payload byte: [0, gmax)
     const uint32_t gmax = len > boff ? (uint32_t)(((a & 3) + (uint32_t)(len - boff) + 3) >> 2) : 0u;
-    for (uint32_t i = lane; i < nw + 2; i += 32) {
+    for (uint32_t i = tid; i < nw + 2; i += DW_T) {
         const uint32_t g0 = i < gmax ? __ldg(g + i) : 0u;
         const uint32_t g1 = i + 1 < gmax ? __ldg(g + i + 1) : 0u;
         d.W[i] = __byte_perm(__funnelshift_r(g0, g1, sh), 0, 0x0123);
     }
-    __syncwarp();
+    __syncthreads();
 }
 
 __device__ __forceinline__ uint32_t dw_top(const DwCtx &d, uint32_t pos)
@@ -368,118 +381,155 @@ __device__ __noinline__ void dw_walk_limited(const uint32_t *lut, const uint32_t
 }
 
 template <bool DEEP>
-__device__ __forceinline__ uint32_t dw_huff_ranges(DwCtx &d, uint32_t nbits, int flat, uint32_t limit)
+__device__ __forceinline__ uint32_t dw_huff_ranges(DwCtx &d, uint32_t nbits, int flat, int dmax, uint32_t limit)
 {
-    const uint32_t lane = dw_lane();
+    const uint32_t tid = dw_lane();
     // ranges: S bits per lane, S / 32 odd (the lanes' word loads fall into different banks); a flat code of F bits
     // never re-synchronises, so S is made a multiple of F as well
-    uint32_t wps = (((nbits + 31) >> 5) + 31) >> 5;
+    uint32_t wps = (((nbits + 31) >> 5) + DW_T - 1) / DW_T;
     if (wps == 0) wps = 1;
     uint32_t op = 1;
     if (flat) { op = (uint32_t)flat; while (!(op & 1)) op >>= 1; }
     wps = (wps + op - 1) / op * op;
     if (!(wps & 1)) wps += op;
     const uint32_t S = 32 * wps, G = S / DW_NCP;
-    const uint32_t base = min(nbits, lane * S), lim = min(nbits, (lane + 1) * S);
-    uint32_t *cp = (uint32_t *)d.out; // [NCP][32] (pos - base) << 16 | symbols before pos; dead before the output pass
+    const uint32_t base = min(nbits, tid * S), lim = min(nbits, (tid + 1) * S);
+    uint32_t *cp = (uint32_t *)d.out;   // [NCP][DW_T] (pos - base) << 16 | symbols before pos; dead before the output pass
+    uint32_t *ends = cp + DW_NCP * DW_T; // [DW_T] where the chain of each lane ends
     uint32_t start = base, pos = base, idx = 0, dummy = 0;
     for (int j = 1; j <= DW_NCP; j++) {
         const uint32_t bound = j < DW_NCP ? min(lim, base + (uint32_t)j * G) : lim;
         dw_walk<false, DEEP>(d, pos, bound, nbits, idx, dummy);
-        if (j < DW_NCP) cp[j * 32 + lane] = ((pos - base) << 16) | idx;
+        if (j < DW_NCP) cp[j * DW_T + tid] = ((pos - base) << 16) | idx;
     }
     uint32_t end = pos, cnt = idx;
-    for (int iter = 0; iter < 33; iter++) {
-        uint32_t ns = __shfl_up_sync(FULL_MASK, end, 1);
-        if (lane == 0) ns = 0;
+    for (int iter = 0; iter <= DW_T; iter++) {
+        ends[tid] = end;
+        __syncthreads();
+        const uint32_t ns = tid ? ends[tid - 1] : 0u;
         const bool need = ns != start;
-        if (!__any_sync(FULL_MASK, need)) break;
+        if (!__syncthreads_or(need)) break; // (also orders the reads of `ends` before the next round's writes)
+        if (!DEEP && iter >= DW_CASCADE) {
+            // Chains of this code do not meet inside a range (near-fixed-length codes: few symbols of almost equal
+            // frequency), so every round fixes one more lane.  Instead: a range is entered less than dmax bits behind
+            // its first bit, so every lane walks its range from each of those entries, and one lane follows the
+            // true entries through the table.
+            uint32_t *tab = ends + DW_T + 2;          // [dmax][DW_T] (end - base) << 16 | codes
+            uint32_t *tstart = tab + DW_LB * DW_T;    // [DW_T + 1] true entry of each lane, then the end of the last
+            for (int k = 0; k < dmax; k++) {
+                uint32_t p = base + (uint32_t)k, c = 0;
+                if (p < lim) dw_walk<false, DEEP>(d, p, lim, nbits, c, dummy);
+                tab[k * DW_T + tid] = ((p - base) << 16) | c;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t sp = 0;
+                for (uint32_t t = 0; t < DW_T; t++) {
+                    const uint32_t bt = min(nbits, t * S), lt = min(nbits, (t + 1) * S);
+                    tstart[t] = sp;
+#ifdef DW_DEBUG
+                    if (sp < lt && (sp < bt || sp - bt >= (uint32_t)dmax))
+                        printf("DWBUG entry t=%u sp=%u bt=%u lt=%u dmax=%d nbits=%u S=%u flat=%d K=%d\n", t, sp, bt, lt, dmax, nbits, S, flat, d.K);
+#endif
+                    if (sp < lt) sp = bt + (tab[(sp - bt) * DW_T + t] >> 16);
+                }
+                tstart[DW_T] = sp;
+            }
+            __syncthreads();
+            start = tstart[tid];
+            end = tstart[tid + 1];
+            cnt = start < lim ? tab[(start - base) * DW_T + tid] & 0xFFFFu : 0u;
+            __syncthreads();
+            break;
+        }
         bool merged = false;
         int mj = DW_NCP;
         uint32_t delta = 0;
-        if (need) { start = ns; pos = ns; idx = 0; }
-        for (int j = 1; j <= DW_NCP; j++) {
-            const uint32_t bound = j < DW_NCP ? min(lim, base + (uint32_t)j * G) : lim;
-            if (need && !merged) {
+        if (need) {
+            start = ns; pos = ns; idx = 0;
+            for (int j = 1; j <= DW_NCP && !merged; j++) {
+                const uint32_t bound = j < DW_NCP ? min(lim, base + (uint32_t)j * G) : lim;
                 dw_walk<false, DEEP>(d, pos, bound, nbits, idx, dummy);
                 if (j < DW_NCP) {
-                    const uint32_t old = cp[j * 32 + lane];
+                    const uint32_t old = cp[j * DW_T + tid];
                     if ((old >> 16) == pos - base) { merged = true; mj = j; delta = idx - (old & 0xFFFFu); }
-                    else cp[j * 32 + lane] = ((pos - base) << 16) | idx;
+                    else cp[j * DW_T + tid] = ((pos - base) << 16) | idx;
                 } else { end = pos; cnt = idx; }
             }
-        }
-        if (merged) { // the rest of the previous chain stands; its symbol counts shift by delta
-            cnt += delta;
-            for (int j = mj; j < DW_NCP; j++) {
-                const uint32_t old = cp[j * 32 + lane];
-                cp[j * 32 + lane] = (old & 0xFFFF0000u) | ((old + delta) & 0xFFFFu);
+            if (merged) { // the rest of the previous chain stands; its symbol counts shift by delta
+                cnt += delta;
+                for (int j = mj; j < DW_NCP; j++) {
+                    const uint32_t old = cp[j * DW_T + tid];
+                    cp[j * DW_T + tid] = (old & 0xFFFF0000u) | ((old + delta) & 0xFFFFu);
+                }
             }
         }
     }
-    __syncwarp();
-    // output pass
+    // output pass: symbol offsets = scan of the counts over the DW_T lanes
     const uint32_t inc = (uint32_t)warp_incl_scan((int)cnt);
-    const uint32_t total = __shfl_sync(FULL_MASK, inc, 31);
-    uint32_t o = inc - cnt;
+    if ((tid & 31) == 31) ends[DW_T + (tid >> 5)] = inc; // (ends[DW_T ..]: still inside the checkpoint area's slack)
+    __syncthreads();
+    const uint32_t w0 = ends[DW_T], total = w0 + ends[DW_T + 1];
+    uint32_t o = inc - cnt + (tid >= 32 ? w0 : 0u);
+    __syncthreads(); // cp / ends are dead now: out is written
     pos = start; idx = 0;
     if (o + cnt <= limit) dw_walk<true, DEEP>(d, pos, lim, nbits, idx, o);
     else dw_walk_limited(d.lut, d.W, d.child0, d.child1, d.leafsym, d.K, d.out, pos, end, nbits, o, limit);
-    __syncwarp();
+    __syncthreads();
     return total;
 }
 
-// payload in[0 .. len) in global memory -> d.out.  Returns the bytes produced or -1.  One warp.
+// payload in[0 .. len) in global memory -> d.out.  Returns the bytes produced or -1.  Collective (DW_T lanes).
 template <int CAP>
 __device__ inline int dw_huff(DwCtx &d, const uint8_t *__restrict__ in, int len, int orig)
 {
     if (len <= 0) return 0;
-    int boff, flat;
-    bool deep;
+    int boff, flat, dmax;
     uint32_t nbits;
-    if (dw_huff_build<CAP>(d, in, len, &boff, &nbits, &flat, &deep) < 0) return -1;
+    if (dw_huff_build<CAP>(d, in, len, &boff, &nbits, &flat, &dmax) < 0) return -1;
     dw_stage_bits(d, in, len, boff, nbits);
     const uint32_t limit = (uint32_t)max(orig, 1); // stops after the append that reaches orig_len (:464-468)
-    const uint32_t total = deep ? dw_huff_ranges<true>(d, nbits, flat, limit) : dw_huff_ranges<false>(d, nbits, flat, limit);
+    const uint32_t total = dmax > DW_LB ? dw_huff_ranges<true>(d, nbits, flat, dmax, limit) : dw_huff_ranges<false>(d, nbits, flat, dmax, limit);
     return (int)min(total, limit);
 }
 
 // ---- RLE --------------------------------------------------------------------------------------------------
-// The pairs are scanned 32 at a time: a pair with a non-zero count that starts before orig sets the bit of its
+// Warp 0 scans the pairs 32 at a time: a pair with a non-zero count that starts before orig sets the bit of its
 // first output byte and appends its value to a list; output byte x is list[popc(bits 0 .. x) - 1].  A run of
-// zeros behind the last pair pads to orig (:145-150).  16 output bytes per lane and step.
+// zeros behind the last pair pads to orig (:145-150).  All lanes expand, 16 output bytes per lane and step.
 template <int CAP>
 __device__ inline int dw_rle(DwCtx &d, const uint8_t *__restrict__ in, int len, int orig)
 {
     if (len <= 0) return 0;
-    const uint32_t lane = dw_lane();
+    const uint32_t tid = dw_lane(), lane = tid & 31;
     constexpr int NW = CAP / 32;                 // bitmap words
     uint32_t *bm = d.W;                          // [NW + 1]
     uint16_t *pre = (uint16_t *)(bm + NW + 1);   // [NW + 1] set bits before word w
     uint8_t *vals = (uint8_t *)(pre + NW + 2);   // [CAP / 2 + 1]
     static_assert(4 * (NW + 1) + 2 * (NW + 2) + CAP / 2 + 1 <= DwCfg<CAP>::W_BYTES, "RLE tables fit W");
-    for (int w = lane; w <= NW; w += 32) bm[w] = 0;
-    __syncwarp();
-    const int P = len >> 1; // complete pairs (:132-133)
-    uint32_t run = 0, nv = 0;
-    for (int k0 = 0; k0 < P && run < (uint32_t)orig; k0 += 32) {
-        const int k = k0 + (int)lane;
-        uint32_t v = 0, c = 0;
-        if (k < P) { v = __ldg(in + 2 * k); c = __ldg(in + 2 * k + 1); }
-        const uint32_t inc = (uint32_t)warp_incl_scan((int)c);
-        const uint32_t st = run + inc - c;
-        const bool live = c != 0 && st < (uint32_t)orig;
-        const uint32_t m = __ballot_sync(FULL_MASK, live);
-        if (live) {
-            vals[nv + __popc(m & ((1u << lane) - 1))] = (uint8_t)v;
-            atomicOr(&bm[st >> 5], 1u << (st & 31));
+    for (int w = tid; w <= NW; w += DW_T) bm[w] = 0;
+    __syncthreads();
+    if (tid < 32) {
+        const int P = len >> 1; // complete pairs (:132-133)
+        uint32_t run = 0, nv = 0;
+        for (int k0 = 0; k0 < P && run < (uint32_t)orig; k0 += 32) {
+            const int k = k0 + (int)lane;
+            uint32_t v = 0, c = 0;
+            if (k < P) { v = __ldg(in + 2 * k); c = __ldg(in + 2 * k + 1); }
+            const uint32_t inc = (uint32_t)warp_incl_scan((int)c);
+            const uint32_t st = run + inc - c;
+            const bool live = c != 0 && st < (uint32_t)orig;
+            const uint32_t m = __ballot_sync(FULL_MASK, live);
+            if (live) {
+                vals[nv + __popc(m & ((1u << lane) - 1))] = (uint8_t)v;
+                atomicOr(&bm[st >> 5], 1u << (st & 31));
+            }
+            nv += __popc(m);
+            run += __shfl_sync(FULL_MASK, inc, 31);
         }
-        nv += __popc(m);
-        run += __shfl_sync(FULL_MASK, inc, 31);
-    }
-    if (run < (uint32_t)orig && lane == 0) { vals[nv] = 0; atomicOr(&bm[run >> 5], 1u << (run & 31)); }
-    __syncwarp();
-    {   // set bits before each bitmap word
+        if (run < (uint32_t)orig && lane == 0) { vals[nv] = 0; atomicOr(&bm[run >> 5], 1u << (run & 31)); }
+        __syncwarp();
+        // set bits before each bitmap word
         constexpr int WPL = NW / 32;
         uint32_t pc[WPL], s = 0;
 #pragma unroll
@@ -488,8 +538,8 @@ __device__ inline int dw_rle(DwCtx &d, const uint8_t *__restrict__ in, int len, 
 #pragma unroll
         for (int q = 0; q < WPL; q++) { pre[lane * WPL + q] = (uint16_t)ex; ex += pc[q]; }
     }
-    __syncwarp();
-    for (int g = lane; 16 * g < orig; g += 32) {
+    __syncthreads();
+    for (int g = tid; 16 * g < orig; g += DW_T) {
         const int x = 16 * g;
         const uint32_t w = bm[x >> 5], sh = x & 31;
         uint32_t slice = (w >> sh) & 0xFFFFu;
@@ -514,7 +564,7 @@ __device__ inline int dw_rle(DwCtx &d, const uint8_t *__restrict__ in, int len, 
         }
         *(uint4 *)(d.out + x) = v4;
     }
-    __syncwarp();
+    __syncthreads();
     return orig;
 }
 
@@ -523,18 +573,17 @@ __device__ __forceinline__ bool dw_eligible(const ambc_pkg &e, uint32_t cap)
     return (e.type == 1 || e.type == 3) && e.comp_len <= cap && e.orig_len <= cap;
 }
 
-// CAP = 4096: packages of at most 4096 bytes; CAP = 8192: the rest up to 8192
+// CAP = 4096: packages of at most 4096 bytes; CAP = 8192: the rest up to 8192.  One CTA of DW_T lanes per package.
 template <int CAP>
-__global__ void __launch_bounds__(DW_WARPS * 32)
+__global__ void __launch_bounds__(DW_T)
 k_decode_warp(const uint8_t *__restrict__ body, const ambc_pkg *__restrict__ table, uint64_t n_entries,
               uint8_t *__restrict__ out, uint32_t *status)
 {
     extern __shared__ uint4 smem4[];
-    const int w = threadIdx.x >> 5;
-    const uint32_t lane = dw_lane();
+    const uint32_t tid = dw_lane();
     DwCtx d;
-    dw_carve<CAP>(d, (uint8_t *)smem4 + (size_t)w * DwCfg<CAP>::PER_WARP);
-    for (uint64_t i = (uint64_t)blockIdx.x * DW_WARPS + w; i < n_entries; i += (uint64_t)gridDim.x * DW_WARPS) {
+    dw_carve<CAP>(d, (uint8_t *)smem4);
+    for (uint64_t i = blockIdx.x; i < n_entries; i += gridDim.x) {
         const ambc_pkg e = table[i];
         if (!dw_eligible(e, 8192) || (CAP == 4096) != (e.comp_len <= 4096 && e.orig_len <= 4096)) continue;
         uint8_t *dst = out + e.dst_off;
@@ -545,9 +594,9 @@ k_decode_warp(const uint8_t *__restrict__ body, const ambc_pkg *__restrict__ tab
         const uint32_t good = produced < 0 ? 0u : min((uint32_t)produced, e.out_len);
         dw_store(dst, d.out, good);
         if (produced < 0 || (uint32_t)produced != nominal) { // codec raised (:440-442) / malformed stream
-            for (uint32_t k = good + lane; k < e.out_len; k += 32) dst[k] = 0;
-            if (lane == 0 && status) atomicAdd(&status[produced < 0 ? 0 : 1], 1u);
+            for (uint32_t k = good + tid; k < e.out_len; k += DW_T) dst[k] = 0;
+            if (tid == 0 && status) atomicAdd(&status[produced < 0 ? 0 : 1], 1u);
         }
-        __syncwarp();
+        __syncthreads();
     }
 }
