@@ -209,9 +209,13 @@ k_select_fast(const uint8_t *__restrict__ in, uint64_t total, uint32_t N, uint32
         // strict mode: a chunk behind a chunk without a winner lies inside the one raw package that ends the file
         // (adaptive_compressor.py:586-590), whatever its own trial would say.  first_raw only ever decreases, so a
         // value below i seen now is final enough: the scan and pack kernels ignore the map from first_raw on.
-        // (one thread reads and the CTA votes: first_raw changes under the kernel's feet, and threads that read
+        // (one thread reads for the CTA: first_raw changes under the kernel's feet, and threads that read
         // different values would part ways in front of the barriers of the trial)
-        if (strict && __syncthreads_or(threadIdx.x == 0 && *(volatile unsigned long long *)first_raw < i)) {
+        if (strict) {
+            if (threadIdx.x == 0) c.red[30] = *(volatile unsigned long long *)first_raw < i;
+            __syncthreads();
+        }
+        if (strict && c.red[30]) {
             if (threadIdx.x == 0) { type[i] = 255; comp[i] = (uint32_t)n; }
             continue;
         }
