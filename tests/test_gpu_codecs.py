@@ -181,3 +181,48 @@ def test_encode_lz_bucket_search_fallback(eng):
         assert lib.ambc_set_lz_force_buckets(0) == 0
     bad = [(i, len(d)) for i, (d, g) in enumerate(zip(datas, got)) if g != O.compress(2, d, lz_fast=True)]
     assert not bad, bad
+
+
+def test_huffman_decode_code_shapes(eng):
+    """the code shapes that steer k_decode_warp's Huffman paths (decode_warp.cuh): flat codes (ranges must be a
+    multiple of the code length), near-flat codes that never re-synchronise (all-entries path), codes longer
+    than the look-up table (tree walk), streams shorter than a lane's range, orig_len below / above the number
+    of symbols in the stream -- every output equals the oracle's decoder (compression_methods.py:407-470)"""
+    r = np.random.RandomState(4242)
+    datas = []
+    for k in (2, 3, 4, 5, 7, 8, 9, 12, 16, 17, 32, 33, 64, 100, 128, 200, 255):  # (near-)uniform alphabets
+        for n in (100, 517, 4096, 8192):
+            datas.append(bytes(r.randint(0, k, size=n).astype(np.uint8)))
+    for n in (300, 4096, 8192):  # exactly equal counts: flat trees
+        for k in (2, 4, 8, 16, 64):
+            datas.append(bytes(np.tile(np.arange(k, dtype=np.uint8), n // k + 1)[:n]))
+    for n in (2000, 4096, 8192):  # geometric and Fibonacci-like counts: codes of 12 .. 20 bits
+        sym, cnt, out = 0, n // 2, []
+        while cnt >= 1 and sym < 40:
+            out += [sym] * int(cnt); sym += 1; cnt = cnt * 0.62
+        a = np.array(out[:n], dtype=np.uint8); r.shuffle(a)
+        datas.append(bytes(a))
+        datas.append(inputs.make("fib", n, 77 + n))
+    payloads, origs = [], []
+    for d in datas:
+        p = O.compress(3, d)
+        if isinstance(p, int):
+            continue
+        for o in (len(d), max(0, len(d) - 37), len(d) + 19, 1):
+            payloads.append(p); origs.append(o)
+    got = eng.codec_decode_batch(3, payloads, origs)
+    bad = [(i, len(p), o, _fmt(g)) for i, (p, o, g) in enumerate(zip(payloads, origs, got)) if g != O.decompress(3, p, o)]
+    assert not bad, bad[:20]
+    # the same payloads framed as packages of a body: the container path of the same kernel
+    body = bytearray()
+    want = bytearray()
+    for p, o in zip(payloads, origs):
+        w = O.decompress(3, p, o)
+        if o == 0 or len(p) > 8192 or not isinstance(w, bytes) or len(w) != o:
+            continue
+        body += b"\xff\xff\x00\x00" + bytes([3, 0]) + int(o).to_bytes(4, "little") * 2 + len(p).to_bytes(4, "little") + p
+        want += w
+    body += b"\xff\xff\x00\x00" + bytes(12)
+    import torch
+    dec, status = eng.decompress_device(torch.frombuffer(bytearray(body), dtype=torch.uint8).cuda(), len(want))
+    assert status == [0, 0] and bytes(dec.cpu().numpy()) == bytes(want)
