@@ -349,26 +349,39 @@ k_decode_lz(const uint8_t *__restrict__ body, const ambc_pkg *__restrict__ table
     extern __shared__ uint4 smem4[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t *buf = (uint8_t *)smem4 + (size_t)w * OUTCAP;
-    for (uint64_t i = (uint64_t)blockIdx.x * DLZ_WARPS + w; i < n_entries; i += (uint64_t)gridDim.x * DLZ_WARPS) {
-        const ambc_pkg e = table[i];
-        if (!dlz_eligible(e) || (e.orig_len <= 4096) != (OUTCAP == DLZ_OUT)) continue;
-        uint8_t *dst = out + e.dst_off;
-        const int produced = dec_lz_warp(body + e.src_off, (int)e.comp_len, (int)e.orig_len, buf, OUTCAP);
-        const uint32_t nominal = e.comp_len == 0 ? 0 : e.orig_len;
-        uint32_t good = produced < 0 ? 0u : min((uint32_t)produced, e.out_len);
-        // smem -> global, 16-byte stores when the destination allows
-        if ((((uintptr_t)dst) & 15) == 0) {
-            const uint32_t nv = good >> 4;
-            for (uint32_t k = lane; k < nv; k += 32) ((uint4 *)dst)[k] = ((const uint4 *)buf)[k];
-            for (uint32_t k = (nv << 4) + lane; k < good; k += 32) dst[k] = buf[k];
-        } else {
-            for (uint32_t k = lane; k < good; k += 32) dst[k] = buf[k];
+    // entry first + k * stride is this warp's k-th; the lanes look at 32 of them at once (one round trip to the
+    // table instead of one per entry: most entries belong to another decoder)
+    const uint64_t first = (uint64_t)blockIdx.x * DLZ_WARPS + w, stride = (uint64_t)gridDim.x * DLZ_WARPS;
+    for (uint64_t k0 = 0; first + k0 * stride < n_entries; k0 += 32) {
+        const uint64_t mine = first + (k0 + lane) * stride;
+        bool want = false;
+        if (mine < n_entries) {
+            const ambc_pkg e = table[mine];
+            want = dlz_eligible(e) && (e.orig_len <= 4096) == (OUTCAP == DLZ_OUT);
         }
-        if (produced < 0 || (uint32_t)produced != nominal) {
-            for (uint32_t k = good + lane; k < e.out_len; k += 32) dst[k] = 0;
-            if (lane == 0 && status) atomicAdd(&status[produced < 0 ? 0 : 1], 1u);
+        uint32_t todo = __ballot_sync(FULL_MASK, want);
+        while (todo) {
+            const int b = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const ambc_pkg e = table[first + (k0 + b) * stride];
+            uint8_t *dst = out + e.dst_off;
+            const int produced = dec_lz_warp(body + e.src_off, (int)e.comp_len, (int)e.orig_len, buf, OUTCAP);
+            const uint32_t nominal = e.comp_len == 0 ? 0 : e.orig_len;
+            uint32_t good = produced < 0 ? 0u : min((uint32_t)produced, e.out_len);
+            // smem -> global, 16-byte stores when the destination allows
+            if ((((uintptr_t)dst) & 15) == 0) {
+                const uint32_t nv = good >> 4;
+                for (uint32_t k = lane; k < nv; k += 32) ((uint4 *)dst)[k] = ((const uint4 *)buf)[k];
+                for (uint32_t k = (nv << 4) + lane; k < good; k += 32) dst[k] = buf[k];
+            } else {
+                for (uint32_t k = lane; k < good; k += 32) dst[k] = buf[k];
+            }
+            if (produced < 0 || (uint32_t)produced != nominal) {
+                for (uint32_t k = good + lane; k < e.out_len; k += 32) dst[k] = 0;
+                if (lane == 0 && status) atomicAdd(&status[produced < 0 ? 0 : 1], 1u);
+            }
+            __syncwarp();
         }
-        __syncwarp();
     }
 }
 

@@ -583,19 +583,38 @@ k_decode_warp(const uint8_t *__restrict__ body, const ambc_pkg *__restrict__ tab
     const uint32_t tid = dw_lane();
     DwCtx d;
     dw_carve<CAP>(d, (uint8_t *)smem4);
-    for (uint64_t i = blockIdx.x; i < n_entries; i += gridDim.x) {
-        const ambc_pkg e = table[i];
-        if (!dw_eligible(e, 8192) || (CAP == 4096) != (e.comp_len <= 4096 && e.orig_len <= 4096)) continue;
-        uint8_t *dst = out + e.dst_off;
-        const uint8_t *src = body + e.src_off;
-        const int produced = e.type == 3 ? dw_huff<CAP>(d, src, (int)e.comp_len, (int)e.orig_len)
-                                         : dw_rle<CAP>(d, src, (int)e.comp_len, (int)e.orig_len);
-        const uint32_t nominal = e.comp_len == 0 ? 0 : e.orig_len; // what the index assumed (nominal_out)
-        const uint32_t good = produced < 0 ? 0u : min((uint32_t)produced, e.out_len);
-        dw_store(dst, d.out, good);
-        if (produced < 0 || (uint32_t)produced != nominal) { // codec raised (:440-442) / malformed stream
-            for (uint32_t k = good + tid; k < e.out_len; k += DW_T) dst[k] = 0;
-            if (tid == 0 && status) atomicAdd(&status[produced < 0 ? 0 : 1], 1u);
+    __shared__ uint32_t s_want[DW_T / 32];
+    // entry blockIdx.x + k * gridDim.x is this CTA's k-th; the lanes look at DW_T of them at once (one round trip
+    // to the table instead of one per entry: many entries belong to another decoder)
+    for (uint64_t k0 = 0; blockIdx.x + k0 * gridDim.x < n_entries; k0 += DW_T) {
+        const uint64_t mine = blockIdx.x + (k0 + tid) * (uint64_t)gridDim.x;
+        bool want = false;
+        if (mine < n_entries) {
+            const ambc_pkg e = table[mine];
+            want = dw_eligible(e, 8192) && (CAP == 4096) == (e.comp_len <= 4096 && e.orig_len <= 4096);
+        }
+        const uint32_t bal = __ballot_sync(FULL_MASK, want);
+        if ((tid & 31) == 0) s_want[tid >> 5] = bal;
+        __syncthreads();
+        for (int wv = 0; wv < DW_T / 32; wv++) {
+            uint32_t todo = s_want[wv];
+            while (todo) {
+                const int b = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const ambc_pkg e = table[blockIdx.x + (k0 + 32 * wv + b) * (uint64_t)gridDim.x];
+                uint8_t *dst = out + e.dst_off;
+                const uint8_t *src = body + e.src_off;
+                const int produced = e.type == 3 ? dw_huff<CAP>(d, src, (int)e.comp_len, (int)e.orig_len)
+                                                 : dw_rle<CAP>(d, src, (int)e.comp_len, (int)e.orig_len);
+                const uint32_t nominal = e.comp_len == 0 ? 0 : e.orig_len; // what the index assumed (nominal_out)
+                const uint32_t good = produced < 0 ? 0u : min((uint32_t)produced, e.out_len);
+                dw_store(dst, d.out, good);
+                if (produced < 0 || (uint32_t)produced != nominal) { // codec raised (:440-442) / malformed stream
+                    for (uint32_t k = good + tid; k < e.out_len; k += DW_T) dst[k] = 0;
+                    if (tid == 0 && status) atomicAdd(&status[produced < 0 ? 0 : 1], 1u);
+                }
+                __syncthreads();
+            }
         }
         __syncthreads();
     }
