@@ -8,6 +8,7 @@ LIB_PATH = os.environ.get("AMBC_LIB_PATH") or os.path.join(_HERE, "libambc.so") 
 
 OK, E_CUDA, E_ARG, E_CAPACITY, E_MARKER, E_TOO_LARGE, E_NO_MARKER = 0, -1, -2, -3, -4, -5, -6
 RLE, DICT, HUFFMAN, DELTA, RAW = 1, 2, 3, 4, 255
+DEFLATE = 5  # zlib streams (advanced_compression.py:71-107): a plug-in codec and a decodable package type, not a trial candidate
 NATIVE_MASK = (1 << 1) | (1 << 2) | (1 << 3) | (1 << 4)
 MAX_CODEC_CHUNK = 8192
 F_PER_CHUNK_RAW = 1

@@ -12,7 +12,8 @@ What differs, on purpose:
     tried at every position on the GPU).  chunk_size=N selects ONE size -- the fixed grid of the benchmarked
     path (--chunk-size 4096 in BASELINE.json's configs), an order of magnitude faster.  Candidate lists are
     searched largest first (the reference honours the list order on ratio ties; its own list is descending).
-  * only the repo-native methods 1-4 (+255) are loaded; third-party codecs 5-11 are out of scope.
+  * only the repo-native methods 1-4 (+255) are loaded by default; DEFLATE (id 5) on request (methods=[..., 5]): decoded
+    on the GPU, not a trial candidate; the other third-party codecs 6-11 are out of scope.
   * per_chunk_raw=True and use_marker_search=True are labelled extensions (files stay readable by
     the reference decoder)."""
 import hashlib
@@ -26,7 +27,7 @@ import torch
 
 from . import _lib as L
 from . import engine
-from .compression_methods import (DeltaCompression, DictionaryCompression, HuffmanCompression, NoCompression,
+from .compression_methods import (DeflateCompression, DeltaCompression, DictionaryCompression, HuffmanCompression, NoCompression,
                                   RLECompression)
 from .marker_finder import MarkerFinder
 
@@ -72,6 +73,10 @@ class AdaptiveCompressor:
                                     DeltaCompression(), NoCompression()]
         if methods is not None:
             keep = set(int(m) for m in methods) | {255}
+            if 5 in keep:
+                # DEFLATE on request (advanced_compression.py:71-107): packages of type 5 decode on the GPU; the
+                # chunk trial of compress() stays with methods 1-4, see _method_mask
+                self.compression_methods.insert(4, DeflateCompression())
             self.compression_methods = [m for m in self.compression_methods if m.type_id in keep]
         if disable_methods:
             drop = set(int(m) for m in disable_methods) - {255}
@@ -148,10 +153,14 @@ class AdaptiveCompressor:
 
     def _method_mask(self):
         ids = [m.type_id for m in self.compression_methods if m.type_id != 255]
-        foreign = [i for i in ids if i not in (1, 2, 3, 4)]
+        foreign = [i for i in ids if i not in (1, 2, 3, 4, 5)]
         if foreign:
             raise NotImplementedError("only the repo-native methods 1-4 run on the B200 path; got %s" % foreign)
-        return engine.method_mask(ids)
+        if 5 in ids:
+            # the GPU DEFLATE encoder does not write zlib.compress(level=9)'s bytes, so a trial with it could
+            # not reproduce the reference's choices: it is a plug-in (DeflateCompression) and a decodable type
+            print("DEFLATE (id 5) is decoded but takes no part in the chunk trial on the B200 path")
+        return engine.method_mask([i for i in ids if i != 5])
 
     # ---- compress (adaptive_compressor.py:221-255) ----
     @staticmethod

@@ -99,6 +99,47 @@ class DeltaCompression(_NativeMethod):
     _id = L.DELTA
 
 
+class DeflateCompression(CompressionMethod):
+    """method id 5 (advanced_compression.py:71-107), where the reference calls zlib.  compress() writes a
+    conforming zlib stream on the GPU (one fixed-Huffman block over a greedy LZ77 parse): stock
+    zlib.decompress reads it, but it is not the byte string zlib.compress(level=9) would write, so this codec
+    is reported separately and is not a candidate of the chunk trial.  decompress() inflates ANY zlib stream
+    on the GPU with the reference's conventions: pad / truncate to original_length, and where zlib raises
+    (bad header, invalid block, truncated stream, Adler-32 mismatch) original_length zero bytes."""
+
+    @property
+    def type_id(self):
+        return L.DEFLATE
+
+    def compress(self, data, level=9):
+        if not data:
+            return b""
+        data = bytes(data)
+        # items of the C-ABI are limited to 8192 bytes; longer inputs become several complete zlib streams only
+        # in the sense of one stream per call, so they are refused rather than silently split
+        out = engine.codec_encode_batch(L.DEFLATE, [data])[0]
+        if isinstance(out, int):
+            raise L.AmbcError(out, "DEFLATE encode failed")
+        return out
+
+    def decompress(self, data, original_length):
+        if not data:
+            return b""
+        out = engine.codec_decode_batch(L.DEFLATE, [bytes(data)], [int(original_length)])[0]
+        if isinstance(out, int):
+            raise L.AmbcError(out, "DEFLATE decode failed")
+        return out
+
+    def should_use(self, data, threshold=0.9):
+        """at least 64 bytes and an entropy below 8.0 (advanced_compression.py:99-107)"""
+        if len(data) < 64:
+            return False
+        if len(data) > L.MAX_CODEC_CHUNK:
+            return True  # (entropy 8.0 needs a perfectly flat histogram; the gate kernel takes items up to 8192 bytes)
+        _, ent = engine.should_use_batch([bytes(data)])
+        return not ent[0] >= 8.0
+
+
 class NoCompression(CompressionMethod):
     """identity (compression_methods.py:670-713)"""
 

@@ -4,12 +4,16 @@
 #include "ambc_internal.h"
 #include "chunk_codec.cuh"
 
+int ambc_deflate_encode_batch(const void *in_dev, const uint64_t *in_off_dev, uint32_t n_items, void *out_dev,
+                              uint64_t out_stride, int32_t *out_len_dev, cudaStream_t stream);
+
 extern "C" uint64_t ambc_codec_bound(int method, uint32_t n)
 {
     switch (method) {
     case 1: return 2ull * n + 16;                 // one pair per byte
     case 2: return 2ull * n + 16;                 // one literal token per byte
     case 3: return 1 + 5 * 256 + 4 + 4ull * n + 16; // table + codes of at most 32 bits
+    case 5: return (uint64_t)n + n / 8 + 32;        // zlib wrapper + fixed codes of at most 9 bits per byte
     default: return (uint64_t)n + 16;
     }
 }
@@ -56,9 +60,10 @@ extern "C" int ambc_codec_encode_batch(int method, const void *in_dev, const uin
                                        void *out_dev, uint64_t out_stride, int32_t *out_len_dev, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (method < 1 || method > 4) return ambc_fail(AMBC_E_ARG, "ambc_codec_encode_batch: unknown method %d", method);
+    if (method < 1 || method > 5) return ambc_fail(AMBC_E_ARG, "ambc_codec_encode_batch: unknown method %d", method);
     if (n_items == 0) return AMBC_OK;
     if (!in_off_dev || !out_dev || !out_len_dev) return ambc_fail(AMBC_E_ARG, "null buffer");
+    if (method == 5) return ambc_deflate_encode_batch(in_dev, in_off_dev, n_items, out_dev, out_stride, out_len_dev, stream);
     // item sizes are validated by the caller (<= AMBC_MAX_CODEC_CHUNK); payload capacity = stride
     const int N = AMBC_NMAX;
     uint64_t need = ambc_codec_bound(method, N);

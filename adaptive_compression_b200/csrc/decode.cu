@@ -3,6 +3,7 @@
 #include "ambc_internal.h"
 #include "decode_codec.cuh"
 #include "decode_warp.cuh"
+#include "deflate.cuh"
 #include <thread>
 #include <cstdlib>
 #include <vector>
@@ -227,6 +228,20 @@ __device__ int decode_package(DecCtx &d, uint32_t type, const uint8_t *__restric
                               uint32_t orig, uint8_t *__restrict__ dst, uint32_t cap)
 {
     const bool fast = comp <= (uint32_t)d.in_cap && orig <= DEC_OUT_CAP;
+    if (type == 5) { // DeflateCompression.decompress (advanced_compression.py:84-97): a zlib error gives zeros, no exception
+        if (comp == 0) return 0;
+        volatile int *res5 = d.red;
+        if (threadIdx.x == 0) {
+            InfCode *codes = (InfCode *)d.X; // 2 x 608 bytes of the 12 KiB scratch
+            const long got = inflate_zlib(src, (long)comp, dst, (long)cap, codes, codes + 1);
+            res5[24] = got < 0 ? 0 : (got < (long)cap ? (int)got : (int)cap);
+        }
+        __syncthreads();
+        const uint32_t good = (uint32_t)res5[24];
+        __syncthreads();
+        for (uint32_t k = good + threadIdx.x; k < cap; k += AMBC_BLOCK) dst[k] = 0;
+        return (int)orig;
+    }
     if (type == 255) { // bytes + zero pad, any size up to RAW_PIECE
         uint32_t done = 0;
         while (done < cap) {
@@ -474,6 +489,9 @@ extern "C" int ambc_decompress_dev(const void *body_dev, uint64_t body_len, cons
     return AMBC_OK;
 }
 
+int ambc_inflate_batch(const void *in_dev, const uint64_t *in_off_dev, const uint32_t *orig_len_dev, uint32_t n_items,
+                       void *out_dev, uint64_t out_stride, int32_t *out_len_dev, cudaStream_t stream);
+
 // ---- codec plug-in batch kernels (CompressionMethod API parity) -------------------------------
 // items the warp decoders take (the same code as the container path, so the codec-level fixtures hold it too)
 __device__ __forceinline__ bool codec_item_warp(int method, uint32_t comp, uint32_t orig)
@@ -537,10 +555,11 @@ extern "C" int ambc_codec_decode_batch(int method, const void *in_dev, const uin
                                        uint64_t out_stride, int32_t *out_len_dev, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (!(method == 1 || method == 2 || method == 3 || method == 4 || method == 255))
+    if (!(method == 1 || method == 2 || method == 3 || method == 4 || method == 5 || method == 255))
         return ambc_fail(AMBC_E_ARG, "ambc_codec_decode_batch: unknown method %d", method);
     if (n_items == 0) return AMBC_OK;
     if (!in_off_dev || !orig_len_dev || !out_dev || !out_len_dev) return ambc_fail(AMBC_E_ARG, "null buffer");
+    if (method == 5) return ambc_inflate_batch(in_dev, in_off_dev, orig_len_dev, n_items, out_dev, out_stride, out_len_dev, stream);
     const int in_cap = 2 * AMBC_NMAX + 2048; // any payload the encoders can emit for <= 8192 bytes
     size_t smem = decctx_smem_bytes(in_cap);
     CUDA_TRY(cudaFuncSetAttribute(k_codec_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -181,7 +181,15 @@ int ambc_decompress_host(const void *body_host, uint64_t body_len, const uint8_t
 /* ------------------------------------------------------------------ */
 /* codec plug-ins: CompressionMethod.compress / decompress / should_use */
 /*   compression_methods.py:78-180 (RLE), :195-343 (Dictionary),         */
-/*   :354-574 (Huffman), :585-667 (Delta), :678-713 (NoCompression)      */
+/*   :354-574 (Huffman), :585-667 (Delta), :678-713 (NoCompression);     */
+/*   method 5 = DeflateCompression, advanced_compression.py:71-107, where */
+/*   the reference calls zlib: encode writes a conforming zlib stream     */
+/*   (RFC 1950 / 1951, one fixed-Huffman block) that stock zlib reads --  */
+/*   not zlib.compress(level=9)'s own bytes, hence a plug-in reported     */
+/*   separately and no candidate of the chunk trial; decode inflates any  */
+/*   zlib stream, pads / truncates to original_length, and returns        */
+/*   original_length zero bytes where zlib.decompress raises (:93-97).    */
+/*   known_mask bit 5 makes packages of type 5 decodable in a body.       */
 /* ------------------------------------------------------------------ */
 
 /*

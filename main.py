@@ -11,7 +11,7 @@ import time
 METHOD_TOKENS = {"rle": 1, "dictionary": 2, "dict": 2, "huffman": 3, "delta": 4, "deflate": 5, "bzip2": 6, "lzma": 7,
                  "zstandard": 8, "zstd": 8, "lz4": 9, "brotli": 10, "lzham": 11, "none": 255, "raw": 255}
 METHOD_LABELS = {1: "Run-Length Encoding (RLE)", 2: "Dictionary-Based", 3: "Huffman Coding", 4: "Delta Encoding",
-                 255: "No Compression"}
+                 5: "DEFLATE", 255: "No Compression"}
 
 
 def parse_methods(text):

@@ -274,3 +274,18 @@ def test_history_record_matches_the_analyzer_schema(tmp_path, golden):
     recs = json.load(open(path))
     assert [r["filename"] for r in recs] == ["a.log", "b.bin", "c"] and recs[1]["compressed_size"] == 30000
     assert recs[2]["extension"] == "unknown"
+
+
+def test_deflate_plugin_surface():
+    """DeflateCompression (advanced_compression.py:71-107) exists with the reference's id and is opt-in in the
+    facade: methods=[..., 5] makes type 5 a known (decodable) method without entering the chunk trial"""
+    from adaptive_compression_b200 import _lib as L
+    from adaptive_compression_b200.adaptive_compressor import AdaptiveCompressor
+    from adaptive_compression_b200.compression_methods import DeflateCompression
+    assert DeflateCompression().type_id == 5 == L.DEFLATE
+    assert DeflateCompression().compress(b"") == b"" and DeflateCompression().decompress(b"", 9) == b""
+    assert not DeflateCompression().should_use(bytes(63))
+    c = AdaptiveCompressor(chunk_size=4096, methods=[1, 2, 3, 5])
+    assert [m.type_id for m in c.compression_methods] == [1, 2, 3, 5, 255]
+    assert c._method_mask() == (1 << 1) | (1 << 2) | (1 << 3)
+    assert [m.type_id for m in AdaptiveCompressor(chunk_size=4096).compression_methods] == [1, 2, 3, 4, 255]
