@@ -117,6 +117,29 @@ __device__ __forceinline__ void copy_g2s(uint8_t *dst, const uint8_t *__restrict
     for (int i = (nv << 4) + threadIdx.x; i < len; i += BS) dst[i] = __ldg(src + i);
 }
 
+// Copy `len` bytes global (any alignment) -> global (16-byte aligned), no staging: raw packages are plain bytes.
+template <int BS = AMBC_BLOCK>
+__device__ __forceinline__ void copy_g2g16(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, uint32_t len)
+{
+    const uint32_t nv = len >> 4;
+    uint4 *d4 = (uint4 *)dst;
+    const uint32_t sh = (uint32_t)((uintptr_t)src & 15);
+    if (sh == 0) {
+        const uint4 *s4 = (const uint4 *)src;
+        for (uint32_t i = threadIdx.x; i < nv; i += BS) d4[i] = __ldg(s4 + i);
+    } else {
+        const uint4 *s4 = (const uint4 *)(src - sh);
+        const uint32_t r = (sh & 3) * 8;
+        switch (sh >> 2) {
+        case 0: for (uint32_t i = threadIdx.x; i < nv; i += BS) d4[i] = shift16<0>(__ldg(s4 + i), __ldg(s4 + i + 1), r); break;
+        case 1: for (uint32_t i = threadIdx.x; i < nv; i += BS) d4[i] = shift16<1>(__ldg(s4 + i), __ldg(s4 + i + 1), r); break;
+        case 2: for (uint32_t i = threadIdx.x; i < nv; i += BS) d4[i] = shift16<2>(__ldg(s4 + i), __ldg(s4 + i + 1), r); break;
+        default: for (uint32_t i = threadIdx.x; i < nv; i += BS) d4[i] = shift16<3>(__ldg(s4 + i), __ldg(s4 + i + 1), r); break;
+        }
+    }
+    for (uint32_t i = (nv << 4) + threadIdx.x; i < len; i += BS) dst[i] = __ldg(src + i);
+}
+
 // Copy `len` bytes shared (any alignment) -> global (any alignment): byte stores up to the
 // first 16-byte boundary of dst, aligned 16-byte stores fed by funnel-shifted shared loads,
 // byte stores for the tail.

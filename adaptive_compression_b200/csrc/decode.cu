@@ -243,6 +243,12 @@ __device__ int decode_package(DecCtx &d, uint32_t type, const uint8_t *__restric
         return (int)orig;
     }
     if (type == 255) { // bytes + zero pad, any size up to RAW_PIECE
+        if ((((uintptr_t)dst) & 15) == 0) { // the usual case (pieces start at multiples of 64 KiB of an aligned output)
+            const uint32_t have = comp < cap ? comp : cap;
+            copy_g2g16(dst, src, have);
+            for (uint32_t i = have + threadIdx.x; i < cap; i += AMBC_BLOCK) dst[i] = 0;
+            return (int)orig;
+        }
         uint32_t done = 0;
         while (done < cap) {
             uint32_t piece = min(cap - done, (uint32_t)DEC_OUT_CAP);
