@@ -230,17 +230,20 @@ __device__ int dec_lz_warp(const uint8_t *__restrict__ in, int len, int orig, ui
         __syncwarp();
         // matches in order, one warp-wide copy each.  32-bit shared addresses and explicit ld / st.shared: with a
         // generic `out` the copy loop alone cost 17 warp instructions per match (ncu, 35 with its bookkeeping).
-        const uint32_t recA = (uint32_t)off | ((uint32_t)mlen << 16);
+        // (destination address | length << 20 and the source address are formed once per window by every lane; a
+        // match then costs two shuffles: shared-window addresses are below 2^18)
+        const uint32_t recD = (so + (uint32_t)off) | ((uint32_t)mlen << 20);
+        const uint32_t recS = so + (uint32_t)off - (uint32_t)dist;
         while (mm) {
             const int i = __ffs(mm) - 1;
             mm &= mm - 1;
-            const uint32_t a = __shfl_sync(FULL_MASK, recA, i);
-            const uint32_t mdist = (uint32_t)__shfl_sync(FULL_MASK, dist, i);
-            const uint32_t ml = a >> 16, dsta = so + (a & 0xFFFFu), srca = dsta - mdist;
-            if (mdist >= ml) {
+            const uint32_t a = __shfl_sync(FULL_MASK, recD, i);
+            const uint32_t srca = __shfl_sync(FULL_MASK, recS, i);
+            const uint32_t ml = a >> 20, dsta = a & 0xFFFFFu, mdist = dsta - srca;
+            if (ml <= min(mdist, 32u)) { // the usual match: at most 32 bytes, source in front of the destination
                 if ((uint32_t)lane < ml) dlz_sts8(dsta + lane, dlz_lds8(srca + lane));
-                if (ml > 32u)
-                    for (uint32_t t = lane + 32; t < ml; t += 32) dlz_sts8(dsta + t, dlz_lds8(srca + t));
+            } else if (mdist >= ml) {
+                for (uint32_t t = lane; t < ml; t += 32) dlz_sts8(dsta + t, dlz_lds8(srca + t));
             } else if (mdist == 1u) { // a run of one byte
                 const uint32_t v = dlz_lds8(srca);
                 for (uint32_t t = lane; t < ml; t += 32) dlz_sts8(dsta + t, v);
