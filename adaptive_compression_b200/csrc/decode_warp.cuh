@@ -9,8 +9,9 @@
 //   RLE      compression_methods.py:116-152   (pairs, odd tail ignored, truncate / zero pad)
 //
 // Huffman: the 64 lanes decode 64 bit ranges of the stream.  Only lane 0 knows where its first code starts, so
-//   pass 1     every lane decodes its range from the range start and remembers, at NCP checkpoints (bit boundaries
-//              inside the range), the first code start at or behind the boundary and how many symbols came before;
+//   pass 1     every lane decodes its range from the range start and remembers, at NCP - 1 checkpoints (bit
+//              boundaries inside the range), the first code start at or behind the boundary and how many symbols came
+//              before;
 //   re-sync    a lane whose predecessor ended somewhere else restarts there and decodes only until it stands on a
 //              checkpoint of its previous chain -- from there on the two chains are the same chain (the next code
 //              start is a function of the position), so the old end and the old counts are adopted.  Huffman codes
