@@ -233,7 +233,7 @@ __device__ int decode_package(DecCtx &d, uint32_t type, const uint8_t *__restric
         volatile int *res5 = d.red;
         if (threadIdx.x == 0) {
             InfCode *codes = (InfCode *)d.X; // 2 x 608 bytes of the 12 KiB scratch
-            const long got = inflate_zlib(src, (long)comp, dst, (long)cap, codes, codes + 1);
+            const long got = inflate_zlib(src, (long)comp, dst, (long)cap, false, codes, codes + 1);
             res5[24] = got < 0 ? 0 : (got < (long)cap ? (int)got : (int)cap);
         }
         __syncthreads();

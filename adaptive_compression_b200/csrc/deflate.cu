@@ -60,7 +60,9 @@ k_inflate_batch(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
         int result = 0;
         if (comp > 0) { // DeflateCompression.decompress: b'' for empty data; zlib error -> zeros (:84-97)
             long got = 0;
-            if (lane == 0) got = inflate_zlib(in + a, comp, dst, (long)want, &codes[w][0], &codes[w][1]);
+            // (32 KiB of window behind the item's original_length bytes when the stride has room for it)
+            const bool ring = out_stride >= (uint64_t)want + 32768u;
+            if (lane == 0) got = inflate_zlib(in + a, comp, dst, (long)want, ring, &codes[w][0], &codes[w][1]);
             got = __shfl_sync(FULL_MASK, (long long)got, 0);
             const uint32_t good = got < 0 ? 0u : (got < (long)want ? (uint32_t)got : want);
             __syncwarp();

@@ -78,11 +78,15 @@ __device__ inline int inf_construct(InfCode &h, const uint8_t *length, int n)
 // in[0 .. len) = a zlib stream.  Writes the first min(total, cap) decompressed bytes to out and returns the total
 // number of decompressed bytes, or -1 where zlib.decompress raises (bad header, invalid block, truncated stream,
 // Adler-32 mismatch).  Bytes behind the stream are ignored, as zlib.decompress ignores them.  One lane.
-// A stream that decompresses to more than cap bytes is walked to its end, but its bytes behind cap are not kept, so
-// matches reaching behind cap and the checksum cannot be verified for it (the reference's own packages never do
-// that: original_length is the decompressed length).
-__device__ inline long inflate_zlib(const uint8_t *in, long len, uint8_t *out, long cap, InfCode *lencode, InfCode *distcode)
+// A stream may decompress to more than cap bytes (the reference truncates, :88-89).  With ring == true, out has
+// 32768 more bytes behind cap that serve as the LZ77 window of the bytes behind cap, and the stream is checked to
+// its end like any other.  Without (the container path writes straight into the file's output, there is no room
+// behind a package), bytes behind cap are not kept, so matches reaching behind cap and the checksum cannot be
+// verified for such a stream (the reference's own packages never do that: original_length is the decompressed
+// length).
+__device__ inline long inflate_zlib(const uint8_t *in, long len, uint8_t *out, long cap, bool ring, InfCode *lencode, InfCode *distcode)
 {
+#define INF_AT(q) ((q) < cap ? (q) : cap + (((q) - cap) & 32767))
     if (len < 2) return -1;
     const uint32_t cmf = in[0], flg = in[1];
     if ((cmf & 15u) != 8u || (cmf >> 4) > 7u || ((cmf << 8) | flg) % 31u != 0u || (flg & 0x20u)) return -1;
@@ -103,7 +107,7 @@ __device__ inline long inflate_zlib(const uint8_t *in, long len, uint8_t *out, l
             if (b.pos + n > b.len) return -1;
             for (uint32_t k = 0; k < n; k++) {
                 const uint8_t v = in[b.pos++];
-                if (o < cap) out[o] = v;
+                if (o < cap || ring) out[INF_AT(o)] = v;
                 s1 += v; if (s1 >= ADLER_MOD) s1 -= ADLER_MOD;
                 s2 += s1; if (s2 >= ADLER_MOD) s2 -= ADLER_MOD;
                 o++;
@@ -154,7 +158,7 @@ __device__ inline long inflate_zlib(const uint8_t *in, long len, uint8_t *out, l
                 int sym = inf_symbol(b, *lencode);
                 if (sym < 0) return -1;
                 if (sym < 256) {
-                    if (o < cap) out[o] = (uint8_t)sym;
+                    if (o < cap || ring) out[INF_AT(o)] = (uint8_t)sym;
                     s1 += (uint32_t)sym; if (s1 >= ADLER_MOD) s1 -= ADLER_MOD;
                     s2 += s1; if (s2 >= ADLER_MOD) s2 -= ADLER_MOD;
                     o++;
@@ -168,8 +172,8 @@ __device__ inline long inflate_zlib(const uint8_t *in, long len, uint8_t *out, l
                     const long dist = c_dist_base[ds] + (long)inf_bits(b, c_dist_extra[ds]);
                     if (b.err || dist > o) return -1; // reaches before the start of the output
                     for (int k = 0; k < mlen; k++) {
-                        const uint8_t v = (o - dist < cap) ? out[o - dist] : 0;
-                        if (o < cap) out[o] = v;
+                        const uint8_t v = (o - dist < cap || ring) ? out[INF_AT(o - dist)] : 0;
+                        if (o < cap || ring) out[INF_AT(o)] = v;
                         s1 += v; if (s1 >= ADLER_MOD) s1 -= ADLER_MOD;
                         s2 += s1; if (s2 >= ADLER_MOD) s2 -= ADLER_MOD;
                         o++;
@@ -182,8 +186,9 @@ __device__ inline long inflate_zlib(const uint8_t *in, long len, uint8_t *out, l
     // Adler-32, big-endian, on the next byte boundary
     if (b.pos + 4 > b.len) return -1;
     const uint32_t want = ((uint32_t)in[b.pos] << 24) | ((uint32_t)in[b.pos + 1] << 16) | ((uint32_t)in[b.pos + 2] << 8) | in[b.pos + 3];
-    if (o <= cap && want != ((s2 << 16) | s1)) return -1;
+    if ((o <= cap || ring) && want != ((s2 << 16) | s1)) return -1;
     return o;
+#undef INF_AT
 }
 
 // ---- deflate ---------------------------------------------------------------------------------------------------

@@ -235,6 +235,8 @@ def codec_decode_batch(method, items, orig_lens):
         return []
     blob, offs = _pack_items(items)
     stride = (max(max(orig_lens), 1) + 512 + 15) & ~15
+    if method == L.DEFLATE:
+        stride += 32768  # window of a stream that runs past original_length (it is checked to its end, then truncated)
     t_in = to_device(blob)
     t_off = torch.from_numpy(offs.view(np.int64)).to("cuda")
     t_orig = torch.tensor(list(orig_lens), dtype=torch.int32, device="cuda")

@@ -108,3 +108,32 @@ def test_plugin_object_and_type5_packages(eng):
     dec, status = eng.decompress_device(t, n, known_mask=eng.method_mask([1, 2, 3, 4]))
     p0 = zlib.compress(chunks[0], 9)
     assert bytes(dec.cpu().numpy())[:len(p0)] == p0
+
+
+def test_gpu_inflate_mutated_streams_vs_zlib(eng):
+    """valid streams with a flipped byte, a cut or an inserted byte: whatever stock zlib does -- data, or an
+    exception that the reference turns into zeros (:93-97) -- the GPU inflater does the same"""
+    r = np.random.RandomState(909)
+    payloads, origs, want = [], [], []
+    kinds = sorted(inputs.KINDS)
+    for i in range(240):
+        d = inputs.make(kinds[i % len(kinds)], int(r.choice([200, 1500, 4096])), 12000 + i)
+        c = bytearray(zlib.compress(d, int(r.choice([1, 6, 9]))))
+        what = r.randint(3)
+        pos = int(r.randint(2, len(c)))
+        if what == 0:
+            c[pos] ^= 1 << int(r.randint(8))
+        elif what == 1:
+            del c[pos:]
+        else:
+            c.insert(pos, int(r.randint(256)))
+        c = bytes(c)
+        try:
+            out = zlib.decompress(c)
+            w = out[:len(d)].ljust(len(d), b"\0")
+        except zlib.error:
+            w = bytes(len(d))
+        payloads.append(c); origs.append(len(d)); want.append(w)
+    got = eng.codec_decode_batch(5, payloads, origs)
+    bad = [(i, len(payloads[i])) for i, (g, w) in enumerate(zip(got, want)) if g != w]
+    assert not bad, bad[:10]
