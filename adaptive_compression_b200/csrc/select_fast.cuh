@@ -1157,6 +1157,32 @@ template <int NMAX> __device__ inline void sf_lz_emit(SfCtx<NMAX> &c)
     __syncthreads();
 }
 
+// A lower bound of the Dictionary payload that needs no index and no parse.  Let D be the number of distinct
+// 4-grams of the chunk, i.e. of positions whose 4-gram has no earlier occurrence.  Inside a match token the 4-gram
+// of every position but the last three is a copy of an earlier one, so a first occurrence is covered by a literal
+// token (2 bytes) or by one of the last three bytes of a match token (4 bytes): D <= literals + 3 * matches, and
+// 2 * literals + 4 * matches >= 4 * D / 3.  (Trigrams give 2 * D3 the same way, g-grams 4 * Dg / (g - 1); on the
+// bench corpus g = 4 is the strongest: low-cardinality chunks 3 187 bytes against a Huffman payload of 1 599,
+// CSV 2 044 against 2 025.)  D is counted with a 17-bit hash set, which can only lose some: still a lower bound.
+// Uses region A (free between the Huffman build and the index).  Block-collective.
+template <int NMAX> __device__ inline int sf_lz_bound_4grams(SfCtx<NMAX> &c)
+{
+    uint32_t *bm = (uint32_t *)c.A; // 2^17 bits
+    static_assert(SfCfg<NMAX>::A_BYTES >= 16384, "4-gram hash set fits region A");
+    const int n = c.n, tid = threadIdx.x;
+    for (int i = tid; i < 1024; i += SF_T) ((uint4 *)bm)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    for (int p = tid; p < n - 3; p += SF_T) {
+        const uint32_t h = (sf_ldsu(c.sdb + p) * 2654435761u) >> 15;
+        atomicOr(&bm[h >> 5], 1u << (h & 31));
+    }
+    __syncthreads();
+    int cnt = 0;
+    for (int i = tid; i < 4096; i += SF_T) cnt += __popc(bm[i]);
+    const int D = sf_block_sum(cnt, c.red);
+    return (4 * D + 2) / 3;
+}
+
 // ---- the decision ------------------------------------------------------------------------------------
 struct SfOut { int type; int len; };
 
@@ -1233,11 +1259,15 @@ template <int NMAX> __device__ SfOut sf_select(SfCtx<NMAX> &c, uint32_t mask, in
             // the Dictionary payload wins iff it is < the RLE payload, <= the Huffman payload and beneficial
             int cutoff = min(best_len, n - ovh);
             if (hf_len != 0x7fffffff) cutoff = min(cutoff, hf_len + 1);
-            if (lz_min < cutoff) {
+            // many distinct trigrams and a Huffman payload in hand: the Dictionary payload usually loses clearly
+            const bool staged = hf_len != 0x7fffffff && 100 * st.distinct3 >= 34 * min(1000, n);
+            // ... and often provably, before any index or parse: 4/3 of the number of distinct 4-grams bounds the
+            // Dictionary payload from below (every low-cardinality chunk of the bench corpus, half of the CSV chunks)
+            bool hopeless = false;
+            if (lz_min < cutoff && staged) hopeless = sf_lz_bound_4grams(c) >= cutoff;
+            if (lz_min < cutoff && !hopeless) {
                 sf_lz_index(c);
                 SF_PH(4);
-                // many distinct trigrams and a Huffman payload in hand: the Dictionary payload usually loses clearly
-                const bool staged = hf_len != 0x7fffffff && 100 * st.distinct3 >= 34 * min(1000, n);
                 const int len = sf_lz_parse(c, cutoff, staged);
                 SF_PH(5);
                 if (len < cutoff) {
