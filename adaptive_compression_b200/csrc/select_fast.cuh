@@ -1157,19 +1157,26 @@ template <int NMAX> __device__ inline void sf_lz_emit(SfCtx<NMAX> &c)
     __syncthreads();
 }
 
-// A lower bound of the Dictionary payload that needs no index and no parse.  Let D be the number of distinct
-// 4-grams of the chunk, i.e. of positions whose 4-gram has no earlier occurrence.  Inside a match token the 4-gram
-// of every position but the last three is a copy of an earlier one, so a first occurrence is covered by a literal
-// token (2 bytes) or by one of the last three bytes of a match token (4 bytes): D <= literals + 3 * matches, and
-// 2 * literals + 4 * matches >= 4 * D / 3.  (Trigrams give 2 * D3 the same way, g-grams 4 * Dg / (g - 1); on the
-// bench corpus g = 4 is the strongest: low-cardinality chunks 3 187 bytes against a Huffman payload of 1 599,
-// CSV 2 044 against 2 025.)  D is counted with a 17-bit hash set, which can only lose some: still a lower bound.
-// Uses region A (free between the Huffman build and the index).  Block-collective.
-template <int NMAX> __device__ inline int sf_lz_bound_4grams(SfCtx<NMAX> &c)
+// A lower bound of the Dictionary payload that needs no index and no parse (tokens: a literal costs 2 bytes, a match
+// of >= 3 bytes 4 bytes, compression_methods.py:211-231).
+//   * Let D be the number of distinct 4-grams of the chunk, i.e. of positions whose 4-gram has no earlier
+//     occurrence ("first" positions).  Inside a match the 4-gram of every position but the last three is a copy of
+//     an earlier one, so a first position is covered by a literal or by one of the last three bytes of a match.
+//   * Let F be the number of positions p whose trigram and the trigrams at p - 1 and p - 2 all occur for the first
+//     time.  Such a position is a literal in every parse: a match that covers p would contain the whole trigram
+//     at p, at p - 1 or at p - 2.  These positions are first positions of their 4-gram as well.
+//   Hence D - F <= other literals + 3 * matches, and the payload is at least 2 F + 4/3 (D - F) = (4 D + 2 F) / 3.
+// On the bench corpus: low-cardinality chunks 3 187 bytes from D alone (Huffman payload 1 599), CSV 2 038 + 196
+// (Huffman 2 037), text 772 + 107 (Huffman 2 043: no help there).  D is counted with a 17-bit hash set and the
+// first trigram positions come from a 12-bit hash table of minimum positions; both can only lose some, and the
+// bound grows with D and F.  `need`: the bound is only compared with this value (F is skipped when D suffices).
+// Uses region A and the first words of the ord / payload area (free between the Huffman build and the index).
+// Block-collective.
+template <int NMAX> __device__ inline int sf_lz_bound_ngrams(SfCtx<NMAX> &c, int need)
 {
+    static_assert(SfCfg<NMAX>::A_BYTES >= 16384, "hash set / table fit region A");
+    const int n = c.n, tid = threadIdx.x, lane = tid & 31;
     uint32_t *bm = (uint32_t *)c.A; // 2^17 bits
-    static_assert(SfCfg<NMAX>::A_BYTES >= 16384, "4-gram hash set fits region A");
-    const int n = c.n, tid = threadIdx.x;
     for (int i = tid; i < 1024; i += SF_T) ((uint4 *)bm)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     for (int p = tid; p < n - 3; p += SF_T) {
@@ -1180,7 +1187,33 @@ template <int NMAX> __device__ inline int sf_lz_bound_4grams(SfCtx<NMAX> &c)
     int cnt = 0;
     for (int i = tid; i < 4096; i += SF_T) cnt += __popc(bm[i]);
     const int D = sf_block_sum(cnt, c.red);
-    return (4 * D + 2) / 3;
+    if ((4 * D) / 3 >= need) return (4 * D) / 3;
+    // first position per trigram hash, then the bitmap of first positions
+    uint32_t *fo = (uint32_t *)c.A;          // 4096 entries
+    uint32_t *fw = (uint32_t *)c.ord;        // NMAX / 32 words
+    __syncthreads();
+    for (int i = tid; i < 1024; i += SF_T) ((uint4 *)fo)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    __syncthreads();
+    for (int p = tid; p < n - 2; p += SF_T)
+        atomicMin(&fo[((sf_ldsu(c.sdb + p) & 0xFFFFFFu) * 2654435761u) >> 20], (uint32_t)p);
+    __syncthreads();
+    for (int p0 = 32 * (tid >> 5); p0 < n; p0 += SF_T) { // a warp per 32 positions
+        const int p = p0 + lane;
+        bool first = false;
+        if (p < n - 2) first = fo[((sf_ldsu(c.sdb + p) & 0xFFFFFFu) * 2654435761u) >> 20] == (uint32_t)p;
+        const uint32_t w = __ballot_sync(FULL_MASK, first);
+        if (lane == 0) fw[p0 >> 5] = w;
+    }
+    __syncthreads();
+    int forced = 0;
+    for (int wd = tid; 32 * wd < n - 3; wd += SF_T) {
+        const uint32_t f = fw[wd], fp = wd ? fw[wd - 1] : 0u;
+        uint32_t z = f & ((f << 1) | (fp >> 31)) & ((f << 2) | (fp >> 30));
+        if (n - 3 < 32 * wd + 32) z &= 0xFFFFFFFFu >> (32 * wd + 32 - (n - 3)); // positions with a 4-gram only
+        forced += __popc(z);
+    }
+    const int F = sf_block_sum(forced, c.red);
+    return (4 * D + 2 * F) / 3;
 }
 
 // ---- the decision ------------------------------------------------------------------------------------
@@ -1261,10 +1294,10 @@ template <int NMAX> __device__ SfOut sf_select(SfCtx<NMAX> &c, uint32_t mask, in
             if (hf_len != 0x7fffffff) cutoff = min(cutoff, hf_len + 1);
             // many distinct trigrams and a Huffman payload in hand: the Dictionary payload usually loses clearly
             const bool staged = hf_len != 0x7fffffff && 100 * st.distinct3 >= 34 * min(1000, n);
-            // ... and often provably, before any index or parse: 4/3 of the number of distinct 4-grams bounds the
-            // Dictionary payload from below (every low-cardinality chunk of the bench corpus, half of the CSV chunks)
+            // ... and often provably, before any index or parse (sf_lz_bound_ngrams: every low-cardinality and CSV chunk
+            // of the bench corpus)
             bool hopeless = false;
-            if (lz_min < cutoff && staged) hopeless = sf_lz_bound_4grams(c) >= cutoff;
+            if (lz_min < cutoff && staged) hopeless = sf_lz_bound_ngrams(c, cutoff) >= cutoff;
             if (lz_min < cutoff && !hopeless) {
                 sf_lz_index(c);
                 SF_PH(4);
